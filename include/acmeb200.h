@@ -1,0 +1,201 @@
+/*
+ * acmeb200.h -- C ABI of the B200-native batched DK-method runtime.
+ *
+ * The reference (HSU-ANT/ACME.jl) has no FFI seam: it is pure Julia and its hot
+ * path is the method
+ *     run!(runner::ModelRunner{<:DiscreteModel,false}, y, u)   src/ACME.jl:658-664
+ * which calls step! (src/ACME.jl:666-715) per sample, which in turn calls
+ *     solve(model.solvers[idx], p)                               src/ACME.jl:687
+ * on a HomotopySolver{CachingSolver{SimpleSolver}} (src/solvers.jl:207-236,
+ * 268-296, 347-396) backed by a KDTree (src/kdtree.jl:192-234).
+ * This header is what a Julia `ccall` binding for that path would bind; the
+ * binding itself (julia/ACMEB200.jl) is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *  - every matrix is Float64, column-major, exactly the Julia `Matrix{Float64}`
+ *    memory of the corresponding DiscreteModel field (src/ACME.jl:118-137);
+ *  - an `acmeb200_array` may be shared by all instances (stride 0) or hold one
+ *    copy per instance (`stride` = distance in doubles between instances);
+ *  - the non-linear element closures of the reference (src/elements.jl) cannot
+ *    cross a C ABI, so each sub-problem carries an element table instead
+ *    (kind + q offset + parameters), in the order of CircuitNLFunc
+ *    (src/circuit.jl:68-86);
+ *  - all functions return 0 on success or a negative ACMEB200_E* code; the
+ *    message is available from acmeb200_last_error() (thread local);
+ *  - numerical failure is not an error: it is reported per instance in the
+ *    status words (mirrors the @warn / error() of src/ACME.jl:688-694).
+ *  - threading: one host thread per model handle at a time; the library never
+ *    calls back into the host runtime.
+ */
+#ifndef ACMEB200_H
+#define ACMEB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ACMEB200_ABI_VERSION 1
+
+/* error codes */
+#define ACMEB200_OK           0
+#define ACMEB200_EINVAL      -1  /* bad argument / inconsistent descriptor  */
+#define ACMEB200_ECUDA       -2  /* CUDA runtime error (see last_error)      */
+#define ACMEB200_ENOMEM      -3
+#define ACMEB200_EUNSUPPORTED -4 /* dimensions beyond what the kernels hold  */
+#define ACMEB200_ENODEVICE   -5  /* no CUDA device: there is no CPU fallback */
+
+/* element kinds and their parameter layouts (all Float64)
+ *  DIODE       src/elements.jl:236-245  {is, eta}                               nq=2 nn=1
+ *  BJT         src/elements.jl:309-406  {ise, isc, eta_e, eta_c, beta_f, beta_r,
+ *                                        ile, ilc, eta_el, eta_cl, vaf, var, ikf, ikr}
+ *                                                                               nq=4 nn=2
+ *  POT         src/elements.jl:20-31    {r}                                     nq=5 nn=2
+ *  MOSFET      src/elements.jl:436-481  {polarity, lambda, n_vt, n_alpha,
+ *                                        vt[4], alpha[4]}                       nq=3 nn=1
+ *  OPAMP_TANH  src/elements.jl:536-551  {gain, scale}                           nq=2 nn=1
+ *  JA          src/elements.jl:104-135  {Ms, a, alpha, c, k}                    nq=4 nn=1
+ *  TEST_QUAD   test/runtests.jl:207-219 (res = q1^2 - 1 + q2), no parameters    nq=2 nn=1
+ */
+#define ACMEB200_ELEM_DIODE       1
+#define ACMEB200_ELEM_BJT         2
+#define ACMEB200_ELEM_POT         3
+#define ACMEB200_ELEM_MOSFET      4
+#define ACMEB200_ELEM_OPAMP_TANH  5
+#define ACMEB200_ELEM_JA          6
+#define ACMEB200_ELEM_TEST_QUAD 100
+
+/* solver selection; the reference default is HOMOTOPY_CACHING
+ * (src/ACME.jl:150).  On the device the cache is a frozen, host-built k-d tree
+ * (read-only lookup, src/solvers.jl:347-371); dynamic insertion
+ * (src/solvers.jl:374-394) is not performed on the device. */
+#define ACMEB200_SOLVER_SIMPLE            0 /* SimpleSolver                          */
+#define ACMEB200_SOLVER_HOMOTOPY          1 /* HomotopySolver{SimpleSolver}          */
+#define ACMEB200_SOLVER_HOMOTOPY_CACHING  2 /* HomotopySolver{CachingSolver{Simple}} */
+
+/* per-instance status bits (src/ACME.jl:688-694) */
+#define ACMEB200_STATUS_NOT_CONVERGED 1u /* "Failed to converge while solving non-linear equation." */
+#define ACMEB200_STATUS_NONFINITE     2u /* "... got non-finite result." -- instance halted        */
+
+/* run flags */
+#define ACMEB200_U_DEVICE 1u /* U is a device pointer (else host)  */
+#define ACMEB200_Y_DEVICE 2u /* Y is a device pointer (else host)  */
+
+#define ACMEB200_HIST_BINS 32 /* iteration histogram: bins 1..31, last bin = 32 and more */
+
+typedef struct acmeb200_array {
+    const double *ptr;
+    int64_t       stride; /* doubles between consecutive instances; 0 = shared */
+} acmeb200_array;
+
+typedef struct acmeb200_elem {
+    int32_t kind;         /* ACMEB200_ELEM_*                                   */
+    int32_t q_offset;     /* first q index of this element within the sub      */
+    int32_t param_offset; /* first parameter within the sub's parameter vector */
+    int32_t nparam;
+} acmeb200_elem;
+
+/* frozen solution cache of one sub-problem: the fields of KDTree
+ * (src/kdtree.jl:4-9) + CachingSolver.zs (src/solvers.jl:321-323);
+ * indices are 1-based as in the reference.  n_points == 0: no cache. */
+typedef struct acmeb200_cache {
+    int32_t        n_points;
+    int32_t        n_columns; /* columns of ps/zs (>= every index in ps_idx)   */
+    const int32_t *cut_dim;   /* n_points-1                                    */
+    const double  *cut_val;   /* n_points-1                                    */
+    const int32_t *ps_idx;    /* n_points                                      */
+    const double  *ps;        /* np x n_columns, column-major                  */
+    const double  *zs;        /* nn x n_columns, column-major                  */
+} acmeb200_cache;
+
+typedef struct acmeb200_sub_desc {
+    int32_t nn, nq, np, nelem;
+    acmeb200_array dq;      /* np x nx        model.dqs[i]      ACME.jl:124 */
+    acmeb200_array eq;      /* np x nu        model.eqs[i]      ACME.jl:125 */
+    acmeb200_array fqprev;  /* np x nn_total  model.fqprevs[i]  ACME.jl:126 */
+    acmeb200_array pexp;    /* nq x np        model.pexps[i]    ACME.jl:123 */
+    acmeb200_array q0;      /* nq             model.q0s[i]      ACME.jl:128 */
+    acmeb200_array fq;      /* nq x nn        model.fqs[i]      ACME.jl:127 */
+    acmeb200_array init_z;  /* nn   initial solution at p = 0   ACME.jl:259 */
+    const acmeb200_elem *elems; /* nelem entries                              */
+    acmeb200_array params;  /* nparams element parameters (per instance for sweeps) */
+    int32_t nparams;
+    int32_t reserved;
+    acmeb200_cache cache;
+} acmeb200_sub_desc;
+
+typedef struct acmeb200_model_desc {
+    int32_t abi_version; /* ACMEB200_ABI_VERSION */
+    int32_t nx, nu, ny, nsub;
+    int32_t solver;      /* ACMEB200_SOLVER_*                                  */
+    int32_t maxiter;     /* 0 -> 500 (src/solvers.jl:207)                      */
+    int32_t reserved;
+    double  tol;         /* 0 -> 1e-10 (src/solvers.jl:175)                    */
+    acmeb200_array a;    /* nx x nx        ACME.jl:119 */
+    acmeb200_array b;    /* nx x nu        ACME.jl:120 */
+    acmeb200_array c;    /* nx x nn_total  ACME.jl:121 */
+    acmeb200_array x0;   /* nx             ACME.jl:122 */
+    acmeb200_array dy;   /* ny x nx        ACME.jl:129 */
+    acmeb200_array ey;   /* ny x nu        ACME.jl:130 */
+    acmeb200_array fy;   /* ny x nn_total  ACME.jl:131 */
+    acmeb200_array y0;   /* ny             ACME.jl:132 */
+    const acmeb200_sub_desc *subs; /* nsub entries, in solve order            */
+} acmeb200_model_desc;
+
+typedef struct acmeb200_stats {
+    uint64_t samples;                        /* instance-samples processed since reset      */
+    uint64_t solves;                         /* sub-problem solves                          */
+    uint64_t newton_iters;                   /* function evaluations (needediterations)     */
+    uint64_t homotopy_solves;                /* solves that entered the homotopy loop       */
+    uint64_t not_converged;                  /* solves that failed (finite)                 */
+    uint64_t iter_hist[ACMEB200_HIST_BINS];  /* per-solve iteration histogram               */
+} acmeb200_stats;
+
+typedef struct acmeb200_model acmeb200_model; /* opaque; owns all device memory */
+
+/* Create the device-resident model for instances [first_instance,
+ * first_instance + n_instances) of the descriptor, on the current CUDA device.
+ * Descriptor arrays are host pointers and are copied; nothing is retained.
+ * Per-instance state (x = 0, extrapolation origin at (p = 0, init_z):
+ * src/solvers.jl:164-178, ACME.jl:145) is initialised on the device. */
+int acmeb200_model_create(const acmeb200_model_desc *desc, int64_t first_instance,
+                          int64_t n_instances, acmeb200_model **out);
+void acmeb200_model_destroy(acmeb200_model *m);
+
+/* run!(runner, y, u) for every instance (src/ACME.jl:658-664).
+ * U: (nu, N, B) column-major, i.e. instance b's block is the reference's nu x N
+ * matrix at U + b*u_stride (u_stride == 0: one input shared by all instances).
+ * Y: (ny, N, B), instance b at Y + b*y_stride (y_stride == 0 -> ny*N).
+ * State (x, extrapolation origins) persists across calls (src/ACME.jl:561-562).
+ * `stream` is a cudaStream_t (NULL = default stream).  With device pointers the
+ * call is asynchronous on `stream`; with host pointers it stages through pinned
+ * buffers and returns when Y is complete. */
+int acmeb200_run(acmeb200_model *m, const double *U, int64_t u_stride, double *Y,
+                 int64_t y_stride, int64_t n_samples, uint32_t flags, void *stream);
+
+/* model.x (nx x B, column-major) */
+int acmeb200_get_state(acmeb200_model *m, double *x_host);
+int acmeb200_set_state(acmeb200_model *m, const double *x_host, int64_t stride);
+/* x = 0 and extrapolation origins back to (0, init_z); clears stats/status */
+int acmeb200_reset(acmeb200_model *m);
+
+/* status words (one uint32 per instance) and the first failing sample index
+ * (int64 per instance, -1 if none); either pointer may be NULL */
+int acmeb200_get_status(acmeb200_model *m, uint32_t *status_host, int64_t *first_fail_host);
+int acmeb200_get_stats(acmeb200_model *m, acmeb200_stats *out);
+
+/* kernel selection: 0 = automatic, 1 = force the generic (runtime-dimension)
+ * kernel; returns the name of the kernel the next run will launch */
+int acmeb200_set_kernel(acmeb200_model *m, int32_t mode);
+const char *acmeb200_kernel_name(const acmeb200_model *m);
+/* number of kernels launched by this model since creation */
+int64_t acmeb200_launch_count(const acmeb200_model *m);
+
+const char *acmeb200_last_error(void);
+int acmeb200_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ACMEB200_H */

@@ -1,0 +1,159 @@
+"""Test circuits shared by the oracle tests (CPU) and the CUDA parity tests (GPU).
+
+Each builder mirrors a circuit of the reference's test suite
+(/root/reference/test/runtests.jl, line numbers in the docstrings).
+"""
+import math
+
+import numpy as np
+
+import acme_jl_b200 as A
+from acme_jl_b200 import (bjt, capacitor, circuit, currentprobe, currentsource, diode, mosfet,
+                          opamp, resistor, voltageprobe, voltagesource)
+
+
+def sine(n=44100, f=1000.0, fs=44100.0):
+    """``sin.(2π*1000/44100*(0:44099)')`` (runtests.jl:689, 700)"""
+    return np.sin(2 * np.pi * f / fs * np.arange(n)).reshape(1, -1)
+
+
+def rc_ladder():
+    """docs/src/ug.md:40-56: cascade of 20 RC low-passes"""
+    c = circuit([("src", voltagesource(), {"-": "gnd"}), ("output", voltageprobe(), {"-": "gnd"})])
+    pin = ("src", "+")
+    for _ in range(20):
+        r = c.add(resistor(1000))
+        k = c.add(capacitor(10e-9))
+        c.connect((r, "1"), pin)
+        c.connect((r, "2"), (k, "1"))
+        c.connect((k, "2"), "gnd")
+        pin = (r, "2")
+    c.connect(pin, ("output", "+"))
+    return c
+
+
+def resistor_diode():
+    """runtests.jl:68-86"""
+    i, r, is_ = 1e-3, 10e3, 1e-12
+    v_r = i * r
+    v_d = 25e-3 * math.log(i / is_ + 1)
+    c = circuit([
+        ("vsrc", voltagesource(v_r + v_d), {"+": "supply voltage", "-": "gnd"}),
+        ("r1", resistor(r), {}),
+        ("d", diode(is_=is_), {"-": "gnd", "+": ("r1", "2")}),
+        ("vprobe", voltageprobe(), {"-": "gnd", "+": ("r1", "2")}),
+    ])
+    c.connect(("r1", "1"), "supply voltage")
+    return c, v_d
+
+
+def no_solution():
+    """runtests.jl:170-183: diode driven by a current source"""
+    return circuit([
+        ("d", diode(), {}),
+        ("src", currentsource(), {"+": ("d", "+"), "-": ("d", "-")}),
+        ("probe", voltageprobe(), {"+": ("d", "+"), "-": ("d", "-")}),
+    ])
+
+
+def three_diodes():
+    """runtests.jl:267-279"""
+    c = circuit([
+        ("src1", voltagesource(), {}),
+        ("probe1", currentprobe(), {}),
+        ("d1", diode(), {"+": ("src1", "+")}),
+        ("d2", diode(), {"+": ("d1", "-"), "-": ("probe1", "+")}),
+    ])
+    c.connect(("probe1", "-"), ("src1", "-"))
+    c.add("src2", voltagesource())
+    c.add("probe2", currentprobe())
+    c.add("d3", diode())
+    c.connect(("src2", "+"), ("d3", "+"))
+    c.connect(("d3", "-"), ("probe2", "+"))
+    c.connect(("probe2", "-"), ("src2", "-"))
+    return c
+
+
+BJT_BASE = dict(isc=1e-6, ise=2e-6, ηc=1.1, ηe=1.0, βf=100, βr=10)
+
+
+def bjt_circuit(typ, **kw):
+    """runtests.jl:490-498 / 518-527"""
+    params = dict(BJT_BASE)
+    params.update(kw)
+    return circuit([
+        ("t", bjt(typ, **params), {}),
+        ("isrc", currentsource(), {"+": ("t", "base")}),
+        ("vsrc", voltagesource(), {"-": ("isrc", "-")}),
+        ("veprobe", voltageprobe(), {"+": ("t", "base"), "-": ("isrc", "-")}),
+        ("vcprobe", voltageprobe(), {"+": ("t", "base"), "-": ("vsrc", "+")}),
+        ("ieprobe", currentprobe(), {"+": ("t", "emitter"), "-": ("isrc", "-")}),
+        ("icprobe", currentprobe(), {"+": ("t", "collector"), "-": ("vsrc", "+")}),
+    ])
+
+
+def bjt_input(typ, N=100):
+    """runtests.jl:501"""
+    ib = 1e-3 if typ == "npn" else -1e-3
+    return np.vstack([np.linspace(0, ib, N),
+                      np.concatenate([np.linspace(1, -1, N // 2), np.linspace(-1, 1, N // 2)])])
+
+
+def bjt_expected(out, ile=0, ilc=0, ηcl=None, ηel=None, vaf=math.inf, var=math.inf,
+                 ikf=math.inf, ikr=math.inf):
+    """closed form of runtests.jl:535-543; returns (ie, ic) for measured (ve, vc)"""
+    isc, ise, ηc, ηe, βf, βr = (BJT_BASE[k] for k in ("isc", "ise", "ηc", "ηe", "βf", "βr"))
+    ηcl = ηc if ηcl is None else ηcl
+    ηel = ηe if ηel is None else ηel
+    ve, vc = out[0], out[1]
+    i_f = βf / (1 + βf) * ise * (np.exp(ve / (ηe * 25e-3)) - 1)
+    i_r = βr / (1 + βr) * isc * (np.exp(vc / (ηc * 25e-3)) - 1)
+    icc = (2 * (1 - ve / var - vc / vaf)) / (1 + np.sqrt(1 + 4 * (i_f / ikf + i_r / ikr))) * (i_f - i_r)
+    ibe = 1 / βf * i_f + ile * (np.exp(ve / (ηel * 25e-3)) - 1)
+    ibc = 1 / βr * i_r + ilc * (np.exp(vc / (ηcl * 25e-3)) - 1)
+    return icc + ibe, -icc + ibc
+
+
+def mosfet_circuit(typ, **kw):
+    """runtests.jl:592-597"""
+    return circuit([
+        ("vgs", voltagesource(), {"-": "gnd"}),
+        ("vds", voltagesource(), {"-": "gnd"}),
+        ("J", mosfet(typ, **kw), {"gate": ("vgs", "+"), "drain": ("vds", "+")}),
+        ("out", currentprobe(), {"+": ("J", "source"), "-": "gnd"}),
+    ])
+
+
+def opamp_shelving(Amax, GBP):
+    """runtests.jl:629-636"""
+    return circuit([
+        ("input", voltagesource(), {"-": "gnd"}),
+        ("op", opamp(maxgain=Amax, gain_bw_prod=GBP), {"in+": ("input", "+"), "out-": "gnd"}),
+        ("r1", resistor(109e3), {"1": ("op", "out+"), "2": ("op", "in-")}),
+        ("r2", resistor(1e3), {"1": ("op", "in-")}),
+        ("c", capacitor(22e-9), {"1": ("r2", "2"), "2": "gnd"}),
+        ("output", voltageprobe(), {"+": ("op", "out+"), "-": "gnd"}),
+    ])
+
+
+def opamp_tanh():
+    """runtests.jl:652-656"""
+    return circuit([
+        ("input", voltagesource(), {"-": "gnd"}),
+        ("op", opamp("macak", 100, -3, 4), {"in+": ("input", "+"), "in-": [("op", "out-"), "gnd"]}),
+        ("output", voltageprobe(), {"+": ("op", "out+"), "-": "gnd"}),
+    ])
+
+
+def test_quad_model(p0=0.0, z0=1.0):
+    """The scalar equation z^2 - 1 + p = 0 of runtests.jl:207-219 as a one-sub
+    model: q = [z; p], u = p, y = z."""
+    from acme_jl_b200.elements import NLElem
+    from acme_jl_b200.model import DiscreteModel, SubProblem
+    sub = SubProblem(nn=1, nq=2, np_=1,
+                     dq=np.zeros((1, 0)), eq=np.ones((1, 1)), fqprev=np.zeros((1, 1)),
+                     pexp=np.array([[0.0], [1.0]]), q0=np.zeros(2), fq=np.array([[1.0], [0.0]]),
+                     init_z=np.array([z0]), elems=[(NLElem(100, (), 2, 1), 0)])
+    return DiscreteModel.from_matrices(a=np.zeros((0, 0)), b=np.zeros((0, 1)), c=np.zeros((0, 1)), x0=np.zeros(0),
+                                       dy=np.zeros((1, 0)), ey=np.zeros((1, 1)), fy=np.ones((1, 1)), y0=np.zeros(1),
+                                       subs=[sub], solver="HomotopySolver{SimpleSolver}")

@@ -1,0 +1,283 @@
+"""Pins the CPU oracle (oracle/acme_oracle.c) against every golden vector and
+known-answer test the reference holds for the run! path:
+G1/G2 doctest vectors and K1-K9 of /root/reference/test/runtests.jl."""
+import math
+
+import numpy as np
+import pytest
+
+import acme_jl_b200 as A
+from acme_jl_b200 import examples as ex
+from oracle import oracle
+from oracle.oracle import OracleModel
+
+import cases
+
+SOLVERS = ["HomotopySolver{CachingSolver{SimpleSolver}}", "HomotopySolver{SimpleSolver}"]
+
+
+def run(model, u, **kw):
+    return OracleModel(model, 1, **kw).run(np.asarray(u, dtype=float))[:, :, 0]
+
+
+@pytest.mark.parametrize("solver", SOLVERS)
+def test_G1_diodeclipper_doctest(solver):
+    """docs/src/gettingstarted.md:106-113"""
+    y = run(ex.diodeclipper(), cases.sine(), solver=solver)
+    assert y.shape == (1, 44100)
+    assert y[0, 0] == 0.0
+    for got, want in zip(y[0, 1:4], (0.0275964, 0.0990996, 0.195777)):
+        assert f"{got:.6g}" == f"{want:.6g}"
+    for got, want in zip(y[0, -3:], (-0.537508, -0.462978, -0.36521)):
+        assert f"{got:.6g}" == f"{want:.6g}"
+
+
+def test_G2_rc_ladder_doctest():
+    """docs/src/ug.md:107-114"""
+    m = A.DiscreteModel(cases.rc_ladder(), 1 / 44100)
+    u = np.zeros((1, 100)); u[0, 0] = 1
+    y = run(m, u)
+    for got, want in zip(y[0, :3], (1.83357e-8, 3.1622e-7, 2.59861e-6)):
+        assert f"{got:.6g}" == f"{want:.6g}"
+    for got, want in zip(y[0, -3:], (0.00465423, 0.00459275, 0.00453208)):
+        assert f"{got:.6g}" == f"{want:.6g}"
+
+
+def test_K1_linearsolver():
+    """runtests.jl:23-41"""
+    Amat = np.array([[1.0, 0.5, 0.4], [2.0, 4.0, 1.7], [4.0, 7.0, 9.1]])
+    rng = np.random.default_rng(1)
+    x = rng.random(3)
+    ok, y = oracle.linsolve(Amat, x)
+    assert ok and np.allclose(Amat @ y, x)
+    ok, _ = oracle.linsolve(np.zeros((3, 3)), x)
+    assert not ok
+
+
+@pytest.mark.parametrize("num", list(range(1, 51)))
+def test_K2_kdtree_self(num):
+    """runtests.jl:187-195"""
+    ps = np.random.default_rng(num).random((4, num))
+    idx = oracle.kdtree_query(ps, ps)
+    assert (ps[:, idx - 1] == ps).all()
+
+
+def test_K2_kdtree_bruteforce():
+    """runtests.jl:197-204 (100 queries instead of one)"""
+    rng = np.random.default_rng(7)
+    ps = rng.random((6, 10000))
+    qs = rng.random((6, 100))
+    idx = oracle.kdtree_query(ps, qs)
+    for k in range(qs.shape[1]):
+        d = ((ps - qs[:, k:k + 1]) ** 2).sum(axis=0)
+        assert np.isclose(d.min(), d[idx[k] - 1])
+
+
+def test_K3_homotopy():
+    """runtests.jl:207-219: z^2 - 1 + p from z0 = 1"""
+    rng = np.random.default_rng(3)
+    for _ in range(20):
+        o = OracleModel(cases.test_quad_model())
+        z, conv, _ = o.solve_sub([-0.5 + rng.random()])
+        assert conv and abs(z[0] ** 2 - 1 + 0) < 2  # converged to a root
+        z, conv, _ = o.solve_sub([1.5 + rng.random()])
+        assert not conv
+
+
+def test_K4_resistor_diode():
+    """runtests.jl:68-86"""
+    c, v_d = cases.resistor_diode()
+    y = run(A.DiscreteModel(c, 1), np.zeros((0, 1)))
+    assert np.isclose(y[0, 0], v_d)
+
+
+def test_empty_circuits():
+    """runtests.jl:54-66"""
+    m = A.DiscreteModel(A.circuit([]), 1)
+    assert run(m, np.zeros((0, 20))).shape == (0, 20)
+    c = A.circuit([("r", A.resistor(0), {"1": ("r", "2")})])
+    assert run(A.DiscreteModel(c, 1), np.zeros((0, 20))).shape == (0, 20)
+
+
+def test_K5_failure_semantics():
+    """runtests.jl:170-183"""
+    m = A.DiscreteModel(cases.no_solution(), 1)
+    assert m.nn() == 1
+    o = OracleModel(m)
+    y = o.run(np.array([[1.0, 1.0]]))
+    assert y.shape == (1, 2, 1) and y[0, 0, 0] == y[0, 1, 0]
+    assert o.status()[0][0] == 0
+    o = OracleModel(m)
+    o.run(np.array([[np.inf]]))
+    assert o.status()[0][0] & 2          # error("... got non-finite result.")
+    o = OracleModel(m)
+    y = o.run(np.array([[-1.0]]))
+    assert y.shape == (1, 1, 1)
+    st, ff = o.status()
+    assert st[0] == 1 and ff[0] == 0     # @warn "Failed to converge ..."
+
+
+def test_K6_decomposition():
+    """runtests.jl:267-292"""
+    c = cases.three_diodes()
+    want = 1e-12 * (math.exp(1 / 25e-3) - 1)
+    for dec in (False, True):
+        y = run(A.DiscreteModel(c, 1, decompose_nonlinearity=dec), np.array([[2.0], [1.0]]))
+        assert np.isclose(y[0, 0], want) and np.isclose(y[1, 0], want)
+
+
+@pytest.mark.parametrize("typ", ["npn", "pnp"])
+def test_K7_bjt_ebers_moll(typ):
+    """runtests.jl:489-509"""
+    m = A.DiscreteModel(cases.bjt_circuit(typ), 1)
+    out = run(m, cases.bjt_input(typ))
+    if typ == "pnp":
+        out = -out
+    ie, ic = cases.bjt_expected(out)
+    assert np.allclose(out[2], ie, rtol=0, atol=1e-10)
+    assert np.allclose(out[3], ic, rtol=0, atol=1e-10)
+
+
+GP = [dict(ile=ile, ilc=ilc, ηcl=ηcl, ηel=ηel, vaf=vaf, var=var, ikf=ikf, ikr=ikr)
+      for ile in (0, 50e-9) for ilc in (0, 100e-9) for ηcl in (1.1, 1.2) for ηel in (1.0, 1.1)
+      for vaf in (math.inf, 10) for var in (math.inf, 50) for ikf in (math.inf, 50e-3)
+      for ikr in (math.inf, 500e-3)]
+
+
+@pytest.mark.parametrize("typ", ["npn", "pnp"])
+@pytest.mark.parametrize("chunk", range(16))
+def test_K7_bjt_gummel_poon(typ, chunk):
+    """runtests.jl:513-546: all 2^8 parameter combinations x npn/pnp"""
+    for kw in GP[chunk::16]:
+        m = A.DiscreteModel(cases.bjt_circuit(typ, **kw), 1)
+        out = run(m, cases.bjt_input(typ))
+        if typ == "pnp":
+            out = -out
+        ie, ic = cases.bjt_expected(out, **kw)
+        assert np.allclose(out[2], ie, rtol=0, atol=1e-10), kw
+        assert np.allclose(out[3], ic, rtol=0, atol=1e-10), kw
+
+
+@pytest.mark.parametrize("typ,pol", [("n", 1), ("p", -1)])
+def test_K8_mosfet_exact(typ, pol):
+    """runtests.jl:591-601"""
+    m = A.DiscreteModel(cases.mosfet_circuit(typ, vt=1, α=1e-4), 1)
+    y = run(m, pol * np.array([[0, 1, 2, 2, 2], [5, 5, 0.5, 1, 1.5]]))
+    want = pol * np.array([0, 0, 1e-4 * (1 - 0.5 / 2) * 0.5, 1e-4 * (1 - 1 / 2) * 1, 1e-4 / 2 * 1 ** 2])
+    assert (y[0] == want).all()
+
+
+@pytest.mark.parametrize("typ,pol", [("n", 1), ("p", -1)])
+@pytest.mark.parametrize("α", [1e-4, (0.0205, -0.0017)])
+@pytest.mark.parametrize("vt", [1, (1.2078, 0.3238), (-1.2454, -0.199, -0.0483)])
+def test_K8_mosfet_grid(typ, pol, α, vt):
+    """runtests.jl:602-623"""
+    m = A.DiscreteModel(cases.mosfet_circuit(typ, vt=vt, α=α, λ=0.05), 1)
+    o = OracleModel(m)
+    ev = lambda x, c: sum(ci * x ** i for i, ci in enumerate(c if isinstance(c, tuple) else (c,)))
+    for vgs in np.linspace(0, 5, 10):
+        for vds in np.linspace(0, 5, 10):
+            y = o.run(pol * np.array([[vgs], [vds]]))[0, 0, 0]
+            a_, vt_ = ev(pol * vgs, α), ev(pol * vgs, vt)
+            if vgs <= vt_:
+                assert y == 0
+            elif vds <= vgs - vt_:
+                assert np.isclose(y, pol * a_ * (vgs - vt_ - vds / 2) * vds * (1 + 0.05 * vds))
+            else:
+                assert np.isclose(y, pol * a_ / 2 * (vgs - vt_) ** 2 * (1 + 0.05 * vds))
+
+
+@pytest.mark.parametrize("Amax", [10, math.inf])
+@pytest.mark.parametrize("GBP", [50e3, math.inf])
+def test_K9_opamp_linear(Amax, GBP):
+    """runtests.jl:627-649"""
+    m = A.DiscreteModel(cases.opamp_shelving(Amax, GBP), 1 / 44100)
+    u = np.zeros((1, 4096)); u[0, 0] = 1
+    y = run(m, u)[0]
+    Y = np.fft.rfft(y)
+    k = np.arange(len(Y))
+    with np.errstate(divide="ignore", invalid="ignore"):
+        w = 2 * 44100 * np.tan(np.pi * k / len(y))
+        s = 1j * w
+        Ginv = math.sqrt(1 - 1 / Amax ** 2) * s / (2 * math.pi * GBP) + 1 / Amax
+        H = (1e3 * 22e-9 * s + 1) / ((109e3 + 1e3) * 22e-9 * s + 1)
+        Yref = 1 / (Ginv + H)
+    ok = np.isfinite(Yref)
+    assert ok.sum() >= len(Y) - 1
+    assert np.allclose(Y[ok], Yref[ok])
+
+
+def test_K9_opamp_tanh():
+    """runtests.jl:651-661"""
+    m = A.DiscreteModel(cases.opamp_tanh(), 1 / 44100)
+    u = np.linspace(-1, 1, 1000)
+    y = run(m, u.reshape(1, -1))[0]
+    yref = 0.5 * (4 + -3) + 0.5 * (4 - -3) * np.tanh(100 / (0.5 * (4 - -3)) * u)
+    assert np.allclose(y, yref)
+
+
+def checksteady(model):
+    """runtests.jl:664-671"""
+    xs = model.steadystate_()
+    o = OracleModel(model, tol=1e-13)
+    o.x = xs
+    o.run(np.zeros((model.nu, 1)))
+    return np.allclose(o.x[:, 0], xs)
+
+
+@pytest.mark.parametrize("name", ["sallenkey", "diodeclipper", "birdie08", "superover_fixed"])
+def test_K11_checksteady(name):
+    """runtests.jl:692, 703, 728, 748"""
+    m = {"sallenkey": ex.sallenkey, "diodeclipper": ex.diodeclipper,
+         "birdie08": lambda: ex.birdie(vol=0.8),
+         "superover_fixed": lambda: ex.superover(1.0, 1.0, 1.0)}[name]()
+    assert checksteady(m)
+
+
+def test_examples_run():
+    """runtests.jl:684-796: every example runs, converges everywhere, has the right size"""
+    u = cases.sine(4410)
+    for m, uu in [(ex.sallenkey(), u), (ex.birdie(vol=0.8), u),
+                  (ex.birdie(), np.vstack([u, np.linspace(1, 0, u.shape[1])])),
+                  (ex.superover(1.0, 1.0, 1.0), u)]:
+        o = OracleModel(m)
+        y = o.run(uu)
+        assert y.shape == (1, u.shape[1], 1) and np.isfinite(y).all()
+        assert o.status()[0][0] == 0
+    n = 1000
+    uu = np.vstack([cases.sine(n), np.linspace(1, 0, n), np.linspace(0, 1, n), np.linspace(1, 0, n)])
+    for m in (ex.superover(), A.DiscreteModel(ex.superover_circuit(vb_source=True), 1 / 44100)):
+        o = OracleModel(m)
+        y = o.run(uu)
+        assert y.shape == (1, n, 1) and np.isfinite(y).all()
+        assert o.status()[0][0] == 0
+
+
+def test_caching_solver_learns():
+    """README.md:122-124 / solvers.jl:374-394: solutions needing > 5 iterations are stored"""
+    m = ex.birdie(vol=0.8)
+    rng = np.random.default_rng(0)
+    u = np.clip(0.5 * rng.standard_normal((1, 20000)), -2, 2)
+    o = OracleModel(m)
+    o.run(u)
+    first = o.stats()["newton_iters"]
+    n0 = oracle.lib().oracle_cache_size(o.h, 0, 0)
+    assert n0 >= 1
+    cache = o.export_cache()
+    assert len(cache["ps_idx"]) == n0
+
+
+def test_batch_sweep_matches_single():
+    """per-instance element parameters == separately built models"""
+    is_vals = [1e-15, 3e-14, 2e-13]
+    eta_vals = [1.0, 1.5, 2.0]
+    base = ex.diodeclipper()
+    B = len(is_vals)
+    params = np.zeros((4, B))
+    for b in range(B):
+        params[:, b] = [is_vals[b], eta_vals[b], 1.8 * is_vals[b], eta_vals[b]]
+    u = cases.sine(2000)
+    yb = OracleModel(base, B, params=[params]).run(u, threads=2)
+    for b in range(B):
+        mb = ex.diodeclipper(is1=is_vals[b], is2=1.8 * is_vals[b], η1=eta_vals[b], η2=eta_vals[b])
+        assert np.array_equal(run(mb, u)[0], yb[0, :, b])
