@@ -13,10 +13,12 @@ from .elements import (Element, NLElem, bjt, capacitor, currentprobe, currentsou
 from .circuit import Circuit, circuit, topomat
 from .model import DiscreteModel, SubProblem, gensolve, rank_factorize
 from . import examples
+from .runner import BatchRunner, ModelRunner, run_, DimensionMismatch
 
 __all__ = [
     "Element", "NLElem", "Circuit", "circuit", "topomat", "DiscreteModel", "SubProblem",
     "gensolve", "rank_factorize", "examples",
+    "BatchRunner", "ModelRunner", "run_", "DimensionMismatch",
     "resistor", "potentiometer", "capacitor", "inductor", "transformer",
     "voltagesource", "currentsource", "voltageprobe", "currentprobe",
     "diode", "bjt", "mosfet", "opamp",

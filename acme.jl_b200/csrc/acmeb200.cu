@@ -1,0 +1,557 @@
+// C-ABI implementation (include/acmeb200.h): model upload, kernel selection,
+// run! for host or device streams, state/statistics access.
+//
+// There is no CPU fallback in this library: every entry point that computes
+// needs a CUDA device and fails with ACMEB200_ENODEVICE / ACMEB200_ECUDA otherwise.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/acmeb200.h"
+#include "devmodel.h"
+#include "elements.cuh"
+#include "kernel_generic.cuh"
+#include "kernel_tpi.cuh"
+
+using namespace acme;
+
+// ------------------------------------------------------------------ errors
+static thread_local std::string g_err;
+static int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+#define CUDA_TRY(x)                                                                           \
+    do {                                                                                      \
+        cudaError_t e_ = (x);                                                                 \
+        if (e_ != cudaSuccess)                                                                \
+            return fail(e_ == cudaErrorMemoryAllocation ? ACMEB200_ENOMEM : ACMEB200_ECUDA,   \
+                        "%s failed: %s (%s:%d)", #x, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+extern "C" const char* acmeb200_last_error(void) { return g_err.c_str(); }
+extern "C" int acmeb200_abi_version(void) { return ACMEB200_ABI_VERSION; }
+
+// ------------------------------------------------------------------ model object
+struct TpiEntry;
+
+struct acmeb200_model {
+    DevModel dm;
+    int64_t B = 0;
+    int device = 0;
+    // device arrays
+    double* d_blob = nullptr;
+    int64_t blob_stride = 0;
+    double* d_consts = nullptr;
+    double* d_initz = nullptr;
+    double* d_ws = nullptr;      // state/workspace of the selected kernel
+    int64_t ws_rows = 0;
+    uint32_t* d_status = nullptr;
+    long long* d_first_fail = nullptr;
+    DevStats* d_stats = nullptr;
+    std::vector<void*> d_cache;  // device copies of the frozen caches
+    // host copies needed to (re)build kernel parameters
+    std::vector<double> h_blob;  // blob of instance 0 (or the shared blob)
+    const TpiEntry* tpi = nullptr;
+    int kernel_mode = 0;
+    std::string kernel_name;
+    int64_t launches = 0;
+    int64_t n_done = 0;
+    // pinned staging for host-pointer runs
+    double* h_stage[2] = {nullptr, nullptr};
+    double* d_stage_u[2] = {nullptr, nullptr};
+    double* d_stage_y[2] = {nullptr, nullptr};
+    size_t stage_u_bytes = 0, stage_y_bytes = 0, hstage_bytes = 0;
+    cudaStream_t copy_streams[2] = {nullptr, nullptr};
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+};
+
+// ------------------------------------------------------------------ specialised kernels registry
+template <class C>
+static void fill_tpi_mats(const DevModel& dm, const double* blob, TpiMats<C>& M) {
+    memset(&M, 0, sizeof M);
+    auto cp = [&](double* dst, int off, int n) { for (int i = 0; i < n; i++) dst[i] = blob[off + i]; };
+    cp(M.a, dm.o_a, C::NX * C::NX); cp(M.b, dm.o_b, C::NX * C::NU); cp(M.c, dm.o_c, C::NX * C::NN);
+    cp(M.x0, dm.o_x0, C::NX);
+    cp(M.dy, dm.o_dy, C::NY * C::NX); cp(M.ey, dm.o_ey, C::NY * C::NU); cp(M.fy, dm.o_fy, C::NY * C::NN);
+    cp(M.y0, dm.o_y0, C::NY);
+    if (C::NN > 0) {
+        const DevSub& s = dm.subs[0];
+        cp(M.dq, s.o_dq, C::NP * C::NX); cp(M.eq, s.o_eq, C::NP * C::NU);
+        cp(M.pexp, s.o_pexp, C::NQ * C::NP); cp(M.q0, s.o_q0, C::NQ); cp(M.fq, s.o_fq, C::NQ * C::NN);
+    }
+}
+
+template <class C>
+static cudaError_t launch_tpi(const acmeb200_model* m, const RunArgs& a, cudaStream_t stream) {
+    TpiMats<C> M;
+    fill_tpi_mats<C>(m->dm, m->h_blob.data(), M);
+    SolverCfg sc{m->dm.tol, m->dm.maxiter, m->dm.solver};
+    DevSub cache;
+    memset(&cache, 0, sizeof cache);
+    if (m->dm.nsub > 0) cache = m->dm.subs[0];
+    const int64_t blocks = (a.ninst + TPI_TPB - 1) / TPI_TPB;
+    const size_t smem = tpi_smem_bytes<C>();
+    if (m->blob_stride)
+        k_tpi<C, true><<<(unsigned)blocks, TPI_TPB, smem, stream>>>(M, a, sc, cache);
+    else
+        k_tpi<C, false><<<(unsigned)blocks, TPI_TPB, smem, stream>>>(M, a, sc, cache);
+    return cudaGetLastError();
+}
+
+struct TpiEntry {
+    const char* name;
+    int nx, nu, ny, np, ne;
+    const int* kinds;
+    int state_rows;
+    cudaError_t (*launch)(const acmeb200_model*, const RunArgs&, cudaStream_t);
+};
+
+template <class C>
+static TpiEntry make_entry(const char* name) {
+    return TpiEntry{name, C::NX, C::NU, C::NY, C::NP, C::NE, C::kinds, C::S_ROWS, &launch_tpi<C>};
+}
+
+// shapes of the BASELINE circuits (SURVEY.md section 8 size table) + small test circuits
+using CfgDiodeClipper = TpiCfg<1, 1, 1, 1, Diode, Diode>;  // examples/diodeclipper.jl
+using CfgSallenKey = TpiCfg<2, 1, 1, 0>;                   // examples/sallenkey.jl (linear)
+using CfgBirdieFixed = TpiCfg<3, 1, 1, 2, Bjt>;            // examples/birdie.jl, vol baked in
+using CfgBirdieVol = TpiCfg<3, 2, 1, 3, Bjt, Pot>;         // examples/birdie.jl, vol as input
+
+static const std::vector<TpiEntry>& tpi_registry() {
+    static const std::vector<TpiEntry> reg = {
+        make_entry<CfgDiodeClipper>("tpi<diodeclipper nx1 nu1 ny1 np1 [diode,diode]>"),
+        make_entry<CfgSallenKey>("tpi<linear nx2 nu1 ny1>"),
+        make_entry<CfgBirdieFixed>("tpi<birdie nx3 nu1 ny1 np2 [bjt]>"),
+        make_entry<CfgBirdieVol>("tpi<birdie nx3 nu2 ny1 np3 [bjt,pot]>"),
+    };
+    return reg;
+}
+
+static const TpiEntry* find_tpi(const DevModel& dm) {
+    if (dm.nsub > 1) return nullptr;
+    for (const TpiEntry& e : tpi_registry()) {
+        if (e.nx != dm.nx || e.nu != dm.nu || e.ny != dm.ny) continue;
+        if (dm.nsub == 0) {
+            if (e.ne == 0) return &e;
+            continue;
+        }
+        const DevSub& s = dm.subs[0];
+        if (e.ne != s.nelem || e.np != s.np) continue;
+        bool same = true;
+        for (int k = 0; k < e.ne; k++) same = same && dm.elems[s.elem0 + k].kind == e.kinds[k];
+        if (same) return &e;
+    }
+    return nullptr;
+}
+
+// ------------------------------------------------------------------ creation
+static void prep_consts(int kind, const double* P, double* C) {
+    switch (kind) {
+#define X(E) case E::KIND: E::prep(P, C); break;
+        ACME_FOR_EACH_ELEM(X)
+#undef X
+    }
+}
+
+static int select_kernel(acmeb200_model* m);
+static int run_init(acmeb200_model* m);
+
+extern "C" void acmeb200_model_destroy(acmeb200_model* m) {
+    if (!m) return;
+    cudaSetDevice(m->device);
+    cudaFree(m->d_blob); cudaFree(m->d_consts); cudaFree(m->d_initz); cudaFree(m->d_ws);
+    cudaFree(m->d_status); cudaFree(m->d_first_fail); cudaFree(m->d_stats);
+    for (void* p : m->d_cache) cudaFree(p);
+    for (int i = 0; i < 2; i++) {
+        if (m->h_stage[i]) cudaFreeHost(m->h_stage[i]);
+        cudaFree(m->d_stage_u[i]); cudaFree(m->d_stage_y[i]);
+        if (m->copy_streams[i]) cudaStreamDestroy(m->copy_streams[i]);
+        if (m->ev[i]) cudaEventDestroy(m->ev[i]);
+    }
+    delete m;
+}
+
+extern "C" int acmeb200_model_create(const acmeb200_model_desc* d, int64_t first, int64_t count,
+                                     acmeb200_model** out) {
+    if (!d || !out) return fail(ACMEB200_EINVAL, "null argument");
+    *out = nullptr;
+    if (d->abi_version != ACMEB200_ABI_VERSION)
+        return fail(ACMEB200_EINVAL, "descriptor ABI version %d, library %d", d->abi_version, ACMEB200_ABI_VERSION);
+    if (count <= 0 || first < 0) return fail(ACMEB200_EINVAL, "bad instance range [%lld, +%lld)", (long long)first, (long long)count);
+    if (d->nx < 0 || d->nu < 0 || d->ny < 0 || d->nsub < 0) return fail(ACMEB200_EINVAL, "negative dimension");
+    if (d->nsub > MAX_SUBS) return fail(ACMEB200_EUNSUPPORTED, "%d sub-problems, at most %d supported", d->nsub, MAX_SUBS);
+    if (d->solver < 0 || d->solver > 2) return fail(ACMEB200_EINVAL, "unknown solver %d", d->solver);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(ACMEB200_ENODEVICE, "no CUDA device available (this library has no CPU fallback)");
+
+    acmeb200_model* m = new acmeb200_model();
+    cudaGetDevice(&m->device);
+    m->B = count;
+    DevModel& dm = m->dm;
+    memset(&dm, 0, sizeof dm);
+    dm.nx = d->nx; dm.nu = d->nu; dm.ny = d->ny; dm.nsub = d->nsub;
+    dm.solver = d->solver;
+    dm.maxiter = d->maxiter > 0 ? d->maxiter : 500;
+    dm.tol = d->tol > 0 ? d->tol : 1e-10;
+    int nnt = 0;
+    for (int i = 0; i < d->nsub; i++) nnt += d->subs[i].nn;
+    dm.nnt = nnt;
+
+    // ---- blob layout: a b c x0 dy ey fy y0 | per sub: dq eq fqprev pexp q0 fq
+    struct Piece { acmeb200_array arr; int len; int* off; };
+    std::vector<Piece> pieces;
+    int off = 0;
+    auto add = [&](acmeb200_array arr, int len, int* o) { *o = off; pieces.push_back({arr, len, o}); off += len; };
+    add(d->a, dm.nx * dm.nx, &dm.o_a); add(d->b, dm.nx * dm.nu, &dm.o_b); add(d->c, dm.nx * nnt, &dm.o_c);
+    add(d->x0, dm.nx, &dm.o_x0); add(d->dy, dm.ny * dm.nx, &dm.o_dy); add(d->ey, dm.ny * dm.nu, &dm.o_ey);
+    add(d->fy, dm.ny * nnt, &dm.o_fy); add(d->y0, dm.ny, &dm.o_y0);
+    int elem_total = 0, const_total = 0, initz_total = 0, zoff = 0, wrow = 0;
+    int max_nn = 0, max_nq = 0, max_np = 0, max_njv = 0;
+    bool per_instance = false;
+    std::vector<std::vector<double>> h_consts;  // [const row][instance]
+    for (int i = 0; i < d->nsub; i++) {
+        const acmeb200_sub_desc& sd = d->subs[i];
+        DevSub& s = dm.subs[i];
+        if (sd.nn < 0 || sd.nq < 0 || sd.np < 0 || sd.nelem < 0) { delete m; return fail(ACMEB200_EINVAL, "negative sub dimension"); }
+        s.nn = sd.nn; s.nq = sd.nq; s.np = sd.np; s.nelem = sd.nelem; s.elem0 = elem_total; s.zoff = zoff;
+        s.o_initz = initz_total;
+        add(sd.dq, sd.np * dm.nx, &s.o_dq); add(sd.eq, sd.np * dm.nu, &s.o_eq);
+        add(sd.fqprev, sd.np * nnt, &s.o_fqprev); add(sd.pexp, sd.nq * sd.np, &s.o_pexp);
+        add(sd.q0, sd.nq, &s.o_q0); add(sd.fq, sd.nq * sd.nn, &s.o_fq);
+        if (elem_total + sd.nelem > MAX_ELEMS) { delete m; return fail(ACMEB200_EUNSUPPORTED, "more than %d non-linear elements", MAX_ELEMS); }
+        int row = 0, joff = 0, qcheck = 0;
+        for (int e = 0; e < sd.nelem; e++) {
+            const acmeb200_elem& el = sd.elems[e];
+            if (elem_nn(el.kind) < 0) { delete m; return fail(ACMEB200_EINVAL, "unknown element kind %d", el.kind); }
+            if (el.nparam != elem_npar(el.kind) || el.param_offset < 0 || el.param_offset + el.nparam > sd.nparams) {
+                delete m; return fail(ACMEB200_EINVAL, "element %d of sub %d: bad parameter range", e, i);
+            }
+            if (el.q_offset < 0 || el.q_offset + elem_nq(el.kind) > sd.nq) { delete m; return fail(ACMEB200_EINVAL, "element %d of sub %d: q range outside the sub", e, i); }
+            DevElem& de = dm.elems[elem_total + e];
+            de.kind = el.kind; de.q_off = el.q_offset; de.c_off = const_total; de.row = row; de.j_off = joff;
+            // derived constants for every instance
+            const int nc = elem_nc(el.kind);
+            for (int k = 0; k < nc; k++) h_consts.emplace_back((size_t)count);
+            for (int64_t b = 0; b < count; b++) {
+                const double* P = sd.params.ptr + (sd.params.stride ? (first + b) * sd.params.stride : 0) + el.param_offset;
+                double C[24];
+                prep_consts(el.kind, P, C);
+                for (int k = 0; k < nc; k++) h_consts[const_total + k][b] = C[k];
+            }
+            const_total += nc;
+            row += elem_nn(el.kind);
+            joff += elem_nj(el.kind);
+            qcheck += elem_nq(el.kind);
+        }
+        if (row != sd.nn) { delete m; return fail(ACMEB200_EINVAL, "sub %d: elements provide %d equations, nn = %d", i, row, sd.nn); }
+        (void)qcheck;
+        s.njv = joff;
+        elem_total += sd.nelem;
+        initz_total += sd.nn;
+        zoff += sd.nn;
+        max_nn = std::max(max_nn, sd.nn); max_nq = std::max(max_nq, sd.nq);
+        max_np = std::max(max_np, sd.np); max_njv = std::max(max_njv, joff);
+        if (sd.init_z.stride || sd.params.stride) { /* per-instance state only; matrices may still be shared */ }
+    }
+    dm.nelem_total = elem_total;
+    dm.nconst = const_total;
+    dm.ninitz = initz_total;
+    dm.blob_len = off;
+    for (const Piece& p : pieces) if (p.arr.stride != 0 && p.len > 0) per_instance = true;
+    for (const Piece& p : pieces)
+        if (p.len > 0 && !p.arr.ptr) { delete m; return fail(ACMEB200_EINVAL, "null matrix pointer in descriptor"); }
+
+    // ---- generic workspace layout (rows of the [row][instance] array)
+    auto rows = [&](int n) { int r = wrow; wrow += n; return r; };
+    dm.w_x = rows(dm.nx); dm.w_u = rows(dm.nu); dm.w_zall = rows(nnt); dm.w_xnew = rows(dm.nx);
+    dm.w_p = rows(max_np); dm.w_pfull = rows(max_nq); dm.w_q = rows(max_nq); dm.w_res = rows(max_nn);
+    dm.w_jv = rows(max_njv); dm.w_z = rows(max_nn); dm.w_tmp = rows(max_nn);
+    dm.w_startp = rows(max_np); dm.w_pa = rows(max_np); dm.w_cp = rows(max_np);
+    for (int i = 0; i < d->nsub; i++) {
+        DevSub& s = dm.subs[i];
+        s.w_lastp = rows(s.np); s.w_lastz = rows(s.nn); s.w_lastJp = rows(s.nn * s.np);
+        s.w_LU[0] = rows(s.nn * s.nn); s.w_LU[1] = rows(s.nn * s.nn);
+        s.w_ipiv[0] = rows(s.nn); s.w_ipiv[1] = rows(s.nn); s.w_sel = rows(1);
+    }
+    dm.w_rows = wrow;
+
+    // ---- pack + upload
+    auto destroy_fail = [&](int code) { acmeb200_model_destroy(m); return code; };
+    const int64_t nblob = per_instance ? count : 1;
+    std::vector<double> blob((size_t)std::max<int64_t>(1, (int64_t)off * nblob));
+    for (int64_t b = 0; b < nblob; b++)
+        for (const Piece& p : pieces) {
+            if (p.len == 0) continue;
+            const double* src = p.arr.ptr + (p.arr.stride ? (first + b) * p.arr.stride : 0);
+            memcpy(blob.data() + b * off + *p.off, src, sizeof(double) * (size_t)p.len);
+        }
+    m->blob_stride = per_instance ? off : 0;
+    m->h_blob.assign(blob.begin(), blob.begin() + std::max(off, 1));
+#define CT(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { fail(e_ == cudaErrorMemoryAllocation ? ACMEB200_ENOMEM : ACMEB200_ECUDA, "%s failed: %s", #x, cudaGetErrorString(e_)); return destroy_fail(e_ == cudaErrorMemoryAllocation ? ACMEB200_ENOMEM : ACMEB200_ECUDA); } } while (0)
+    CT(cudaMalloc(&m->d_blob, sizeof(double) * blob.size()));
+    CT(cudaMemcpy(m->d_blob, blob.data(), sizeof(double) * blob.size(), cudaMemcpyHostToDevice));
+    {
+        std::vector<double> flat((size_t)std::max<int64_t>(1, (int64_t)const_total * count));
+        for (int k = 0; k < const_total; k++) memcpy(flat.data() + (size_t)k * count, h_consts[k].data(), sizeof(double) * (size_t)count);
+        CT(cudaMalloc(&m->d_consts, sizeof(double) * flat.size()));
+        CT(cudaMemcpy(m->d_consts, flat.data(), sizeof(double) * flat.size(), cudaMemcpyHostToDevice));
+    }
+    {
+        std::vector<double> flat((size_t)std::max<int64_t>(1, (int64_t)initz_total * count));
+        for (int i = 0; i < d->nsub; i++) {
+            const acmeb200_sub_desc& sd = d->subs[i];
+            for (int k = 0; k < sd.nn; k++)
+                for (int64_t b = 0; b < count; b++)
+                    flat[(size_t)(dm.subs[i].o_initz + k) * count + b] =
+                        sd.init_z.ptr ? sd.init_z.ptr[(sd.init_z.stride ? (first + b) * sd.init_z.stride : 0) + k] : 0.0;
+        }
+        CT(cudaMalloc(&m->d_initz, sizeof(double) * flat.size()));
+        CT(cudaMemcpy(m->d_initz, flat.data(), sizeof(double) * flat.size(), cudaMemcpyHostToDevice));
+    }
+    for (int i = 0; i < d->nsub; i++) {
+        const acmeb200_cache& c = d->subs[i].cache;
+        DevSub& s = dm.subs[i];
+        s.cache_n = 0;
+        if (c.n_points <= 0) continue;
+        if (c.n_points > (1 << 20)) return destroy_fail(fail(ACMEB200_EUNSUPPORTED, "cache with %d points", c.n_points));
+        for (int k = 0; k < c.n_points; k++)
+            if (c.ps_idx[k] < 1 || c.ps_idx[k] > c.n_columns) return destroy_fail(fail(ACMEB200_EINVAL, "cache index out of range"));
+        auto up = [&](const void* src, size_t bytes, const void** dst) -> cudaError_t {
+            void* p = nullptr;
+            cudaError_t e = cudaMalloc(&p, std::max<size_t>(bytes, 8));
+            if (e != cudaSuccess) return e;
+            m->d_cache.push_back(p);
+            *dst = p;
+            return bytes ? cudaMemcpy(p, src, bytes, cudaMemcpyHostToDevice) : cudaSuccess;
+        };
+        CT(up(c.cut_dim, sizeof(int32_t) * (size_t)(c.n_points - 1), (const void**)&s.cut_dim));
+        CT(up(c.cut_val, sizeof(double) * (size_t)(c.n_points - 1), (const void**)&s.cut_val));
+        CT(up(c.ps_idx, sizeof(int32_t) * (size_t)c.n_points, (const void**)&s.ps_idx));
+        CT(up(c.ps, sizeof(double) * (size_t)s.np * c.n_columns, (const void**)&s.ps));
+        CT(up(c.zs, sizeof(double) * (size_t)s.nn * c.n_columns, (const void**)&s.zs));
+        s.cache_n = c.n_points;
+        s.cache_cols = c.n_columns;
+    }
+    CT(cudaMalloc(&m->d_status, sizeof(uint32_t) * (size_t)count));
+    CT(cudaMalloc(&m->d_first_fail, sizeof(long long) * (size_t)count));
+    CT(cudaMalloc(&m->d_stats, sizeof(DevStats)));
+    CT(cudaMemset(m->d_stats, 0, sizeof(DevStats)));
+#undef CT
+    int rc = select_kernel(m);
+    if (rc) return destroy_fail(rc);
+    *out = m;
+    return ACMEB200_OK;
+}
+
+// picks the kernel, (re)allocates its state and initialises it
+static int select_kernel(acmeb200_model* m) {
+    m->tpi = m->kernel_mode == 1 ? nullptr : find_tpi(m->dm);
+    m->ws_rows = m->tpi ? m->tpi->state_rows : m->dm.w_rows;
+    m->kernel_name = m->tpi ? m->tpi->name : "generic<thread-per-instance, runtime dims>";
+    cudaFree(m->d_ws);
+    m->d_ws = nullptr;
+    CUDA_TRY(cudaMalloc(&m->d_ws, sizeof(double) * (size_t)std::max<int64_t>(1, m->ws_rows * m->B)));
+    CUDA_TRY(cudaMemset(m->d_ws, 0, sizeof(double) * (size_t)std::max<int64_t>(1, m->ws_rows * m->B)));
+    return run_init(m);
+}
+
+static RunArgs base_args(acmeb200_model* m) {
+    RunArgs a;
+    memset(&a, 0, sizeof a);
+    a.blob = m->d_blob; a.blob_stride = m->blob_stride; a.consts = m->d_consts; a.initz = m->d_initz;
+    a.ws = m->d_ws; a.ld = m->B; a.status = m->d_status; a.first_fail = m->d_first_fail; a.stats = m->d_stats;
+    a.n_done = m->n_done;
+    return a;
+}
+
+static cudaError_t launch(acmeb200_model* m, const RunArgs& a, cudaStream_t stream) {
+    m->launches++;
+    if (m->tpi) return m->tpi->launch(m, a, stream);
+    const int tpb = 128;
+    k_generic<<<(unsigned)((a.ninst + tpb - 1) / tpb), tpb, 0, stream>>>(m->dm, a);
+    return cudaGetLastError();
+}
+
+static int run_init(acmeb200_model* m) {
+    RunArgs a = base_args(m);
+    a.init = 1; a.inst0 = 0; a.ninst = m->B; a.N = 0;
+    CUDA_TRY(launch(m, a, nullptr));
+    CUDA_TRY(cudaMemsetAsync(m->d_stats, 0, sizeof(DevStats), nullptr));
+    CUDA_TRY(cudaDeviceSynchronize());
+    m->n_done = 0;
+    return ACMEB200_OK;
+}
+
+extern "C" int acmeb200_reset(acmeb200_model* m) {
+    if (!m) return fail(ACMEB200_EINVAL, "null model");
+    CUDA_TRY(cudaSetDevice(m->device));
+    return run_init(m);
+}
+
+extern "C" int acmeb200_set_kernel(acmeb200_model* m, int32_t mode) {
+    if (!m) return fail(ACMEB200_EINVAL, "null model");
+    if (mode != 0 && mode != 1) return fail(ACMEB200_EINVAL, "kernel mode must be 0 (auto) or 1 (generic)");
+    CUDA_TRY(cudaSetDevice(m->device));
+    m->kernel_mode = mode;
+    return select_kernel(m);
+}
+extern "C" const char* acmeb200_kernel_name(const acmeb200_model* m) { return m ? m->kernel_name.c_str() : ""; }
+extern "C" int64_t acmeb200_launch_count(const acmeb200_model* m) { return m ? m->launches : 0; }
+
+// ------------------------------------------------------------------ run
+static int ensure_staging(acmeb200_model* m, size_t ubytes, size_t ybytes) {
+    for (int i = 0; i < 2; i++) {
+        if (!m->copy_streams[i]) CUDA_TRY(cudaStreamCreateWithFlags(&m->copy_streams[i], cudaStreamNonBlocking));
+        if (!m->ev[i]) CUDA_TRY(cudaEventCreateWithFlags(&m->ev[i], cudaEventDisableTiming));
+    }
+    if (ubytes > m->stage_u_bytes) {
+        for (int i = 0; i < 2; i++) { cudaFree(m->d_stage_u[i]); m->d_stage_u[i] = nullptr; CUDA_TRY(cudaMalloc(&m->d_stage_u[i], ubytes)); }
+        m->stage_u_bytes = ubytes;
+    }
+    if (ybytes > m->stage_y_bytes) {
+        for (int i = 0; i < 2; i++) { cudaFree(m->d_stage_y[i]); m->d_stage_y[i] = nullptr; CUDA_TRY(cudaMalloc(&m->d_stage_y[i], ybytes)); }
+        m->stage_y_bytes = ybytes;
+    }
+    return ACMEB200_OK;
+}
+
+static bool is_pinned_or_managed(const void* p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged;
+}
+
+extern "C" int acmeb200_run(acmeb200_model* m, const double* U, int64_t u_stride, double* Y,
+                            int64_t y_stride, int64_t N, uint32_t flags, void* stream_) {
+    if (!m) return fail(ACMEB200_EINVAL, "null model");
+    if (N < 0) return fail(ACMEB200_EINVAL, "negative sample count");
+    if (N >= (1ll << 27)) return fail(ACMEB200_EUNSUPPORTED, "at most 2^27-1 samples per call; split the run");
+    const DevModel& dm = m->dm;
+    if (y_stride == 0) y_stride = (int64_t)dm.ny * N;
+    if (u_stride != 0 && u_stride < (int64_t)dm.nu * N) return fail(ACMEB200_EINVAL, "u_stride smaller than nu*N");
+    if (y_stride < (int64_t)dm.ny * N) return fail(ACMEB200_EINVAL, "y_stride smaller than ny*N");
+    if (N == 0) return ACMEB200_OK;
+    if ((dm.nu > 0 && !U) || (dm.ny > 0 && !Y)) return fail(ACMEB200_EINVAL, "null stream pointer");
+    CUDA_TRY(cudaSetDevice(m->device));
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const bool udev = (flags & ACMEB200_U_DEVICE) || dm.nu == 0, ydev = (flags & ACMEB200_Y_DEVICE) || dm.ny == 0;
+
+    if (udev && ydev) {
+        RunArgs a = base_args(m);
+        a.U = U; a.u_stride = u_stride; a.Y = Y; a.y_stride = y_stride; a.N = N; a.inst0 = 0; a.ninst = m->B;
+        CUDA_TRY(launch(m, a, stream));
+        m->n_done += N;
+        return ACMEB200_OK;
+    }
+
+    // ---- host streams: chunks of instances, double-buffered H2D / kernel / D2H
+    const size_t u_per = (size_t)dm.nu * N * sizeof(double), y_per = (size_t)dm.ny * N * sizeof(double);
+    const size_t target = (size_t)256 << 20;
+    int64_t chunk = (int64_t)std::max<size_t>(1, target / std::max<size_t>(1, std::max(u_per, y_per)));
+    chunk = std::min<int64_t>(chunk, m->B);
+    if (chunk >= 64) chunk -= chunk % 64;
+    const bool shared_u = (u_stride == 0) || dm.nu == 0;
+    int rc = ensure_staging(m, udev ? 8 : (shared_u ? std::max<size_t>(u_per, 8) : u_per * chunk), ydev ? 8 : y_per * chunk);
+    if (rc) return rc;
+    // pageable host memory is staged through the driver; pinned memory is DMA'd directly
+    (void)is_pinned_or_managed;
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    if (!udev && shared_u && dm.nu > 0)
+        CUDA_TRY(cudaMemcpyAsync(m->d_stage_u[0], U, u_per, cudaMemcpyHostToDevice, m->copy_streams[0]));
+    if (!udev && shared_u && dm.nu > 0) {
+        CUDA_TRY(cudaStreamSynchronize(m->copy_streams[0]));
+    }
+    int buf = 0;
+    for (int64_t b0 = 0; b0 < m->B; b0 += chunk, buf ^= 1) {
+        const int64_t nb = std::min(chunk, m->B - b0);
+        cudaStream_t cs = m->copy_streams[buf];
+        RunArgs a = base_args(m);
+        a.N = N; a.inst0 = b0; a.ninst = nb;
+        if (udev) { a.U = U + (u_stride ? b0 * u_stride : 0); a.u_stride = u_stride; }
+        else if (shared_u) { a.U = m->d_stage_u[0]; a.u_stride = 0; }
+        else {
+            if (u_stride == (int64_t)dm.nu * N)
+                CUDA_TRY(cudaMemcpyAsync(m->d_stage_u[buf], U + b0 * u_stride, u_per * nb, cudaMemcpyHostToDevice, cs));
+            else
+                CUDA_TRY(cudaMemcpy2DAsync(m->d_stage_u[buf], u_per, U + b0 * u_stride, u_stride * sizeof(double), u_per, nb, cudaMemcpyHostToDevice, cs));
+            a.U = m->d_stage_u[buf]; a.u_stride = (int64_t)dm.nu * N;
+        }
+        if (ydev) { a.Y = Y + b0 * y_stride; a.y_stride = y_stride; }
+        else { a.Y = m->d_stage_y[buf]; a.y_stride = (int64_t)dm.ny * N; }
+        CUDA_TRY(launch(m, a, cs));
+        if (!ydev) {
+            if (y_stride == (int64_t)dm.ny * N)
+                CUDA_TRY(cudaMemcpyAsync(Y + b0 * y_stride, m->d_stage_y[buf], y_per * nb, cudaMemcpyDeviceToHost, cs));
+            else
+                CUDA_TRY(cudaMemcpy2DAsync(Y + b0 * y_stride, y_stride * sizeof(double), m->d_stage_y[buf], y_per, y_per, nb, cudaMemcpyDeviceToHost, cs));
+        }
+        // the buffer pair `buf` is reused two chunks later: stream order on cs protects it
+    }
+    CUDA_TRY(cudaStreamSynchronize(m->copy_streams[0]));
+    CUDA_TRY(cudaStreamSynchronize(m->copy_streams[1]));
+    m->n_done += N;
+    return ACMEB200_OK;
+}
+
+// ------------------------------------------------------------------ state / statistics
+static int state_row_of_x(const acmeb200_model* m) { return m->tpi ? 0 : m->dm.w_x; }
+
+extern "C" int acmeb200_get_state(acmeb200_model* m, double* x_host) {
+    if (!m || !x_host) return fail(ACMEB200_EINVAL, "null argument");
+    CUDA_TRY(cudaSetDevice(m->device));
+    CUDA_TRY(cudaDeviceSynchronize());
+    const int nx = m->dm.nx;
+    if (nx == 0) return ACMEB200_OK;
+    std::vector<double> rows((size_t)nx * m->B);
+    CUDA_TRY(cudaMemcpy(rows.data(), m->d_ws + (size_t)state_row_of_x(m) * m->B, sizeof(double) * rows.size(), cudaMemcpyDeviceToHost));
+    for (int64_t b = 0; b < m->B; b++)
+        for (int i = 0; i < nx; i++) x_host[b * nx + i] = rows[(size_t)i * m->B + b];
+    return ACMEB200_OK;
+}
+
+extern "C" int acmeb200_set_state(acmeb200_model* m, const double* x_host, int64_t stride) {
+    if (!m || !x_host) return fail(ACMEB200_EINVAL, "null argument");
+    CUDA_TRY(cudaSetDevice(m->device));
+    CUDA_TRY(cudaDeviceSynchronize());
+    const int nx = m->dm.nx;
+    if (nx == 0) return ACMEB200_OK;
+    std::vector<double> rows((size_t)nx * m->B);
+    for (int64_t b = 0; b < m->B; b++)
+        for (int i = 0; i < nx; i++) rows[(size_t)i * m->B + b] = x_host[b * stride + i];
+    CUDA_TRY(cudaMemcpy(m->d_ws + (size_t)state_row_of_x(m) * m->B, rows.data(), sizeof(double) * rows.size(), cudaMemcpyHostToDevice));
+    return ACMEB200_OK;
+}
+
+extern "C" int acmeb200_get_status(acmeb200_model* m, uint32_t* status_host, int64_t* first_fail_host) {
+    if (!m) return fail(ACMEB200_EINVAL, "null model");
+    CUDA_TRY(cudaSetDevice(m->device));
+    CUDA_TRY(cudaDeviceSynchronize());
+    if (status_host) CUDA_TRY(cudaMemcpy(status_host, m->d_status, sizeof(uint32_t) * (size_t)m->B, cudaMemcpyDeviceToHost));
+    if (first_fail_host) CUDA_TRY(cudaMemcpy(first_fail_host, m->d_first_fail, sizeof(long long) * (size_t)m->B, cudaMemcpyDeviceToHost));
+    return ACMEB200_OK;
+}
+
+extern "C" int acmeb200_get_stats(acmeb200_model* m, acmeb200_stats* out) {
+    if (!m || !out) return fail(ACMEB200_EINVAL, "null argument");
+    CUDA_TRY(cudaSetDevice(m->device));
+    CUDA_TRY(cudaDeviceSynchronize());
+    DevStats s;
+    CUDA_TRY(cudaMemcpy(&s, m->d_stats, sizeof s, cudaMemcpyDeviceToHost));
+    out->samples = s.samples; out->solves = s.solves; out->newton_iters = s.newton_iters;
+    out->homotopy_solves = s.homotopy_solves; out->not_converged = s.not_converged;
+    for (int i = 0; i < ACMEB200_HIST_BINS; i++) out->iter_hist[i] = s.iter_hist[i];
+    return ACMEB200_OK;
+}

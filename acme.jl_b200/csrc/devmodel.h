@@ -1,0 +1,71 @@
+// Device-side model description shared by the host code and all kernels.
+#pragma once
+#include <cstdint>
+#include "../../include/acmeb200.h"
+
+namespace acme {
+
+constexpr int MAX_SUBS = 8;
+constexpr int MAX_ELEMS = 48;
+
+struct DevElem {
+    int kind;
+    int q_off;  // first q of this element within its sub (CircuitNLFunc order, circuit.jl:76)
+    int c_off;  // first derived constant within the model's constant table
+    int row;    // first residual row within its sub
+    int j_off;  // first variable Jacobian entry within the sub's jv scratch
+};
+
+struct DevSub {
+    int nn, nq, np, nelem, elem0, zoff, njv, o_initz;
+    // offsets (in doubles) into the matrix blob, all column-major
+    int o_dq, o_eq, o_fqprev, o_pexp, o_q0, o_fq;
+    // generic-kernel workspace rows that persist across run calls
+    int w_lastp, w_lastz, w_lastJp, w_LU[2], w_ipiv[2], w_sel;
+    // frozen solution cache (device pointers), kdtree.jl:4-9 + solvers.jl:321-323
+    int cache_n, cache_cols;
+    const int* cut_dim;
+    const double* cut_val;
+    const int* ps_idx;
+    const double* ps;
+    const double* zs;
+};
+
+struct DevModel {
+    int nx, nu, ny, nsub, nnt, solver, maxiter, nelem_total;
+    double tol;
+    int o_a, o_b, o_c, o_x0, o_dy, o_ey, o_fy, o_y0, blob_len, nconst, ninitz;
+    // generic-kernel workspace rows
+    int w_x, w_u, w_zall, w_xnew, w_p, w_pfull, w_q, w_res, w_jv, w_z, w_tmp, w_startp, w_pa, w_cp, w_rows;
+    DevSub subs[MAX_SUBS];
+    DevElem elems[MAX_ELEMS];
+};
+
+// device statistics block (mirrors acmeb200_stats, all 64-bit counters)
+struct DevStats {
+    unsigned long long samples, solves, newton_iters, homotopy_solves, not_converged;
+    unsigned long long iter_hist[ACMEB200_HIST_BINS];
+};
+
+struct RunArgs {
+    const double* blob;      // matrices: shared (blob_stride 0) or one blob per instance
+    int64_t blob_stride;
+    const double* consts;    // derived element constants, [nconst][ld]
+    const double* initz;     // initial solutions, [ninitz][ld]
+    double* ws;              // generic workspace / kernel-private state, [rows][ld]
+    int64_t ld;              // instances in this model (leading dimension of the SoA arrays)
+    const double* U;         // (nu, N, B) for the instances of this launch
+    int64_t u_stride;
+    double* Y;
+    int64_t y_stride;
+    int64_t N;               // samples in this call
+    int64_t n_done;          // samples processed by earlier calls (for first_fail)
+    int64_t inst0;           // first instance of this launch (index into the SoA arrays)
+    int64_t ninst;           // instances in this launch
+    uint32_t* status;
+    long long* first_fail;
+    DevStats* stats;
+    int init;                // 1: (re)initialise the solver state, process no samples
+};
+
+}  // namespace acme

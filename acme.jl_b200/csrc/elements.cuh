@@ -1,0 +1,316 @@
+// Non-linear element laws as __device__ functions.
+//
+// The reference stores these as Julia closures q -> (res, J)
+// (/root/reference/src/elements.jl:25-30 pot, :107-129 Jiles-Atherton,
+// :238-244 diode, :323-401 BJT, :453-479 MOSFET, :540-546 tanh op-amp).
+// Here every element type E provides
+//   NN, NQ        rows / columns of its Jacobian block
+//   NPAR          raw parameters (layout in include/acmeb200.h)
+//   NC            per-instance constants derived once from the parameters
+//                 (exactly the sub-expressions the reference's closure captures)
+//   NJ            number of Jacobian entries that are not compile-time constants
+//   prep(P, C)    parameters -> constants
+//   eval(C, q, res, jv)   residuals and the variable Jacobian entries
+//   row<R>(jv, m)         (row R of the Jacobian block) . (m(0..NQ-1)), used for
+//                         J = Jq*fq (ACME.jl:186) and Jp = Jq*pexp (ACME.jl:249)
+//                         without multiplying by the structural zeros / +-1
+#pragma once
+#include <cmath>
+#include "../../include/acmeb200.h"
+
+namespace acme {
+
+#define ACME_DI __host__ __device__ __forceinline__
+
+struct Diode {  // elements.jl:236-245
+    static constexpr int KIND = ACMEB200_ELEM_DIODE, NN = 1, NQ = 2, NPAR = 2, NC = 3, NJ = 1;
+    ACME_DI static void prep(const double* P, double* C) {
+        const double is = P[0], eta = P[1];
+        C[0] = is;
+        C[1] = 1 / (25e-3 * eta);
+        C[2] = is / (25e-3 * eta);
+    }
+    ACME_DI static void eval(const double* C, const double* q, double* res, double* jv) {
+        const double ex = exp(q[0] * C[1]);
+        res[0] = C[0] * (ex - 1) - q[1];
+        jv[0] = C[2] * ex;
+    }
+    template <int R, class F> ACME_DI static double row(const double* jv, F m) {
+        return fma(jv[0], m(0), -m(1));
+    }
+};
+
+struct Pot {  // elements.jl:20-31
+    static constexpr int KIND = ACMEB200_ELEM_POT, NN = 2, NQ = 5, NPAR = 1, NC = 1, NJ = 4;
+    ACME_DI static void prep(const double* P, double* C) { C[0] = P[0]; }
+    ACME_DI static void eval(const double* C, const double* q, double* res, double* jv) {
+        const double r = C[0];
+        const double v1 = q[0], v2 = q[1], i1 = q[2], i2 = q[3], pos = q[4];
+        res[0] = v1 - r * pos * i1;
+        res[1] = v2 - r * (1 - pos) * i2;
+        jv[0] = -r * pos;
+        jv[1] = -r * i1;
+        jv[2] = -r * (1 - pos);
+        jv[3] = -r * i2;
+    }
+    template <int R, class F> ACME_DI static double row(const double* jv, F m) {
+        if constexpr (R == 0) return fma(jv[1], m(4), fma(jv[0], m(2), m(0)));
+        return fma(jv[3], m(4), fma(jv[2], m(3), m(1)));
+    }
+};
+
+struct OpampTanh {  // elements.jl:536-551
+    static constexpr int KIND = ACMEB200_ELEM_OPAMP_TANH, NN = 1, NQ = 2, NPAR = 2, NC = 3, NJ = 1;
+    ACME_DI static void prep(const double* P, double* C) {
+        C[0] = P[0];         // gain
+        C[1] = P[1];         // scale
+        C[2] = P[0] / P[1];  // gain/scale
+    }
+    ACME_DI static void eval(const double* C, const double* q, double* res, double* jv) {
+        const double vs = q[0] * C[2];
+        const double ch = cosh(vs);
+        res[0] = tanh(vs) * C[1] - q[1];
+        jv[0] = C[0] / (ch * ch);
+    }
+    template <int R, class F> ACME_DI static double row(const double* jv, F m) {
+        return fma(jv[0], m(0), -m(1));
+    }
+};
+
+struct TestQuad {  // test/runtests.jl:207-219
+    static constexpr int KIND = ACMEB200_ELEM_TEST_QUAD, NN = 1, NQ = 2, NPAR = 0, NC = 1, NJ = 1;
+    ACME_DI static void prep(const double*, double* C) { C[0] = 0; }
+    ACME_DI static void eval(const double*, const double* q, double* res, double* jv) {
+        res[0] = q[0] * q[0] - 1 + q[1];
+        jv[0] = 2 * q[0];
+    }
+    template <int R, class F> ACME_DI static double row(const double* jv, F m) {
+        return fma(jv[0], m(0), m(1));
+    }
+};
+
+struct Bjt {  // elements.jl:309-406
+    static constexpr int KIND = ACMEB200_ELEM_BJT, NN = 2, NQ = 4, NPAR = 14, NC = 20, NJ = 4;
+    // flags packed in C[19]: bit0 early, bit1 knee, bit2 ile!=0, bit3 own exp for the
+    // emitter leakage, bit4 ilc!=0, bit5 own exp for the collector leakage
+    ACME_DI static void prep(const double* P, double* C) {
+        const double ise = P[0], isc = P[1], ne = P[2], nc = P[3], bf = P[4], br = P[5];
+        const double ile = P[6], ilc = P[7], nel = P[8], ncl = P[9];
+        const double vaf = P[10], var = P[11], ikf = P[12], ikr = P[13];
+        C[0] = 1 / (25e-3 * ne);
+        C[1] = 1 / (25e-3 * nc);
+        C[2] = bf / (1 + bf) * ise;
+        C[3] = br / (1 + br) * isc;
+        C[4] = bf / (1 + bf) * ise / (25e-3 * ne);
+        C[5] = br / (1 + br) * isc / (25e-3 * nc);
+        C[6] = 1 / bf;
+        C[7] = 1 / br;
+        C[8] = ile;
+        C[9] = ilc;
+        C[10] = 1 / (25e-3 * nel);
+        C[11] = 1 / (25e-3 * ncl);
+        C[12] = ile / (25e-3 * ne);
+        C[13] = ilc / (25e-3 * nc);
+        C[14] = 1 / var;
+        C[15] = 1 / vaf;
+        C[16] = 1 / ikf;
+        C[17] = 1 / ikr;
+        C[18] = 0;
+        int flags = 0;
+        if (!(var == INFINITY && vaf == INFINITY)) flags |= 1;
+        if (!(ikf == INFINITY && ikr == INFINITY)) flags |= 2;
+        if (ile != 0) flags |= 4;
+        if (nel != ne) flags |= 8;
+        if (ilc != 0) flags |= 16;
+        if (ncl != nc) flags |= 32;
+        C[19] = (double)flags;
+    }
+    ACME_DI static void eval(const double* C, const double* q, double* res, double* jv) {
+        const int flags = (int)C[19];
+        const double vE = q[0], vC = q[1], iE = q[2], iC = q[3];
+        const double expE = exp(vE * C[0]);
+        const double expC = exp(vC * C[1]);
+        const double i_f = C[2] * (expE - 1);
+        const double i_r = C[3] * (expC - 1);
+        const double di_f1 = C[4] * expE;
+        const double di_r2 = C[5] * expC;
+        double i_cc, di_cc1, di_cc2;
+        if ((flags & 3) == 0) {
+            i_cc = i_f - i_r;
+            di_cc1 = di_f1;
+            di_cc2 = -di_r2;
+        } else if ((flags & 3) == 1) {
+            const double q1 = 1 - vE * C[14] - vC * C[15];
+            i_cc = q1 * (i_f - i_r);
+            di_cc1 = (-C[14]) * (i_f - i_r) + q1 * di_f1;
+            di_cc2 = (-C[15]) * (i_f - i_r) - q1 * di_r2;
+        } else if ((flags & 3) == 2) {
+            const double q2 = i_f * C[16] + i_r * C[17];
+            const double qden = 1 + sqrt(1 + 4 * q2);
+            const double qfact = 2 / qden;
+            i_cc = qfact * (i_f - i_r);
+            const double dq21 = di_f1 * C[16], dq22 = di_r2 * C[17];
+            const double dqf1 = -4 * dq21 / (qden - 1) / (qden * qden);
+            const double dqf2 = -4 * dq22 / (qden - 1) / (qden * qden);
+            di_cc1 = dqf1 * (i_f - i_r) + qfact * di_f1;
+            di_cc2 = dqf2 * (i_f - i_r) - qfact * di_r2;
+        } else {
+            const double q1 = 1 - vE * C[14] - vC * C[15];
+            const double q2 = i_f * C[16] + i_r * C[17];
+            const double qden = 1 + sqrt(1 + 4 * q2);
+            const double qfact = 2 * q1 / qden;
+            i_cc = qfact * (i_f - i_r);
+            const double dq21 = di_f1 * C[16], dq22 = di_r2 * C[17];
+            const double dqf1 = (2 * (-C[14]) * qden - q1 * 4 * dq21 / (qden - 1)) / (qden * qden);
+            const double dqf2 = (2 * (-C[15]) * qden - q1 * 4 * dq22 / (qden - 1)) / (qden * qden);
+            di_cc1 = dqf1 * (i_f - i_r) + qfact * di_f1;
+            di_cc2 = dqf2 * (i_f - i_r) - qfact * di_r2;
+        }
+        double iBE = C[6] * i_f, diBE1 = C[6] * di_f1;
+        if (flags & 4) {
+            const double expEl = (flags & 8) ? exp(vE * C[10]) : expE;
+            iBE += C[8] * (expEl - 1);
+            diBE1 += C[12] * expEl;
+        }
+        double iBC = C[7] * i_r, diBC2 = C[7] * di_r2;
+        if (flags & 16) {
+            const double expCl = (flags & 32) ? exp(vC * C[11]) : expC;
+            iBC += C[9] * (expCl - 1);
+            diBC2 += C[13] * expCl;
+        }
+        res[0] = i_cc + iBE - iE;
+        res[1] = -i_cc + iBC - iC;
+        jv[0] = di_cc1 + diBE1;
+        jv[1] = di_cc2;
+        jv[2] = -di_cc1;
+        jv[3] = -di_cc2 + diBC2;
+    }
+    template <int R, class F> ACME_DI static double row(const double* jv, F m) {
+        if constexpr (R == 0) return fma(jv[1], m(1), fma(jv[0], m(0), -m(2)));
+        return fma(jv[3], m(1), fma(jv[2], m(0), -m(3)));
+    }
+};
+
+struct Mosfet {  // elements.jl:436-481
+    static constexpr int KIND = ACMEB200_ELEM_MOSFET, NN = 1, NQ = 3, NPAR = 12, NC = 12, NJ = 2;
+    ACME_DI static void prep(const double* P, double* C) {
+        for (int i = 0; i < 12; i++) C[i] = P[i];
+    }
+    ACME_DI static double poly(double x, const double* c, int n) {  // Horner (Base.evalpoly)
+        double acc = c[n - 1];
+        for (int i = n - 2; i >= 0; i--) acc = fma(x, acc, c[i]);
+        return acc;
+    }
+    ACME_DI static void eval(const double* C, const double* q, double* res, double* jv) {
+        const double pol = C[0], lam = C[1];
+        const int nvt = (int)C[2], nal = (int)C[3];
+        const double *vt = C + 4, *al = C + 8;
+        double dvt[3] = {0, 0, 0}, dal[3] = {0, 0, 0};
+        for (int k = 1; k < 4; k++) {
+            if (k < nvt) dvt[k - 1] = vt[k] * k;
+            if (k < nal) dal[k - 1] = al[k] * k;
+        }
+        const double vgs = q[0], vds = q[1], id = q[2];
+        const double a_ = poly(pol * vgs, al, nal);
+        const double da = nal > 1 ? poly(pol * vgs, dal, nal - 1) : 0;
+        const double vt_ = poly(pol * vgs, vt, nvt);
+        const double dvt_ = nvt > 1 ? poly(pol * vgs, dvt, nvt - 1) : 0;
+        const double lam_ = vds >= 0 ? lam : 0.0;
+        if (vgs <= vt_) {
+            res[0] = -id;
+            jv[0] = 0.0;
+            jv[1] = 0.0;
+        } else if (vds <= vgs - vt_) {
+            res[0] = a_ * (vgs - vt_ - 0.5 * vds) * vds * (1 + lam_ * vds) - id;
+            jv[0] = a_ * (1 - dvt_) * vds * (1 + lam_ * vds) +
+                    da * (vgs - vt_ - 0.5 * vds) * vds * (1 + lam_ * vds);
+            jv[1] = a_ * (vgs - vt_ + vds * (2 * lam_ * (vgs - vt_ - 0.75 * vds) - 1));
+        } else {
+            const double d = vgs - vt_;
+            res[0] = (a_ / 2) * (d * d) * (1 + lam_ * vds) - id;
+            jv[0] = a_ * d * (1 - dvt_) * (1 + lam_ * vds) + da / 2 * (d * d) * (1 + lam_ * vds);
+            jv[1] = lam_ * a_ / 2 * (d * d);
+        }
+    }
+    template <int R, class F> ACME_DI static double row(const double* jv, F m) {
+        return fma(jv[1], m(1), fma(jv[0], m(0), -m(2)));
+    }
+};
+
+struct JilesAtherton {  // elements.jl:104-135
+    static constexpr int KIND = ACMEB200_ELEM_JA, NN = 1, NQ = 4, NPAR = 5, NC = 5, NJ = 4;
+    ACME_DI static void prep(const double* P, double* C) {
+        for (int i = 0; i < 5; i++) C[i] = P[i];
+    }
+    ACME_DI static double sgn(double x) { return (double)((x > 0) - (x < 0)); }
+    ACME_DI static void eval(const double* C, const double* q, double* res, double* jv) {
+        const double Ms = C[0], a = C[1], alpha = C[2], c = C[3], k = C[4];
+        const double q1 = q[0], q2 = q[1], q3 = q[2], q4 = q[3];
+        const double coth_q1 = 1 / tanh(q1);
+        const double a_q1 = fabs(q1);
+        const double L = a_q1 < 1e-4 ? q1 / 3 : coth_q1 - 1 / q1;
+        const double Ld = a_q1 < 1e-4 ? 1.0 / 3 : 1 / (q1 * q1) - coth_q1 * coth_q1 + 1;
+        const double Ld2 = a_q1 < 1e-3 ? -2.0 / 15 * q1
+                                        : 2 * coth_q1 * (coth_q1 * coth_q1 - 1) - 2 / (q1 * q1 * q1);
+        const double delta = q3 > 0 ? 1.0 : -1.0;
+        const double Man = Ms * L;
+        const double dM = sgn(q3) == sgn(Man - q2) ? 1.0 : 0.0;
+        const double den = delta * (k * (1 - c)) - alpha * (Man - q2);
+        const double s = 1e-4 / Ms;
+        res[0] = s * ((1 - c) * dM * (Man - q2) / den * q3 + (c * Ms / a) * (q3 + alpha * q4) * Ld - q4);
+        jv[0] = s * (((1 - c) * (1 - c) * k * Ms) * dM * Ld * delta / (den * den) * q3 +
+                     (c * Ms / a) * (q3 + alpha * q4) * Ld2);
+        jv[1] = s * -((1 - c) * (1 - c)) * k * dM * delta / (den * den) * q3;
+        jv[2] = s * ((1 - c) * dM * (Man - q2) / den + (c * Ms / a) * Ld);
+        jv[3] = s * ((c * Ms / a * alpha) * Ld - 1);
+    }
+    template <int R, class F> ACME_DI static double row(const double* jv, F m) {
+        return fma(jv[3], m(3), fma(jv[2], m(2), fma(jv[1], m(1), jv[0] * m(0))));
+    }
+};
+
+// runtime-kind dispatch helpers (generic kernel / host-side tables)
+#define ACME_FOR_EACH_ELEM(X) X(Diode) X(Bjt) X(Pot) X(Mosfet) X(OpampTanh) X(JilesAtherton) X(TestQuad)
+
+__host__ __device__ inline int elem_nn(int kind) {
+    switch (kind) {
+#define X(E) case E::KIND: return E::NN;
+        ACME_FOR_EACH_ELEM(X)
+#undef X
+    }
+    return -1;
+}
+__host__ __device__ inline int elem_nq(int kind) {
+    switch (kind) {
+#define X(E) case E::KIND: return E::NQ;
+        ACME_FOR_EACH_ELEM(X)
+#undef X
+    }
+    return -1;
+}
+__host__ __device__ inline int elem_npar(int kind) {
+    switch (kind) {
+#define X(E) case E::KIND: return E::NPAR;
+        ACME_FOR_EACH_ELEM(X)
+#undef X
+    }
+    return -1;
+}
+__host__ __device__ inline int elem_nc(int kind) {
+    switch (kind) {
+#define X(E) case E::KIND: return E::NC;
+        ACME_FOR_EACH_ELEM(X)
+#undef X
+    }
+    return -1;
+}
+__host__ __device__ inline int elem_nj(int kind) {
+    switch (kind) {
+#define X(E) case E::KIND: return E::NJ;
+        ACME_FOR_EACH_ELEM(X)
+#undef X
+    }
+    return -1;
+}
+
+}  // namespace acme

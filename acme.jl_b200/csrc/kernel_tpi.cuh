@@ -1,0 +1,605 @@
+// Thread-per-instance kernels with compile-time dimensions and element sequence.
+//
+// One thread owns one model instance for the whole call: its state vector x,
+// the extrapolation origin (last_p, last_z) and the extrapolation matrix
+// Mx = J^-1 * Jp live in registers; the shared model matrices arrive as a
+// __grid_constant__ kernel parameter, so with fully unrolled loops every matrix
+// element is a constant-bank operand of a DFMA.  The (nu, N, B) / (ny, N, B)
+// streams are instance-slowest (each instance is a contiguous reference-layout
+// block), so each warp stages [32 instances x T samples] tiles through shared
+// memory with coalesced 128-byte row segments.
+//
+// Per sample this is step! (/root/reference/src/ACME.jl:666-715) with the
+// SimpleSolver Newton loop (src/solvers.jl:207-236) inlined; the homotopy
+// fallback (solvers.jl:268-296) and the cache lookup (solvers.jl:347-371) are
+// cold, out-of-line paths working on a spilled copy of the state.
+//
+// Deviation from the reference's data layout (not its arithmetic): instead of
+// keeping (last_LU, last_Jp) and solving last_LU \ (last_Jp*dp) every sample
+// (solvers.jl:209-215) the kernel stores Mx = last_LU \ last_Jp once per
+// converged solve; the start vector z0 = last_z - Mx*dp is the same up to
+// rounding.
+#pragma once
+#include "devmodel.h"
+#include "elements.cuh"
+#include "kernel_generic.cuh"  // kd_nearest
+
+namespace acme {
+
+template <int V> struct IC { static constexpr int value = V; };
+template <class... Es> struct EList {};
+
+template <int I, int N, class F>
+__device__ __forceinline__ void static_for(F&& f) {
+    if constexpr (I < N) {
+        f(IC<I>{});
+        static_for<I + 1, N>(f);
+    }
+}
+
+template <int ROW, int QOFF, int COFF, int JOFF, class F>
+__device__ __forceinline__ void for_each_elem(EList<>, F&&) {}
+template <int ROW, int QOFF, int COFF, int JOFF, class F, class E, class... R>
+__device__ __forceinline__ void for_each_elem(EList<E, R...>, F&& f) {
+    f(E{}, IC<ROW>{}, IC<QOFF>{}, IC<COFF>{}, IC<JOFF>{});
+    for_each_elem<ROW + E::NN, QOFF + E::NQ, COFF + E::NC, JOFF + E::NJ>(EList<R...>{}, f);
+}
+
+__host__ __device__ constexpr int dim1(int n) { return n > 0 ? n : 1; }
+
+template <int NX_, int NU_, int NY_, int NP_, class... Es>
+struct TpiCfg {
+    static constexpr int NX = NX_, NU = NU_, NY = NY_, NP = NP_;
+    static constexpr int NE = sizeof...(Es);
+    static constexpr int NN = (Es::NN + ... + 0);
+    static constexpr int NQ = (Es::NQ + ... + 0);
+    static constexpr int NC = (Es::NC + ... + 0);
+    static constexpr int NJ = (Es::NJ + ... + 0);
+    using Elems = EList<Es...>;
+    static constexpr int kinds[dim1(NE)] = {Es::KIND...};
+    // rows of the kernel-private state in RunArgs::ws
+    static constexpr int S_X = 0, S_LP = NX, S_LZ = NX + NP, S_MX = NX + NP + NN, S_ROWS = NX + NP + NN + NN * NP;
+};
+
+// shared model matrices, column-major (field for field ACME.jl:119-132)
+template <class C>
+struct TpiMats {
+    double a[dim1(C::NX * C::NX)], b[dim1(C::NX * C::NU)], c[dim1(C::NX * C::NN)], x0[dim1(C::NX)];
+    double dq[dim1(C::NP * C::NX)], eq[dim1(C::NP * C::NU)], pexp[dim1(C::NQ * C::NP)], q0[dim1(C::NQ)],
+        fq[dim1(C::NQ * C::NN)];
+    double dy[dim1(C::NY * C::NX)], ey[dim1(C::NY * C::NU)], fy[dim1(C::NY * C::NN)], y0[dim1(C::NY)];
+};
+
+struct SolverCfg {
+    double tol;
+    int maxiter;
+    int solver;
+};
+
+template <class C>
+struct TpiState {  // what persists from sample to sample
+    double x[dim1(C::NX)], lp[dim1(C::NP)], lz[dim1(C::NN)], Mx[dim1(C::NN * C::NP)];
+};
+
+// ---- small dense LU in registers: setlhs!/solve! (solvers.jl:46-132), fully unrolled ----
+template <int N>
+__device__ __forceinline__ bool lu_reg(double (&A)[dim1(N * N)], int (&piv)[dim1(N)]) {
+    bool ok = true;
+    static_for<0, N>([&](auto kk) {
+        constexpr int k = decltype(kk)::value;
+        int kp = k;
+        double amax = 0.0;
+        static_for<k, N>([&](auto ii) {
+            constexpr int i = decltype(ii)::value;
+            const double absi = fabs(A[k * N + i]);
+            if (absi > amax) { kp = i; amax = absi; }
+        });
+        piv[k] = kp;
+        static_for<k + 1, N>([&](auto ii) {
+            constexpr int i = decltype(ii)::value;
+            if (kp == i) {
+                static_for<0, N>([&](auto cc) {
+                    constexpr int c = decltype(cc)::value;
+                    const double t = A[c * N + k];
+                    A[c * N + k] = A[c * N + i];
+                    A[c * N + i] = t;
+                });
+            }
+        });
+        if (A[k * N + k] == 0.0) ok = false;  // exactly singular: the reference bails out (solvers.jl:84-86)
+        const double inv = 1.0 / A[k * N + k];
+        A[k * N + k] = inv;
+        static_for<k + 1, N>([&](auto ii) { A[k * N + decltype(ii)::value] *= inv; });
+        static_for<k + 1, N>([&](auto jj) {
+            constexpr int j = decltype(jj)::value;
+            const double akj = A[j * N + k];
+            static_for<k + 1, N>([&](auto ii) {
+                constexpr int i = decltype(ii)::value;
+                A[j * N + i] = fma(-A[k * N + i], akj, A[j * N + i]);
+            });
+        });
+    });
+    return ok;
+}
+
+template <int N>
+__device__ __forceinline__ void lu_solve_reg(const double (&A)[dim1(N * N)], const int (&piv)[dim1(N)],
+                                             double (&x)[dim1(N)]) {
+    static_for<0, N>([&](auto kk) {
+        constexpr int k = decltype(kk)::value;
+        static_for<k + 1, N>([&](auto ii) {
+            constexpr int i = decltype(ii)::value;
+            if (piv[k] == i) { const double t = x[k]; x[k] = x[i]; x[i] = t; }
+        });
+    });
+    static_for<0, N>([&](auto jj) {
+        constexpr int j = decltype(jj)::value;
+        static_for<j + 1, N>([&](auto ii) {
+            constexpr int i = decltype(ii)::value;
+            x[i] = fma(-A[j * N + i], x[j], x[i]);
+        });
+    });
+    static_for<0, N>([&](auto jr) {
+        constexpr int j = N - 1 - decltype(jr)::value;
+        x[j] = A[j * N + j] * x[j];
+        static_for<0, j>([&](auto ii) {
+            constexpr int i = decltype(ii)::value;
+            x[i] = fma(-A[j * N + i], x[j], x[i]);
+        });
+    });
+}
+
+// ---- model closures (ACME.jl:176-194, 236-252), compile-time shapes ----
+template <class C, class M>
+__device__ __forceinline__ void tpi_set_p(const M& m, const double (&p)[dim1(C::NP)], double (&pfull)[dim1(C::NQ)]) {
+    static_for<0, C::NQ>([&](auto ii) {
+        constexpr int i = decltype(ii)::value;
+        double acc = m.q0[i];
+        static_for<0, C::NP>([&](auto jj) {
+            constexpr int j = decltype(jj)::value;
+            acc = fma(m.pexp[j * C::NQ + i], p[j], acc);
+        });
+        pfull[i] = acc;
+    });
+}
+
+// evaluate!: returns max|res| (NaN if any residual is NaN); J column-major; jv kept for calc_Jp
+template <class C, class M>
+__device__ __forceinline__ double tpi_evaluate(const M& m, const double (&Cn)[dim1(C::NC)],
+                                               const double (&pfull)[dim1(C::NQ)], const double (&z)[dim1(C::NN)],
+                                               double (&res)[dim1(C::NN)], double (&jv)[dim1(C::NJ)],
+                                               double (&J)[dim1(C::NN * C::NN)], bool& Jfinite) {
+    double q[dim1(C::NQ)];
+    static_for<0, C::NQ>([&](auto ii) {
+        constexpr int i = decltype(ii)::value;
+        double acc = pfull[i];
+        static_for<0, C::NN>([&](auto jj) {
+            constexpr int j = decltype(jj)::value;
+            acc = fma(m.fq[j * C::NQ + i], z[j], acc);
+        });
+        q[i] = acc;
+    });
+    double resmax = 0.0, jsum = 0.0;
+    bool nan = false;
+    for_each_elem<0, 0, 0, 0>(typename C::Elems{}, [&](auto e, auto row, auto qoff, auto coff, auto joff) {
+        using E = decltype(e);
+        constexpr int ROW = decltype(row)::value, QOFF = decltype(qoff)::value, COFF = decltype(coff)::value,
+                      JOFF = decltype(joff)::value;
+        E::eval(&Cn[COFF], &q[QOFF], &res[ROW], &jv[JOFF]);
+        static_for<0, E::NJ>([&](auto kk) { jsum += fabs(jv[JOFF + decltype(kk)::value]); });
+        static_for<0, E::NN>([&](auto rr) {
+            constexpr int r = decltype(rr)::value;
+            const double ar = fabs(res[ROW + r]);
+            if (ar != ar) nan = true;
+            if (ar > resmax) resmax = ar;
+            static_for<0, C::NN>([&](auto cc) {
+                constexpr int c = decltype(cc)::value;
+                J[c * C::NN + ROW + r] =
+                    E::template row<r>(&jv[JOFF], [&](int k) { return m.fq[c * C::NQ + QOFF + k]; });
+            });
+        });
+    });
+    Jfinite = isfinite(jsum);
+    return nan ? NAN : resmax;
+}
+
+// Mx = LU \ (Jq*pexp)  (calc_Jp! ACME.jl:246-251 followed by the solve of solvers.jl:213)
+template <class C, class M>
+__device__ __forceinline__ void tpi_update_Mx(const M& m, const double (&jv)[dim1(C::NJ)],
+                                              const double (&LU)[dim1(C::NN * C::NN)],
+                                              const int (&piv)[dim1(C::NN)], double (&Mx)[dim1(C::NN * C::NP)]) {
+    static_for<0, C::NP>([&](auto cc) {
+        constexpr int c = decltype(cc)::value;
+        double col[dim1(C::NN)];
+        for_each_elem<0, 0, 0, 0>(typename C::Elems{}, [&](auto e, auto row, auto qoff, auto, auto joff) {
+            using E = decltype(e);
+            constexpr int ROW = decltype(row)::value, QOFF = decltype(qoff)::value, JOFF = decltype(joff)::value;
+            static_for<0, E::NN>([&](auto rr) {
+                constexpr int r = decltype(rr)::value;
+                col[ROW + r] = E::template row<r>(&jv[JOFF], [&](int k) { return m.pexp[c * C::NQ + QOFF + k]; });
+            });
+        });
+        lu_solve_reg<C::NN>(LU, piv, col);
+        static_for<0, C::NN>([&](auto ii) { Mx[c * C::NN + decltype(ii)::value] = col[decltype(ii)::value]; });
+    });
+}
+
+// set_extrapolation_origin(solver, p, z)  (solvers.jl:183-196)
+template <class C, class M>
+__device__ __forceinline__ void tpi_set_origin(const M& m, const double (&Cn)[dim1(C::NC)], TpiState<C>& S,
+                                               const double (&p)[dim1(C::NP)], const double (&z)[dim1(C::NN)]) {
+    double pfull[dim1(C::NQ)], res[dim1(C::NN)], jv[dim1(C::NJ)], J[dim1(C::NN * C::NN)];
+    int piv[dim1(C::NN)];
+    bool Jfin;
+    tpi_set_p<C>(m, p, pfull);
+    tpi_evaluate<C>(m, Cn, pfull, z, res, jv, J, Jfin);
+    lu_reg<C::NN>(J, piv);
+    tpi_update_Mx<C>(m, jv, J, piv, S.Mx);
+    static_for<0, C::NP>([&](auto i) { S.lp[decltype(i)::value] = p[decltype(i)::value]; });
+    static_for<0, C::NN>([&](auto i) { S.lz[decltype(i)::value] = z[decltype(i)::value]; });
+}
+
+// solve(::SimpleSolver, p)  (solvers.jl:207-236)
+template <class C, class M>
+__device__ __forceinline__ bool tpi_simple_solve(const M& m, const double (&Cn)[dim1(C::NC)], TpiState<C>& S,
+                                                 const double (&p)[dim1(C::NP)], double (&z)[dim1(C::NN)],
+                                                 const SolverCfg& sc, int& iters) {
+    double pfull[dim1(C::NQ)], res[dim1(C::NN)], jv[dim1(C::NJ)], J[dim1(C::NN * C::NN)];
+    int piv[dim1(C::NN)];
+    tpi_set_p<C>(m, p, pfull);
+    static_for<0, C::NN>([&](auto ii) {
+        constexpr int i = decltype(ii)::value;
+        double acc = S.lz[i];
+        static_for<0, C::NP>([&](auto jj) {
+            constexpr int j = decltype(jj)::value;
+            acc = fma(-S.Mx[j * C::NN + i], p[j] - S.lp[j], acc);
+        });
+        z[i] = acc;
+    });
+    bool converged = false;
+    for (iters = 1; iters <= sc.maxiter; iters++) {
+        bool Jfin;
+        const double resmax = tpi_evaluate<C>(m, Cn, pfull, z, res, jv, J, Jfin);
+        if (!isfinite(resmax) || !Jfin) return resmax < sc.tol;
+        if (!lu_reg<C::NN>(J, piv)) return resmax < sc.tol;
+        if (resmax < sc.tol) { converged = true; break; }
+        lu_solve_reg<C::NN>(J, piv, res);
+        static_for<0, C::NN>([&](auto i) { z[decltype(i)::value] -= res[decltype(i)::value]; });
+    }
+    if (iters > sc.maxiter) iters = sc.maxiter;
+    if (converged) {
+        tpi_update_Mx<C>(m, jv, J, piv, S.Mx);
+        static_for<0, C::NP>([&](auto i) { S.lp[decltype(i)::value] = p[decltype(i)::value]; });
+        static_for<0, C::NN>([&](auto i) { S.lz[decltype(i)::value] = z[decltype(i)::value]; });
+    }
+    return converged;
+}
+
+// everything the cold paths need, spilled to local memory on purpose
+template <class C>
+struct TpiCold {
+    TpiState<C> S;
+    double Cn[dim1(C::NC)];
+    double p[dim1(C::NP)];
+    double z[dim1(C::NN)];
+    double initz[dim1(C::NN)];
+    int iters;
+    int used_homotopy;
+};
+
+// solve(::CachingSolver, p) against the frozen cache (solvers.jl:347-373)
+template <class C, class M>
+__device__ __forceinline__ bool tpi_base_solve_cold(const M& m, TpiCold<C>& k, const double (&p)[dim1(C::NP)],
+                                                    const SolverCfg& sc, const DevSub& cache, int& iters) {
+    if (sc.solver == ACMEB200_SOLVER_HOMOTOPY_CACHING) {
+        double best = 0.0;
+        for (int i = 0; i < C::NP; i++) { const double d = p[i] - k.S.lp[i]; best = fma(d, d, best); }
+        double cp[dim1(C::NP)], cz[dim1(C::NN)];
+        bool take = false;
+        if (cache.cache_n > 0) {
+            const int idx = kd_nearest(cache, [&](int i) { return p[i]; }, best);
+            if (idx != 0) {
+                take = true;
+                for (int i = 0; i < C::NP; i++) cp[i] = cache.ps[(int64_t)(idx - 1) * C::NP + i];
+                for (int i = 0; i < C::NN; i++) cz[i] = cache.zs[(int64_t)(idx - 1) * C::NN + i];
+            }
+        } else {
+            double d0 = 0.0;
+            for (int i = 0; i < C::NP; i++) d0 = fma(p[i], p[i], d0);
+            if (d0 < best) {
+                take = true;
+                for (int i = 0; i < C::NP; i++) cp[i] = 0.0;
+                for (int i = 0; i < C::NN; i++) cz[i] = k.initz[i];
+            }
+        }
+        if (take) tpi_set_origin<C>(m, k.Cn, k.S, cp, cz);
+    }
+    return tpi_simple_solve<C>(m, k.Cn, k.S, p, k.z, sc, iters);
+}
+
+// cold entry: mode 0 = cache lookup + base solve, then homotopy if needed
+// (solve(::HomotopySolver, p), solvers.jl:268-296); mode 1 = the base solve has
+// already failed in the hot path, go straight to the homotopy.
+template <class C, class M>
+__device__ __noinline__ bool tpi_cold_solve(const M* mp, TpiCold<C>* kp, SolverCfg sc, const DevSub* cache,
+                                            int mode) {
+    const M& m = *mp;
+    TpiCold<C>& k = *kp;
+    bool conv = false;
+    int total = k.iters;
+    if (mode == 0) {
+        int it;
+        conv = tpi_base_solve_cold<C>(m, k, k.p, sc, *cache, it);
+        total = it;
+    }
+    k.used_homotopy = 0;
+    if (!conv && sc.solver != ACMEB200_SOLVER_SIMPLE) {
+        k.used_homotopy = 1;
+        double a = 0.5, best_a = 0.0;
+        double start_p[dim1(C::NP)], pa[dim1(C::NP)];
+        for (int i = 0; i < C::NP; i++) start_p[i] = k.S.lp[i];
+        while (best_a < 1) {
+            for (int i = 0; i < C::NP; i++) {
+                double v = start_p[i];
+                v *= (1 - a);
+                v += a * k.p[i];
+                pa[i] = v;
+            }
+            int it;
+            conv = tpi_base_solve_cold<C>(m, k, pa, sc, *cache, it);
+            total += it;
+            if (conv) {
+                best_a = a;
+                a = 1.0;
+            } else {
+                const double new_a = (a + best_a) / 2;
+                if (!(best_a < new_a && new_a < a)) break;
+                a = new_a;
+            }
+        }
+    }
+    k.iters = total;
+    return conv;
+}
+
+constexpr int TPI_T = 16;    // samples per staged tile
+constexpr int TPI_TPB = 64;  // threads per block (2 warps): small CTAs balance 148 SMs
+
+template <class C>
+constexpr size_t tpi_smem_bytes() {
+    return (size_t)(TPI_TPB / 32) * 32 * ((TPI_T * C::NU + 1) + (TPI_T * C::NY + 1)) * sizeof(double);
+}
+
+template <class C, bool PERINST>
+__global__ void __launch_bounds__(TPI_TPB) k_tpi(const __grid_constant__ TpiMats<C> Msh, const RunArgs a,
+                                                 const SolverCfg sc, const __grid_constant__ DevSub cache) {
+    constexpr int NX = C::NX, NU = C::NU, NY = C::NY, NN = C::NN, NP = C::NP;
+    constexpr int T = TPI_T, IW = T * NU, IS = IW + 1, OW = T * NY, OS = OW + 1;
+    extern __shared__ double smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double* tin = smem + (size_t)warp * 32 * (IS + OS);
+    double* tout = tin + 32 * IS;
+
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // launch-local instance
+    const int64_t wbase = t - lane;
+    const bool active = t < a.ninst;
+    const int64_t inst = a.inst0 + (active ? t : 0);
+
+    // matrices: shared constant-bank copy, or this instance's own copy in registers
+    TpiMats<C> Mown;
+    if constexpr (PERINST) {
+        const double* src = a.blob + inst * a.blob_stride;
+        double* dst = reinterpret_cast<double*>(&Mown);
+        for (int i = 0; i < (int)(sizeof(TpiMats<C>) / sizeof(double)); i++) dst[i] = 0.0;
+        // blob order == TpiMats field order with true (unpadded) lengths
+        int o = 0;
+        auto take = [&](double* f, int n) { for (int i = 0; i < n; i++) f[i] = __ldg(src + o + i); o += n; };
+        take(Mown.a, NX * NX); take(Mown.b, NX * NU); take(Mown.c, NX * NN); take(Mown.x0, NX);
+        take(Mown.dy, NY * NX); take(Mown.ey, NY * NU); take(Mown.fy, NY * NN); take(Mown.y0, NY);
+        take(Mown.dq, NP * NX); take(Mown.eq, NP * NU);
+        o += NP * NN;  // fqprev (single sub: unused)
+        take(Mown.pexp, C::NQ * NP); take(Mown.q0, C::NQ); take(Mown.fq, C::NQ * NN);
+    }
+    const TpiMats<C>& m = PERINST ? Mown : Msh;
+
+    double Cn[dim1(C::NC)];
+    static_for<0, C::NC>([&](auto i) { Cn[decltype(i)::value] = a.consts[(int64_t)decltype(i)::value * a.ld + inst]; });
+    TpiState<C> S;
+    double* st = a.ws + inst;
+
+    if (a.init) {
+        if (!active) return;
+        static_for<0, NX>([&](auto i) { S.x[decltype(i)::value] = 0.0; });
+        if constexpr (NN > 0) {
+            double p0[dim1(NP)], z0[dim1(NN)];
+            static_for<0, NP>([&](auto i) { p0[decltype(i)::value] = 0.0; });
+            static_for<0, NN>([&](auto i) { z0[decltype(i)::value] = a.initz[(int64_t)decltype(i)::value * a.ld + inst]; });
+            tpi_set_origin<C>(m, Cn, S, p0, z0);
+        }
+        static_for<0, NX>([&](auto i) { st[(int64_t)(C::S_X + decltype(i)::value) * a.ld] = S.x[decltype(i)::value]; });
+        static_for<0, NP>([&](auto i) { st[(int64_t)(C::S_LP + decltype(i)::value) * a.ld] = S.lp[decltype(i)::value]; });
+        static_for<0, NN>([&](auto i) { st[(int64_t)(C::S_LZ + decltype(i)::value) * a.ld] = S.lz[decltype(i)::value]; });
+        static_for<0, NN * NP>([&](auto i) { st[(int64_t)(C::S_MX + decltype(i)::value) * a.ld] = S.Mx[decltype(i)::value]; });
+        a.status[inst] = 0;
+        a.first_fail[inst] = -1;
+        return;
+    }
+
+    static_for<0, NX>([&](auto i) { S.x[decltype(i)::value] = st[(int64_t)(C::S_X + decltype(i)::value) * a.ld]; });
+    static_for<0, NP>([&](auto i) { S.lp[decltype(i)::value] = st[(int64_t)(C::S_LP + decltype(i)::value) * a.ld]; });
+    static_for<0, NN>([&](auto i) { S.lz[decltype(i)::value] = st[(int64_t)(C::S_LZ + decltype(i)::value) * a.ld]; });
+    static_for<0, NN * NP>([&](auto i) { S.Mx[decltype(i)::value] = st[(int64_t)(C::S_MX + decltype(i)::value) * a.ld]; });
+
+    uint32_t status = active ? a.status[inst] : 0u;
+    bool dead = !active || (status & ACMEB200_STATUS_NONFINITE);
+    const bool shared_u = (a.u_stride == 0);
+    const bool cold_cache = (sc.solver == ACMEB200_SOLVER_HOMOTOPY_CACHING);
+    unsigned long long n_iters = 0, hpack = 0;
+    unsigned int hist[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    unsigned int n_samples = 0, n_homotopy = 0, n_notconv = 0;
+    long long first_fail = -1;
+
+    for (int64_t n0 = 0; n0 < a.N; n0 += T) {
+        const int cnt = (int)((a.N - n0) < T ? (a.N - n0) : T);
+        // ---- stage the input tile: 32 instances x T samples, coalesced row segments
+        if (!shared_u && NU > 0) {
+            __syncwarp();
+#pragma unroll 4
+            for (int f = lane; f < 32 * IW; f += 32) {
+                const int r = f / dim1(IW), col = f % dim1(IW);
+                const int64_t ti = wbase + r;
+                if (ti < a.ninst && col < cnt * NU)
+                    tin[r * IS + col] = __ldcs(a.U + ti * a.u_stride + n0 * NU + col);
+            }
+            __syncwarp();
+        }
+        for (int tt = 0; tt < cnt; tt++) {
+            double u[dim1(NU)], y[dim1(NY)], zall[dim1(NN)];
+            static_for<0, NU>([&](auto kk) {
+                constexpr int k = decltype(kk)::value;
+                u[k] = shared_u ? __ldg(a.U + (n0 + tt) * NU + k) : tin[lane * IS + tt * NU + k];
+            });
+            if (!dead) {
+                if constexpr (NN > 0) {
+                    // p = dq*x + eq*u   (ACME.jl:678-686)
+                    double p[dim1(NP)];
+                    static_for<0, NP>([&](auto ii) {
+                        constexpr int i = decltype(ii)::value;
+                        double acc = 0.0;
+                        static_for<0, NX>([&](auto jj) { acc = fma(m.dq[decltype(jj)::value * NP + i], S.x[decltype(jj)::value], acc); });
+                        static_for<0, NU>([&](auto jj) { acc = fma(m.eq[decltype(jj)::value * NP + i], u[decltype(jj)::value], acc); });
+                        p[i] = acc;
+                    });
+                    int iters = 0;
+                    bool conv;
+                    bool homotopy = false;
+                    bool need_cold = false;
+                    int cold_mode = 0;
+                    if (cold_cache) {
+                        // cheap inline test for the common case "the origin is the nearest start point"
+                        if (cache.cache_n > 0) {
+                            need_cold = true;
+                        } else {
+                            double best = 0.0, d0 = 0.0;
+                            static_for<0, NP>([&](auto ii) {
+                                constexpr int i = decltype(ii)::value;
+                                const double d = p[i] - S.lp[i];
+                                best = fma(d, d, best);
+                                d0 = fma(p[i], p[i], d0);
+                            });
+                            need_cold = d0 < best;
+                        }
+                    }
+                    if (!need_cold) {
+                        conv = tpi_simple_solve<C>(m, Cn, S, p, zall, sc, iters);
+                        if (!conv && sc.solver != ACMEB200_SOLVER_SIMPLE) { need_cold = true; cold_mode = 1; }
+                    }
+                    if (need_cold) {
+                        TpiCold<C> k;
+                        k.S = S;
+                        static_for<0, C::NC>([&](auto i) { k.Cn[decltype(i)::value] = Cn[decltype(i)::value]; });
+                        static_for<0, NP>([&](auto i) { k.p[decltype(i)::value] = p[decltype(i)::value]; });
+                        static_for<0, NN>([&](auto i) {
+                            k.z[decltype(i)::value] = zall[decltype(i)::value];
+                            k.initz[decltype(i)::value] = a.initz[(int64_t)decltype(i)::value * a.ld + inst];
+                        });
+                        k.iters = iters;
+                        conv = tpi_cold_solve<C>(&m, &k, sc, &cache, cold_mode);
+                        homotopy = k.used_homotopy != 0;
+                        S = k.S;
+                        static_for<0, NN>([&](auto i) { zall[decltype(i)::value] = k.z[decltype(i)::value]; });
+                        iters = k.iters;
+                    }
+                    n_iters += (unsigned)iters;
+                    n_homotopy += homotopy ? 1u : 0u;
+                    {
+                        int bin = iters < 1 ? 1 : iters;
+                        if (bin > ACMEB200_HIST_BINS) bin = ACMEB200_HIST_BINS;
+                        if (bin <= 8) hpack += 1ull << (8 * (bin - 1));
+                        else atomicAdd(&a.stats->iter_hist[bin - 1], 1ull);
+                    }
+                    if (!conv) {
+                        if (first_fail < 0) first_fail = a.n_done + n0 + tt;
+                        bool fin = true;
+                        static_for<0, NN>([&](auto i) { fin = fin && isfinite(zall[decltype(i)::value]); });
+                        if (fin) { status |= ACMEB200_STATUS_NOT_CONVERGED; n_notconv++; }
+                        else { status |= ACMEB200_STATUS_NONFINITE; dead = true; }
+                    }
+                }
+            }
+            if (!dead) {
+                // y = y0 + dy*x + ey*u + fy*z   (ACME.jl:699-706, x before the update)
+                static_for<0, NY>([&](auto ii) {
+                    constexpr int i = decltype(ii)::value;
+                    double acc = m.y0[i];
+                    static_for<0, NX>([&](auto jj) { acc = fma(m.dy[decltype(jj)::value * NY + i], S.x[decltype(jj)::value], acc); });
+                    static_for<0, NU>([&](auto jj) { acc = fma(m.ey[decltype(jj)::value * NY + i], u[decltype(jj)::value], acc); });
+                    static_for<0, NN>([&](auto jj) { acc = fma(m.fy[decltype(jj)::value * NY + i], zall[decltype(jj)::value], acc); });
+                    y[i] = acc;
+                });
+                // x = x0 + a*x + b*u + c*z      (ACME.jl:708-714)
+                double xn[dim1(NX)];
+                static_for<0, NX>([&](auto ii) {
+                    constexpr int i = decltype(ii)::value;
+                    double acc = m.x0[i];
+                    static_for<0, NX>([&](auto jj) { acc = fma(m.a[decltype(jj)::value * NX + i], S.x[decltype(jj)::value], acc); });
+                    static_for<0, NU>([&](auto jj) { acc = fma(m.b[decltype(jj)::value * NX + i], u[decltype(jj)::value], acc); });
+                    static_for<0, NN>([&](auto jj) { acc = fma(m.c[decltype(jj)::value * NX + i], zall[decltype(jj)::value], acc); });
+                    xn[i] = acc;
+                });
+                static_for<0, NX>([&](auto i) { S.x[decltype(i)::value] = xn[decltype(i)::value]; });
+                n_samples++;
+            } else {
+                static_for<0, NY>([&](auto i) { y[decltype(i)::value] = NAN; });
+            }
+            static_for<0, NY>([&](auto kk) { tout[lane * OS + tt * NY + decltype(kk)::value] = y[decltype(kk)::value]; });
+        }
+        // fold the packed per-tile histogram (<= 16 per 8-bit field) into the 32-bit bins
+        static_for<0, 8>([&](auto i) { hist[decltype(i)::value] += (unsigned)((hpack >> (8 * decltype(i)::value)) & 0xffu); });
+        hpack = 0;
+        // ---- write the output tile back, coalesced
+        if (NY > 0) {
+            __syncwarp();
+#pragma unroll 4
+            for (int f = lane; f < 32 * OW; f += 32) {
+                const int r = f / dim1(OW), col = f % dim1(OW);
+                const int64_t ti = wbase + r;
+                if (ti < a.ninst && col < cnt * NY)
+                    __stcs(a.Y + ti * a.y_stride + n0 * NY + col, tout[r * OS + col]);
+            }
+        }
+    }
+
+    if (active) {
+        static_for<0, NX>([&](auto i) { st[(int64_t)(C::S_X + decltype(i)::value) * a.ld] = S.x[decltype(i)::value]; });
+        static_for<0, NP>([&](auto i) { st[(int64_t)(C::S_LP + decltype(i)::value) * a.ld] = S.lp[decltype(i)::value]; });
+        static_for<0, NN>([&](auto i) { st[(int64_t)(C::S_LZ + decltype(i)::value) * a.ld] = S.lz[decltype(i)::value]; });
+        static_for<0, NN * NP>([&](auto i) { st[(int64_t)(C::S_MX + decltype(i)::value) * a.ld] = S.Mx[decltype(i)::value]; });
+        a.status[inst] = status;
+        if (first_fail >= 0 && a.first_fail[inst] < 0) a.first_fail[inst] = first_fail;
+    }
+    // warp-reduce the counters, one set of atomics per warp
+    const unsigned full = 0xffffffffu;
+    unsigned s_samples = __reduce_add_sync(full, n_samples);
+    unsigned s_hom = __reduce_add_sync(full, n_homotopy);
+    unsigned s_nc = __reduce_add_sync(full, n_notconv);
+    unsigned it_lo = __reduce_add_sync(full, (unsigned)(n_iters & 0xffffu));
+    unsigned it_hi = __reduce_add_sync(full, (unsigned)(n_iters >> 16));
+    unsigned hsum[8];
+    static_for<0, 8>([&](auto i) { hsum[decltype(i)::value] = __reduce_add_sync(full, hist[decltype(i)::value]); });
+    if (lane == 0) {
+        if (s_samples) {
+            atomicAdd(&a.stats->samples, (unsigned long long)s_samples);
+            if (NN > 0) atomicAdd(&a.stats->solves, (unsigned long long)s_samples);
+        }
+        const unsigned long long its = (unsigned long long)it_lo + ((unsigned long long)it_hi << 16);
+        if (its) atomicAdd(&a.stats->newton_iters, its);
+        if (s_hom) atomicAdd(&a.stats->homotopy_solves, (unsigned long long)s_hom);
+        if (s_nc) atomicAdd(&a.stats->not_converged, (unsigned long long)s_nc);
+        static_for<0, 8>([&](auto i) {
+            if (hsum[decltype(i)::value]) atomicAdd(&a.stats->iter_hist[decltype(i)::value], (unsigned long long)hsum[decltype(i)::value]);
+        });
+    }
+}
+
+}  // namespace acme

@@ -1,0 +1,244 @@
+"""``ModelRunner`` / ``run!`` over the CUDA library.
+
+Mirrors /root/reference/src/ACME.jl:567-664: ``run_(model, u)`` is
+``run!(model, u)``, ``ModelRunner`` pre-allocates (here: uploads the model and
+keeps the per-instance state on the device), ``run_(runner, y, u)`` is the
+in-place method.  :class:`BatchRunner` is the batched extension: B independent
+instances of one circuit (swept element parameters / matrices, or many inputs),
+``U`` of shape ``(nu, N, B)`` and ``Y`` of shape ``(ny, N, B)`` -- instance
+slowest, so each instance's block is exactly the reference's ``nu x N`` matrix.
+
+Nothing here computes samples on the CPU: the only implementation of the
+per-sample path is the CUDA library; without it (or without a device) the
+constructors raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import warnings
+from typing import Optional
+
+import numpy as np
+
+from . import _abi
+from ._abi import make_desc, Stats
+from ._lib import check, lib
+
+WARN_NOT_CONVERGED = "Failed to converge while solving non-linear equation."       # ACME.jl:690
+ERR_NONFINITE = "Failed to converge while solving non-linear equation, got non-finite result."  # ACME.jl:692
+
+
+class DimensionMismatch(ValueError):
+    pass
+
+
+def _is_torch_cuda(t):
+    return hasattr(t, "is_cuda") and t.is_cuda
+
+
+class BatchRunner:
+    """B instances of ``model`` resident on the current CUDA device.
+
+    ``first``/``count`` select the slice of instances this runner owns (for
+    sharding one descriptor over several GPUs); per-instance arrays are always
+    given for the full batch.
+    """
+
+    def __init__(self, model, batch: int = 1, *, first: int = 0, count: Optional[int] = None,
+                 kernel: str = "auto", **desc_kw):
+        self.model = model
+        self.batch_total = batch
+        self.first = first
+        self.batch = batch - first if count is None else count
+        self._holder = make_desc(model, batch, **desc_kw)
+        h = C.c_void_p()
+        check(lib().acmeb200_model_create(C.byref(self._holder.desc), first, self.batch, C.byref(h)))
+        self._h = h
+        if kernel == "generic":
+            check(lib().acmeb200_set_kernel(self._h, 1))
+        elif kernel != "auto":
+            raise ValueError("kernel must be 'auto' or 'generic'")
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().acmeb200_model_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ info
+    @property
+    def kernel_name(self) -> str:
+        return lib().acmeb200_kernel_name(self._h).decode()
+
+    @property
+    def launch_count(self) -> int:
+        return int(lib().acmeb200_launch_count(self._h))
+
+    def stats(self) -> dict:
+        s = Stats()
+        check(lib().acmeb200_get_stats(self._h, C.byref(s)))
+        return s.as_dict()
+
+    def status(self):
+        st = np.zeros(self.batch, dtype=np.uint32)
+        ff = np.zeros(self.batch, dtype=np.int64)
+        check(lib().acmeb200_get_status(self._h, st.ctypes.data_as(C.c_void_p), ff.ctypes.data_as(C.c_void_p)))
+        return st, ff
+
+    def reset(self):
+        check(lib().acmeb200_reset(self._h))
+
+    @property
+    def x(self) -> np.ndarray:
+        """model.x of every instance, shape (nx, B)"""
+        out = np.zeros(max(self.model.nx * self.batch, 1))
+        check(lib().acmeb200_get_state(self._h, out.ctypes.data_as(C.c_void_p)))
+        return out[:self.model.nx * self.batch].reshape((self.model.nx, self.batch), order="F")
+
+    @x.setter
+    def x(self, val):
+        v = np.asarray(val, dtype=np.float64).reshape(self.model.nx, -1)
+        v = np.ascontiguousarray(np.broadcast_to(v, (self.model.nx, self.batch)).ravel(order="F"))
+        if v.size:
+            check(lib().acmeb200_set_state(self._h, v.ctypes.data_as(C.c_void_p), self.model.nx))
+
+    # ------------------------------------------------------------------ run
+    def _check_sizes(self, u_rows, u_cols, y_rows=None, y_cols=None):
+        """checkiosizes (ACME.jl:625-635)"""
+        m = self.model
+        if u_rows != m.nu:
+            raise DimensionMismatch(f"input matrix has {u_rows} rows, but model has {m.nu} inputs")
+        if y_rows is not None and y_rows != m.ny:
+            raise DimensionMismatch(f"output matrix has {y_rows} rows, but model has {m.ny} outputs")
+        if y_cols is not None and u_cols != y_cols:
+            raise DimensionMismatch(f"input matrix has {u_cols} columns, output matrix has {y_cols} columns")
+
+    def run(self, u, y=None, *, stream=None, check_status: bool = True):
+        """``run!`` for all instances.
+
+        u: numpy array (host) or torch CUDA tensor (device), shape (nu, N) -- one
+        input shared by all instances -- or (nu, N, B) in Julia (column-major)
+        layout, i.e. ``u[:, :, b]`` contiguous per instance.  Torch tensors must
+        be float64 with that memory layout: shape (B, N, nu) C-contiguous is the
+        same bytes and is accepted as such.
+        Returns y with the matching convention.
+        """
+        m = self.model
+        if _is_torch_cuda(u):
+            return self._run_torch(u, y, stream, check_status)
+        u = np.asarray(u, dtype=np.float64)
+        if u.ndim == 2:
+            N = u.shape[1]
+            self._check_sizes(u.shape[0], N)
+            ubuf = np.ascontiguousarray(u.ravel(order="F"))
+            ustride = 0
+        elif u.ndim == 3:
+            N = u.shape[1]
+            self._check_sizes(u.shape[0], N)
+            if u.shape[2] != self.batch:
+                raise DimensionMismatch(f"input has {u.shape[2]} instances, runner has {self.batch}")
+            ubuf = np.ascontiguousarray(u.ravel(order="F"))
+            ustride = m.nu * N
+        else:
+            raise DimensionMismatch("u must be (nu, N) or (nu, N, B)")
+        if y is None:
+            ybuf = np.empty(max(m.ny * N * self.batch, 1))
+        else:
+            if y.shape[:2] != (m.ny, N):
+                self._check_sizes(u.shape[0], N, y.shape[0], y.shape[1])
+            if not (y.flags.f_contiguous and y.dtype == np.float64):
+                raise ValueError("y must be a Fortran-contiguous float64 array")
+            ybuf = y.reshape(-1, order="F") if y.size else np.empty(1)
+        if ubuf.size == 0:
+            ubuf = np.zeros(1)
+        check(lib().acmeb200_run(self._h, ubuf.ctypes.data_as(C.c_void_p), ustride,
+                                 ybuf.ctypes.data_as(C.c_void_p), m.ny * N, N, 0, None))
+        if check_status:
+            self.raise_for_status()
+        if y is not None:
+            return y
+        return ybuf[:m.ny * N * self.batch].reshape((m.ny, N, self.batch), order="F")
+
+    def _run_torch(self, u, y, stream, check_status):
+        import torch
+        m = self.model
+        if u.dtype != torch.float64 or not u.is_contiguous():
+            raise ValueError("device input must be a contiguous float64 tensor")
+        # torch layout: (N, nu) shared or (B, N, nu), C-contiguous == Julia (nu, N[, B])
+        if u.dim() == 2:
+            N, nu = u.shape
+            ustride = 0
+        elif u.dim() == 3:
+            B, N, nu = u.shape
+            if B != self.batch:
+                raise DimensionMismatch(f"input has {B} instances, runner has {self.batch}")
+            ustride = N * nu
+        else:
+            raise DimensionMismatch("device u must be (N, nu) or (B, N, nu)")
+        self._check_sizes(nu, N)
+        if y is None:
+            y = torch.empty((self.batch, N, m.ny), dtype=torch.float64, device=u.device)
+        elif tuple(y.shape) != (self.batch, N, m.ny) or y.dtype != torch.float64 or not y.is_contiguous():
+            raise DimensionMismatch(f"device y must be a contiguous float64 tensor of shape {(self.batch, N, m.ny)}")
+        s = stream if stream is not None else torch.cuda.current_stream(u.device)
+        check(lib().acmeb200_run(self._h, C.c_void_p(u.data_ptr()), ustride, C.c_void_p(y.data_ptr()),
+                                 N * m.ny, N, _abi.U_DEVICE | _abi.Y_DEVICE, C.c_void_p(s.cuda_stream)))
+        if check_status:
+            self.raise_for_status()
+        return y
+
+    def run_host_pinned(self, u_ptr: int, ustride: int, y_ptr: int, N: int):
+        """raw-pointer host run (used by bench.py for the end-to-end leg with pinned torch buffers)"""
+        check(lib().acmeb200_run(self._h, C.c_void_p(u_ptr), ustride, C.c_void_p(y_ptr),
+                                 self.model.ny * N, N, 0, None))
+
+    def raise_for_status(self):
+        """Re-raises the reference's failure semantics (ACME.jl:688-694)."""
+        st, _ = self.status()
+        if (st & _abi.STATUS_NONFINITE).any():
+            raise RuntimeError(ERR_NONFINITE)
+        if (st & _abi.STATUS_NOT_CONVERGED).any():
+            warnings.warn(WARN_NOT_CONVERGED)
+
+
+class ModelRunner(BatchRunner):
+    """``ModelRunner(model, showprogress)`` (ACME.jl:570-604) -- a batch of one."""
+
+    def __init__(self, model, showprogress: bool = False, **kw):
+        super().__init__(model, 1, **kw)
+        self.showprogress = showprogress
+        self.x = model.x
+
+
+def run_(target, *args, showprogress=False, **kw):
+    """``run!`` (ACME.jl:567, 619, 650/658).
+
+    run_(model, u)        -> y, model.x is advanced
+    run_(runner, u)       -> y
+    run_(runner, y, u)    -> fills y in place
+    """
+    if isinstance(target, BatchRunner):
+        runner = target
+        if len(args) == 1:
+            y = runner.run(args[0], **kw)
+        elif len(args) == 2:
+            y = runner.run(args[1], args[0], **kw)
+        else:
+            raise TypeError("run_(runner, [y,] u)")
+        if isinstance(runner, ModelRunner) and hasattr(y, "ndim") and y.ndim == 3:
+            y = y[:, :, 0]
+        if isinstance(runner, ModelRunner):
+            runner.model.x = runner.x[:, 0].copy()
+        return y
+    model = target
+    (u,) = args
+    runner = ModelRunner(model, showprogress, **kw)
+    try:
+        return run_(runner, u)
+    finally:
+        runner.close()

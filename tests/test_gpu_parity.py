@@ -1,0 +1,423 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle and the
+reference's golden vectors / known-answer tests.  Needs a GPU: ``-m gpu``.
+
+Tolerance (north_star: 1e-6 relative on probe outputs; relative error is
+undefined at zero crossings, so the reference magnitude is floored at 1e-3 of
+the waveform's peak -- SURVEY.md section 7):
+    |y - y_ref| <= 1e-6 * max(|y_ref|, 1e-3 * max|y_ref|)
+"""
+import math
+import warnings
+
+import numpy as np
+import pytest
+
+import acme_jl_b200 as A
+from acme_jl_b200 import BatchRunner, ModelRunner, examples as ex, run_
+from oracle.oracle import OracleModel
+
+import cases
+
+pytestmark = pytest.mark.gpu
+
+KERNELS = ["auto", "generic"]
+H = "HomotopySolver{SimpleSolver}"
+HC = "HomotopySolver{CachingSolver{SimpleSolver}}"
+
+
+def assert_parity(y, yref, rtol=1e-6):
+    y = np.asarray(y); yref = np.asarray(yref)
+    assert y.shape == yref.shape
+    peak = np.max(np.abs(yref)) if yref.size else 0.0
+    scale = np.maximum(np.abs(yref), 1e-3 * peak)
+    err = np.abs(y - yref)
+    bad = err > rtol * scale + 1e-300
+    assert not bad.any(), f"max rel err {np.max(err / np.maximum(scale, 1e-300)):.3e}"
+
+
+def gpu_run(model, u, kernel="auto", **kw):
+    r = BatchRunner(model, 1, kernel=kernel, **kw)
+    try:
+        return r.run(np.asarray(u, dtype=float))[:, :, 0]
+    finally:
+        r.close()
+
+
+def cpu_run(model, u, **kw):
+    return OracleModel(model, 1, **kw).run(np.asarray(u, dtype=float))[:, :, 0]
+
+
+# ------------------------------------------------------------------ golden vectors
+@pytest.mark.parametrize("kernel", KERNELS)
+@pytest.mark.parametrize("solver", [H, HC])
+def test_G1_diodeclipper_doctest(kernel, solver):
+    """docs/src/gettingstarted.md:106-113"""
+    y = gpu_run(ex.diodeclipper(), cases.sine(), kernel, solver=solver)
+    assert y.shape == (1, 44100) and y[0, 0] == 0.0
+    for got, want in zip(y[0, 1:4], (0.0275964, 0.0990996, 0.195777)):
+        assert f"{got:.6g}" == f"{want:.6g}"
+    for got, want in zip(y[0, -3:], (-0.537508, -0.462978, -0.36521)):
+        assert f"{got:.6g}" == f"{want:.6g}"
+
+
+def test_G2_rc_ladder_doctest():
+    """docs/src/ug.md:107-114"""
+    m = A.DiscreteModel(cases.rc_ladder(), 1 / 44100)
+    u = np.zeros((1, 100)); u[0, 0] = 1
+    y = gpu_run(m, u)
+    for got, want in zip(y[0, :3], (1.83357e-8, 3.1622e-7, 2.59861e-6)):
+        assert f"{got:.6g}" == f"{want:.6g}"
+    for got, want in zip(y[0, -3:], (0.00465423, 0.00459275, 0.00453208)):
+        assert f"{got:.6g}" == f"{want:.6g}"
+
+
+# ------------------------------------------------------------------ example circuits vs oracle
+EXAMPLES = {
+    "diodeclipper": (ex.diodeclipper, lambda n: cases.sine(n)),
+    "sallenkey": (ex.sallenkey, lambda n: cases.sine(n)),
+    "birdie08": (lambda: ex.birdie(vol=0.8), lambda n: cases.sine(n)),
+    "birdie": (ex.birdie, lambda n: np.vstack([cases.sine(n), np.linspace(1, 0, n)])),
+    "superover_fixed": (lambda: ex.superover(1.0, 1.0, 1.0), lambda n: cases.sine(n)),
+    "superover": (ex.superover, lambda n: np.vstack([cases.sine(n), np.linspace(1, 0, n), np.linspace(0, 1, n), np.linspace(1, 0, n)])),
+    "superover_simplified": (lambda: A.DiscreteModel(ex.superover_circuit(vb_source=True), 1 / 44100),
+                             lambda n: np.vstack([cases.sine(n), np.linspace(1, 0, n), np.linspace(0, 1, n), np.linspace(1, 0, n)])),
+}
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+@pytest.mark.parametrize("name", list(EXAMPLES))
+def test_examples_match_oracle(name, kernel):
+    mk, mu = EXAMPLES[name]
+    m = mk()
+    n = 4410 if "superover" not in name else 1000
+    u = mu(n)
+    yref = cpu_run(m, u, solver=H)
+    r = BatchRunner(m, 1, kernel=kernel, solver=H)
+    y = r.run(u)[:, :, 0]
+    assert_parity(y, yref)
+    # identical start-point logic -> (nearly) identical Newton iteration counts
+    o = OracleModel(m, 1, solver=H); o.run(u)
+    so, sg = o.stats(), r.stats()
+    assert sg["samples"] == so["samples"] == n
+    assert abs(sg["newton_iters"] - so["newton_iters"]) <= max(3, 0.002 * so["newton_iters"])
+    assert sg["homotopy_solves"] == so["homotopy_solves"]
+    if kernel == "auto" and name in ("diodeclipper", "sallenkey", "birdie08", "birdie"):
+        assert r.kernel_name.startswith("tpi<")
+    r.close()
+
+
+def test_examples_steady_state_run():
+    """checksteady! (runtests.jl:664-671) on the GPU"""
+    for m in (ex.sallenkey(), ex.diodeclipper(), ex.birdie(vol=0.8), ex.superover(1.0, 1.0, 1.0)):
+        xs = m.steadystate_()
+        r = ModelRunner(m, tol=1e-13)
+        run_(r, np.zeros((m.nu, 1)))
+        assert np.allclose(r.x[:, 0], xs)
+        r.close()
+
+
+# ------------------------------------------------------------------ known-answer tests of runtests.jl
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_K3_homotopy(kernel):
+    """runtests.jl:207-219"""
+    rng = np.random.default_rng(3)
+    for _ in range(5):
+        m = cases.test_quad_model()
+        r = BatchRunner(m, 1, kernel=kernel)
+        r.run(np.array([[-0.5 + rng.random()]]))
+        assert r.status()[0][0] == 0
+        with pytest.warns(UserWarning, match="Failed to converge"):
+            r.run(np.array([[1.5 + rng.random()]]))
+        r.close()
+
+
+def test_K4_resistor_diode():
+    c, v_d = cases.resistor_diode()
+    assert np.isclose(gpu_run(A.DiscreteModel(c, 1), np.zeros((0, 1)))[0, 0], v_d)
+
+
+def test_empty_circuits():
+    """runtests.jl:54-66"""
+    assert run_(A.DiscreteModel(A.circuit([]), 1), np.zeros((0, 20))).shape == (0, 20)
+
+
+def test_K5_failure_semantics():
+    """runtests.jl:170-183"""
+    m = A.DiscreteModel(cases.no_solution(), 1)
+    y = run_(m, np.array([[1.0, 1.0]]))
+    assert y.shape == (1, 2) and y[0, 0] == y[0, 1]
+    with pytest.raises(RuntimeError, match="got non-finite result"):
+        run_(A.DiscreteModel(cases.no_solution(), 1), np.array([[np.inf]]))
+    with pytest.warns(UserWarning, match="Failed to converge while solving non-linear equation."):
+        y = run_(A.DiscreteModel(cases.no_solution(), 1), np.array([[-1.0]]))
+    assert y.shape == (1, 1)
+
+
+def test_io_size_checks():
+    """checkiosizes, ACME.jl:625-635"""
+    r = ModelRunner(ex.diodeclipper())
+    with pytest.raises(A.DimensionMismatch, match="input matrix has 2 rows, but model has 1 inputs"):
+        run_(r, np.zeros((2, 10)))
+    with pytest.raises(A.DimensionMismatch, match="output matrix has 2 rows, but model has 1 outputs"):
+        run_(r, np.zeros((2, 10), order="F"), np.zeros((1, 10)))
+    with pytest.raises(A.DimensionMismatch, match="input matrix has 10 columns, output matrix has 11 columns"):
+        run_(r, np.zeros((1, 11), order="F"), np.zeros((1, 10)))
+    r.close()
+
+
+@pytest.mark.parametrize("dec", [False, True])
+def test_K6_decomposition(dec):
+    want = 1e-12 * (math.exp(1 / 25e-3) - 1)
+    y = gpu_run(A.DiscreteModel(cases.three_diodes(), 1, decompose_nonlinearity=dec), np.array([[2.0], [1.0]]))
+    assert np.isclose(y[0, 0], want) and np.isclose(y[1, 0], want)
+
+
+@pytest.mark.parametrize("typ", ["npn", "pnp"])
+def test_K7_bjt_ebers_moll(typ):
+    out = gpu_run(A.DiscreteModel(cases.bjt_circuit(typ), 1), cases.bjt_input(typ))
+    if typ == "pnp":
+        out = -out
+    ie, ic = cases.bjt_expected(out)
+    assert np.allclose(out[2], ie, rtol=0, atol=1e-10) and np.allclose(out[3], ic, rtol=0, atol=1e-10)
+
+
+GP = [dict(ile=ile, ilc=ilc, ηcl=ηcl, ηel=ηel, vaf=vaf, var=var, ikf=ikf, ikr=ikr)
+      for ile in (0, 50e-9) for ilc in (0, 100e-9) for ηcl in (1.1, 1.2) for ηel in (1.0, 1.1)
+      for vaf in (math.inf, 10) for var in (math.inf, 50) for ikf in (math.inf, 50e-3)
+      for ikr in (math.inf, 500e-3)]
+
+
+@pytest.mark.parametrize("typ", ["npn", "pnp"])
+def test_K7_bjt_gummel_poon(typ):
+    """runtests.jl:513-546: all 2^8 combinations in ONE batched run (per-instance parameters)"""
+    base = A.DiscreteModel(cases.bjt_circuit(typ), 1)
+    B = len(GP)
+    params = np.zeros((14, B))
+    for b, kw in enumerate(GP):
+        mb = A.DiscreteModel(cases.bjt_circuit(typ, **kw), 1)
+        params[:, b] = mb.subs[0].elems[0][0].params
+        assert np.array_equal(mb.subs[0].fq, base.subs[0].fq)  # only the closure parameters differ
+    r = BatchRunner(base, B, params=[params])
+    out = r.run(cases.bjt_input(typ))
+    r.close()
+    for b, kw in enumerate(GP):
+        o = out[:, :, b] if typ == "npn" else -out[:, :, b]
+        ie, ic = cases.bjt_expected(o, **kw)
+        assert np.allclose(o[2], ie, rtol=0, atol=1e-10), kw
+        assert np.allclose(o[3], ic, rtol=0, atol=1e-10), kw
+
+
+@pytest.mark.parametrize("typ,pol", [("n", 1), ("p", -1)])
+def test_K8_mosfet(typ, pol):
+    m = A.DiscreteModel(cases.mosfet_circuit(typ, vt=1, α=1e-4), 1)
+    y = gpu_run(m, pol * np.array([[0, 1, 2, 2, 2], [5, 5, 0.5, 1, 1.5]]))
+    want = pol * np.array([0, 0, 1e-4 * (1 - 0.5 / 2) * 0.5, 1e-4 * (1 - 1 / 2) * 1, 1e-4 / 2 * 1 ** 2])
+    assert np.allclose(y[0], want, rtol=1e-15, atol=0)
+    for α in (1e-4, (0.0205, -0.0017)):
+        for vt in (1, (1.2078, 0.3238), (-1.2454, -0.199, -0.0483)):
+            m = A.DiscreteModel(cases.mosfet_circuit(typ, vt=vt, α=α, λ=0.05), 1)
+            g = np.array([[vgs, vds] for vgs in np.linspace(0, 5, 10) for vds in np.linspace(0, 5, 10)]).T
+            r = BatchRunner(m, g.shape[1])   # every grid point is its own instance (fresh solver)
+            y = r.run((pol * g).reshape(2, 1, -1))[0, 0, :]
+            r.close()
+            yref = OracleModel(m, g.shape[1]).run((pol * g).reshape(2, 1, -1))[0, 0, :]
+            assert_parity(y, yref)
+
+
+def test_K9_opamp():
+    for Amax in (10, math.inf):
+        for GBP in (50e3, math.inf):
+            m = A.DiscreteModel(cases.opamp_shelving(Amax, GBP), 1 / 44100)
+            u = np.zeros((1, 4096)); u[0, 0] = 1
+            assert_parity(gpu_run(m, u), cpu_run(m, u), rtol=1e-9)
+    m = A.DiscreteModel(cases.opamp_tanh(), 1 / 44100)
+    u = np.linspace(-1, 1, 1000)
+    y = gpu_run(m, u.reshape(1, -1))[0]
+    assert np.allclose(y, 0.5 * (4 + -3) + 0.5 * (4 - -3) * np.tanh(100 / (0.5 * (4 - -3)) * u))
+
+
+# ------------------------------------------------------------------ batched sweeps (BASELINE configs, reduced B)
+def clipper_sweep(B):
+    k = np.arange(B)
+    Is = 10.0 ** (-16 + 4 * (k % 16) / 15)
+    eta = 1 + (k // 16 % 16) / 15
+    return np.vstack([Is, eta, 1.8 * Is, eta])
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_config2_diodeclipper_sweep(kernel):
+    B, N = 256, 4410
+    m = ex.diodeclipper()
+    P = clipper_sweep(B)
+    u = cases.sine(N)
+    yref = OracleModel(m, B, params=[P], solver=H).run(u, threads=0)
+    r = BatchRunner(m, B, params=[P], solver=H, kernel=kernel)
+    y = r.run(u)                       # one shared input row
+    assert_parity(y, yref)
+    r.reset()
+    ub = np.repeat(u[:, :, None], B, axis=2) * np.linspace(0.5, 1.5, B)[None, None, :]
+    y2 = r.run(np.asfortranarray(ub))  # per-instance input streams
+    yref2 = OracleModel(m, B, params=[P], solver=H).run(ub, threads=0)
+    assert_parity(y2, yref2)
+    r.close()
+
+
+def sallenkey_sweep(B):
+    mats = {k: [] for k in ("a", "b", "x0", "dy", "ey", "y0")}
+    for k in range(B):
+        R = 10 ** (3 + 2 * (k % 8) / 7)
+        kap = 10 ** (1.3 * (k // 8) / max(B // 8 - 1, 1))
+        mk = ex.sallenkey(fs=96000, r1=R, r2=R, c1=10e-9 * kap, c2=10e-9 / kap)
+        for key in mats:
+            mats[key].append(getattr(mk, key))
+    return {k: np.stack(v, axis=-1) for k, v in mats.items()}
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_config3_sallenkey_per_instance_matrices(kernel):
+    B, N = 64, 9600
+    base = ex.sallenkey(fs=96000)
+    ov = sallenkey_sweep(B)
+    u = cases.sine(N, fs=96000.0)
+    yref = OracleModel(base, B, overrides=ov).run(u, threads=0)
+    r = BatchRunner(base, B, overrides=ov, kernel=kernel)
+    assert_parity(r.run(u), yref, rtol=1e-9)
+    r.close()
+
+
+def test_config4_superover_pots_as_inputs():
+    B, N = 16, 1000
+    m = ex.superover()
+    u = np.zeros((4, N, B), order="F")
+    u[0] = cases.sine(N)[0][:, None]
+    u[1] = (np.arange(B) % 4 + 0.5)[None, :] / 4
+    u[2] = (np.arange(B) // 4 + 0.5)[None, :] / 4
+    u[3] = 1.0
+    yref = OracleModel(m, B, solver=H).run(u, threads=0)
+    r = BatchRunner(m, B, solver=H)
+    assert_parity(r.run(u), yref)
+    r.close()
+
+
+def test_config5_birdie_noise_histogram():
+    B, N = 64, 4410
+    m = ex.birdie(vol=0.8)
+    rng = np.random.default_rng(0xACE5EED)
+    u = np.asfortranarray(np.clip(0.2 * rng.standard_normal((1, N, B)), -1, 1))
+    o = OracleModel(m, B, solver=H)
+    yref = o.run(u, threads=0)
+    r = BatchRunner(m, B, solver=H)
+    assert_parity(r.run(u), yref)
+    ho, hg = np.array(o.stats()["iter_hist"]), np.array(r.stats()["iter_hist"])
+    assert hg.sum() == ho.sum() == B * N
+    assert np.abs(hg - ho).sum() <= 0.002 * B * N
+    r.close()
+
+
+# ------------------------------------------------------------------ state, chunking, pointers
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_state_persists_across_calls(kernel):
+    """ACME.jl:561-562: model state survives run! calls -> chunked == one shot"""
+    m = ex.birdie(vol=0.8)
+    u = cases.sine(3000)
+    r = BatchRunner(m, 3, kernel=kernel, solver=H)
+    y1 = r.run(u)
+    r.reset()
+    y2 = np.concatenate([r.run(u[:, :1234]), r.run(u[:, 1234:])], axis=1)
+    assert np.array_equal(y1, y2)
+    x = r.x.copy()
+    r.x = x
+    assert np.array_equal(r.x, x)
+    r.close()
+
+
+def test_run_bang_updates_model_state():
+    m = ex.sallenkey()
+    y1 = run_(m, cases.sine(100))
+    assert np.any(m.x != 0)
+    y2 = run_(m, cases.sine(100))
+    assert not np.array_equal(y1, y2)
+
+
+def test_device_pointers_torch():
+    import torch
+    B, N = 96, 2048
+    m = ex.diodeclipper()
+    P = clipper_sweep(B)
+    r = BatchRunner(m, B, params=[P], solver=H)
+    u_host = np.asfortranarray(np.repeat(cases.sine(N)[:, :, None], B, axis=2))
+    y_host = r.run(u_host)
+    r.reset()
+    u_dev = torch.from_numpy(np.ascontiguousarray(u_host.transpose(2, 1, 0))).cuda()
+    y_dev = r.run(u_dev)
+    torch.cuda.synchronize()
+    assert np.array_equal(y_dev.cpu().numpy().transpose(2, 1, 0), y_host)
+    assert r.launch_count >= 2
+    r.close()
+
+
+def test_frozen_cache_lookup():
+    """a cache learnt by the oracle's CachingSolver is used as a frozen start-point table"""
+    m = ex.birdie(vol=0.8)
+    rng = np.random.default_rng(1)
+    u = np.clip(0.6 * rng.standard_normal((1, 6000)), -2, 2)
+    o = OracleModel(m, 1, solver=HC)
+    o.run(u)
+    cache = o.export_cache()
+    u2 = np.clip(0.6 * rng.standard_normal((1, 3000)), -2, 2)
+    yref = cpu_run(m, u2, solver=H)
+    for kernel in KERNELS:
+        r = BatchRunner(m, 1, kernel=kernel, solver=HC, caches=[cache])
+        assert_parity(r.run(u2)[:, :, 0], yref)
+        it_cached = r.stats()["newton_iters"]
+        r.close()
+        r = BatchRunner(m, 1, kernel=kernel, solver=H)
+        r.run(u2)
+        assert it_cached <= r.stats()["newton_iters"] * 1.05
+        r.close()
+
+
+# ------------------------------------------------------------------ full BASELINE sizes: size-independent properties
+def test_full_size_config2_properties():
+    """diode clipper, B = 65 536, 1 s @ 44.1 kHz: (1) instances with identical
+    parameters give identical outputs wherever they sit in the batch; (2) spot
+    instances match the oracle; (3) every solve converged."""
+    import torch
+    B, N = 65536, 44100
+    m = ex.diodeclipper()
+    k = np.arange(B)
+    Is = 10.0 ** (-16 + 4 * (k % 256) / 255)
+    eta = 1 + (k // 256) / 255
+    P = np.vstack([Is, eta, 1.8 * Is, eta])
+    P[:, -1] = P[:, 0]; P[:, 40000] = P[:, 123]
+    r = BatchRunner(m, B, params=[P], solver=H)
+    u = torch.from_numpy(cases.sine(N)[0].copy()).cuda().reshape(N, 1)
+    y = r.run(u)
+    torch.cuda.synchronize()
+    assert r.kernel_name.startswith("tpi<")
+    assert torch.equal(y[-1], y[0]) and torch.equal(y[40000], y[123])
+    assert bool(torch.isfinite(y).all())
+    st = r.stats()
+    assert st["samples"] == B * N and st["not_converged"] == 0
+    spots = [0, 255, 256 * 255, B - 2, 31337]
+    yref = OracleModel(m, len(spots), params=[P[:, spots]], solver=H).run(cases.sine(N), threads=0)
+    assert_parity(y[spots].cpu().numpy().transpose(2, 1, 0), yref)
+    r.close()
+
+
+def test_full_size_config3_linearity():
+    """Sallen-Key, per-instance matrices, 1 s @ 96 kHz: the model is linear, so
+    y(2u) == 2 y(u) up to rounding, and chunked == one-shot bit for bit."""
+    import torch
+    B, N = 4096, 96000
+    base = ex.sallenkey(fs=96000)
+    ov = sallenkey_sweep(64)
+    ov = {k: np.tile(v, (1,) * (v.ndim - 1) + (B // 64,)) for k, v in ov.items()}
+    r = BatchRunner(base, B, overrides=ov)
+    u = torch.from_numpy(cases.sine(N, fs=96000.0)[0].copy()).cuda().reshape(N, 1)
+    y1 = r.run(u).clone()
+    r.reset()
+    y2 = r.run(2 * u)
+    assert torch.allclose(y2, 2 * y1, rtol=1e-12, atol=1e-15)
+    assert torch.equal(y1[:64], y1[64:128])
+    r.close()
