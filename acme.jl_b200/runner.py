@@ -102,6 +102,8 @@ class BatchRunner:
 
     @x.setter
     def x(self, val):
+        if self.model.nx == 0:
+            return
         v = np.asarray(val, dtype=np.float64).reshape(self.model.nx, -1)
         v = np.ascontiguousarray(np.broadcast_to(v, (self.model.nx, self.batch)).ravel(order="F"))
         if v.size:

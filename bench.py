@@ -1,0 +1,320 @@
+#!/usr/bin/env python
+"""Headline benchmark: batched circuit-samples per second (BASELINE.json metric).
+
+Workload (BASELINE.json configs[1]): examples/diodeclipper.jl, batch = 65 536
+instances per GPU with swept Is / eta (256 x 256 grid, SURVEY.md section 8d
+config 2), 1 s of a unit 1 kHz sine at 44.1 kHz per instance.  One "step" = one
+``run!`` of that second for the whole batch.  Weak scaling: every GPU owns its
+own 65 536 instances (independent instances shard with no data-path collective).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N ...            # CPU restatement of the reference
+
+Prints ONE JSON line (rank 0).  `value` is timed with the streams resident in
+HBM (CUDA events on the launching stream); `e2e` is the same metric through the
+public API with pinned HOST buffers, H2D and D2H inside the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FS = 44100
+N_SAMPLES = 44100
+BATCH_PER_GPU = 65536
+SOLVER = "HomotopySolver{CachingSolver{SimpleSolver}}"  # the reference's default (ACME.jl:150)
+METRIC = "Msamples/sec (batched circuit-samples)"
+ALG_BYTES_PER_SAMPLE = 16  # one f64 input read + one f64 probe sample written
+
+
+def sweep_params(batch_total: int, first: int, count: int) -> np.ndarray:
+    """Is_k = 10^(-16 + 4k/255), eta_j = 1 + j/255, d2 uses 1.8*Is (diodeclipper.jl:11-12)."""
+    idx = np.arange(first, first + count) % 65536
+    k, j = idx % 256, idx // 256
+    Is = 10.0 ** (-16 + 4 * k / 255)
+    eta = 1 + j / 255
+    return np.vstack([Is, eta, 1.8 * Is, eta])
+
+
+def sine_row() -> np.ndarray:
+    return np.sin(2 * np.pi * 1000 / FS * np.arange(N_SAMPLES))
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        self.t.join(timeout=2)
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); smax.append(float(r[2]))
+            except Exception:
+                continue
+            for nm, v in zip(names, r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_baseline(budget_s: float = 12.0, threads: int = 0) -> dict:
+    """The oracle (CPU restatement of the reference's run! path) on all host cores, on a
+    bounded sample of the same workload: the first `b` instances of the sweep, full 1 s signal."""
+    from acme_jl_b200 import examples as ex
+    from oracle import oracle
+    from oracle.oracle import OracleModel
+    cores = threads or oracle.lib().oracle_num_threads()
+    m = ex.diodeclipper()
+    u = sine_row().reshape(1, -1)
+    b = 4 * cores
+    P = sweep_params(BATCH_PER_GPU, 0, b)
+    o = OracleModel(m, b, params=[P], solver=SOLVER)
+    t0 = time.perf_counter(); o.run(u, threads=cores); dt = time.perf_counter() - t0
+    rate = b * N_SAMPLES / dt
+    b2 = int(min(BATCH_PER_GPU, max(b, budget_s * rate / N_SAMPLES)))
+    b2 -= b2 % cores or 0
+    b2 = max(b2, cores)
+    idx = (np.arange(b2) * (BATCH_PER_GPU // b2)) % BATCH_PER_GPU  # spread over the sweep grid
+    P = sweep_params(BATCH_PER_GPU, 0, BATCH_PER_GPU)[:, idx]
+    o = OracleModel(m, b2, params=[P], solver=SOLVER)
+    t0 = time.perf_counter(); o.run(u, threads=cores); dt = time.perf_counter() - t0
+    return {"value": b2 * N_SAMPLES / dt / 1e6, "unit": "Msamples/s", "cores": cores, "kind": "port",
+            "sample": f"{b2} of the 65536 swept instances x {N_SAMPLES} samples, {dt:.1f} s, "
+                      f"HomotopySolver{{CachingSolver{{SimpleSolver}}}} restated in C (oracle/acme_oracle.c); "
+                      f"the Julia reference cannot run here (no Julia toolchain)"}
+
+
+def measured_peak() -> tuple:
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic():
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get("dram_bytes_per_launch")
+        except Exception:
+            return None
+    return None
+
+
+def run_reference(args, rank: int, world: int):
+    """--impl reference: the reference's CPU algorithm (restated; see cpu_baseline) on the host cores."""
+    if rank != 0:
+        return
+    per_step = []
+    info = None
+    for i in range(args.warmup + args.steps):
+        info = cpu_baseline(budget_s=6.0)
+        if i >= args.warmup:
+            per_step.append(info["value"])
+    v = float(np.mean(per_step)) if per_step else info["value"]
+    info["value"] = v
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "Msamples/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "diodeclipper.jl, swept Is/eta, 1 s of 1 kHz sine @ 44.1 kHz; bounded sample per step",
+                   "batch_per_gpu": BATCH_PER_GPU, "samples": N_SAMPLES},
+        "cpu_baseline": info,
+        "e2e": {"value": v, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="instances per GPU (default: the BASELINE config)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--kernel", default="auto")
+    ap.add_argument("--samples", type=int, default=N_SAMPLES, help="samples per instance (default 44100 = 1 s; "
+                    "smaller values are for profiling under ncu only, such a line is not a bench value)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    global N_SAMPLES
+    N_SAMPLES = args.samples
+
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback for the product path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    from acme_jl_b200 import BatchRunner, examples as ex
+    Bper = args.batch
+    model = ex.diodeclipper()
+    P = sweep_params(Bper * world, rank * Bper, Bper)
+    runner = BatchRunner(model, Bper, params=[P], solver=SOLVER, kernel=args.kernel)
+
+    row = torch.from_numpy(sine_row()).to(dev)
+    U = row.reshape(1, N_SAMPLES, 1).expand(Bper, N_SAMPLES, 1).contiguous()  # (B, N, nu): per-instance streams in HBM
+    Y = torch.empty((Bper, N_SAMPLES, 1), dtype=torch.float64, device=dev)
+    stream = torch.cuda.current_stream(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    for _ in range(args.warmup):
+        runner.run(U, Y, check_status=False)
+    torch.cuda.synchronize()
+    launches0 = runner.launch_count
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    barrier(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        runner.run(U, Y, check_status=False)
+    e1.record(stream)
+    torch.cuda.synchronize(); barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = runner.launch_count - launches0
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    st = runner.stats()
+    status_bad = int((runner.status()[0] != 0).sum())
+    samples_step = Bper * world * N_SAMPLES
+    value = samples_step * args.steps / (ms / 1e3) / 1e6
+    kernel_ms = ms / args.steps  # one kernel launch per step: launch duration == step duration
+
+    # ---- end to end: pinned host buffers, H2D + D2H inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        import psutil
+        need = 2 * Bper * N_SAMPLES * 8
+        avail = psutil.virtual_memory().available / max(world, 1)
+        Be = Bper
+        while Be > 1024 and need * (Be / Bper) * 1.6 > avail:
+            Be //= 2
+        del U, Y
+        torch.cuda.empty_cache()
+        r2 = runner if Be == Bper else BatchRunner(model, Be, params=[P[:, :Be]], solver=SOLVER, kernel=args.kernel)
+        hu = torch.empty((Be, N_SAMPLES, 1), dtype=torch.float64, pin_memory=True)
+        hy = torch.empty((Be, N_SAMPLES, 1), dtype=torch.float64, pin_memory=True)
+        hu.copy_(row.cpu().reshape(1, N_SAMPLES, 1).expand(Be, N_SAMPLES, 1))
+        e2e_steps = max(1, min(args.steps, 3))
+        r2.run_host_pinned(hu.data_ptr(), N_SAMPLES, hy.data_ptr(), N_SAMPLES)  # warm-up (allocates staging)
+        barrier(); torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        l0 = r2.launch_count
+        for _ in range(e2e_steps):
+            r2.run_host_pinned(hu.data_ptr(), N_SAMPLES, hy.data_ptr(), N_SAMPLES)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        le = r2.launch_count - l0
+        barrier()
+        if world > 1:
+            t = torch.tensor([dt], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        e2e = {"value": Be * world * N_SAMPLES * e2e_steps / dt / 1e6, "unit": "Msamples/s",
+               "h2d_bytes_per_step": int(Be * N_SAMPLES * 8), "d2h_bytes_per_step": int(Be * N_SAMPLES * 8),
+               "batch_per_gpu": Be, "steps": e2e_steps, "kernel_launches": int(le),
+               "checksum": float(hy[0, :, 0].abs().sum())}
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        per_gpu_rate = Bper * N_SAMPLES / (kernel_ms / 1e3)
+        achieved = ALG_BYTES_PER_SAMPLE * per_gpu_rate / 1e9
+        out = {
+            "metric": METRIC, "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "examples/diodeclipper.jl, batch=65536 instances/GPU with swept Is/eta (256x256), "
+                                   "1 s of unit 1 kHz sine @ 44.1 kHz per instance (BASELINE.json configs[1])",
+                       "batch_per_gpu": Bper, "global_batch": Bper * world, "samples": N_SAMPLES, "solver": SOLVER,
+                       "parallelism": f"instances sharded over {world} GPU(s), no data-path collective",
+                       "l2": "inputs larger than L2 (23 GB U + 23 GB Y per GPU per step)",
+                       "kernel": runner.kernel_name},
+            "clocks": clocks,
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": ncu_traffic(), "peak_source": peak_src,
+                         "note": "HBM fraction is the asked-for metric; the kernel is FP64-pipe bound (see DESIGN.md)",
+                         "algorithmic_bytes_per_launch": ALG_BYTES_PER_SAMPLE * Bper * N_SAMPLES,
+                         "kernel_ms": kernel_ms},
+            "newton": {"mean_iters": st["newton_iters"] / max(st["solves"], 1), "hist_1_to_8": st["iter_hist"][:8],
+                       "homotopy_solves": st["homotopy_solves"], "not_converged": st["not_converged"],
+                       "instances_with_status": status_bad},
+        }
+        if e2e is not None:
+            out["e2e"] = e2e
+        if world == 1 and not args.no_cpu:
+            out["cpu_baseline"] = cpu_baseline()
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -35,6 +35,21 @@ def assert_parity(y, yref, rtol=1e-6):
     assert not bad.any(), f"max rel err {np.max(err / np.maximum(scale, 1e-300)):.3e}"
 
 
+def assert_parity_within_reference_accuracy(y, yref, yexact, rtol=1e-6):
+    """The reference stops Newton when max|res| < 1e-10 (solvers.jl:226), which leaves
+    its own output uncertain by E_ref = max|y_ref - y_converged| (measured here with the
+    oracle at tol = 1e-14; e.g. 5e-6 V on birdie with noise input).  Two faithful
+    implementations whose iterates differ in the last bits may stop one iteration apart,
+    so at the default tolerance parity can only be asked up to that uncertainty."""
+    peak = np.max(np.abs(yref))
+    scale = np.maximum(np.abs(yref), 1e-3 * peak)
+    e_ref = np.max(np.abs(yref - yexact))
+    err = np.abs(y - yref)
+    assert (err <= rtol * scale + 2 * e_ref).all(), f"max abs err {err.max():.3e}, E_ref {e_ref:.3e}"
+    # and the GPU must not be less accurate than the reference is
+    assert np.max(np.abs(y - yexact)) <= 2 * e_ref + rtol * peak * 1e-3
+
+
 def gpu_run(model, u, kernel="auto", **kw):
     r = BatchRunner(model, 1, kernel=kernel, **kw)
     try:
@@ -304,10 +319,16 @@ def test_config5_birdie_noise_histogram():
     m = ex.birdie(vol=0.8)
     rng = np.random.default_rng(0xACE5EED)
     u = np.asfortranarray(np.clip(0.2 * rng.standard_normal((1, N, B)), -1, 1))
+    # (1) stopping tolerance tightened on both sides (set_resabstol!, solvers.jl:181): strict 1e-6 parity
+    yexact = OracleModel(m, B, solver=H, tol=1e-13).run(u, threads=0)
+    r = BatchRunner(m, B, solver=H, tol=1e-13)
+    assert_parity(r.run(u), yexact)
+    r.close()
+    # (2) default tolerance: parity up to the reference's own stopping-rule uncertainty
     o = OracleModel(m, B, solver=H)
     yref = o.run(u, threads=0)
     r = BatchRunner(m, B, solver=H)
-    assert_parity(r.run(u), yref)
+    assert_parity_within_reference_accuracy(r.run(u), yref, yexact)
     ho, hg = np.array(o.stats()["iter_hist"]), np.array(r.stats()["iter_hist"])
     assert hg.sum() == ho.sum() == B * N
     assert np.abs(hg - ho).sum() <= 0.002 * B * N
@@ -364,11 +385,17 @@ def test_frozen_cache_lookup():
     o = OracleModel(m, 1, solver=HC)
     o.run(u)
     cache = o.export_cache()
+    assert len(cache["ps_idx"]) > 1
     u2 = np.clip(0.6 * rng.standard_normal((1, 3000)), -2, 2)
+    yexact = cpu_run(m, u2, solver=H, tol=1e-13)
     yref = cpu_run(m, u2, solver=H)
     for kernel in KERNELS:
+        # different start points, same solution: strict parity once both sides converge fully
+        r = BatchRunner(m, 1, kernel=kernel, solver=HC, caches=[cache], tol=1e-13)
+        assert_parity(r.run(u2)[:, :, 0], yexact)
+        r.close()
         r = BatchRunner(m, 1, kernel=kernel, solver=HC, caches=[cache])
-        assert_parity(r.run(u2)[:, :, 0], yref)
+        assert_parity_within_reference_accuracy(r.run(u2)[:, :, 0], yref, yexact)
         it_cached = r.stats()["newton_iters"]
         r.close()
         r = BatchRunner(m, 1, kernel=kernel, solver=H)
