@@ -42,6 +42,7 @@ def lib():
         L.acmeb200_kernel_name.restype = C.c_char_p
         L.acmeb200_launch_count.argtypes = [vp]
         L.acmeb200_launch_count.restype = i64
+        L.acmeb200_measure_fp64_peak.argtypes = [C.POINTER(C.c_double)]
         L.acmeb200_last_error.restype = C.c_char_p
         L.acmeb200_abi_version.restype = C.c_int
         _LIB = L
@@ -55,5 +56,12 @@ def check(rc):
 
 EXPORTS = ["acmeb200_model_create", "acmeb200_model_destroy", "acmeb200_run", "acmeb200_get_state",
            "acmeb200_set_state", "acmeb200_reset", "acmeb200_get_status", "acmeb200_get_stats",
-           "acmeb200_set_kernel", "acmeb200_kernel_name", "acmeb200_launch_count",
+           "acmeb200_set_kernel", "acmeb200_kernel_name", "acmeb200_launch_count", "acmeb200_measure_fp64_peak",
            "acmeb200_last_error", "acmeb200_abi_version"]
+
+
+def measure_fp64_peak() -> float:
+    """measured DFMA throughput of the current device, TFLOP/s"""
+    v = C.c_double(0)
+    check(lib().acmeb200_measure_fp64_peak(C.byref(v)))
+    return v.value

@@ -555,3 +555,43 @@ extern "C" int acmeb200_get_stats(acmeb200_model* m, acmeb200_stats* out) {
     for (int i = 0; i < ACMEB200_HIST_BINS; i++) out->iter_hist[i] = s.iter_hist[i];
     return ACMEB200_OK;
 }
+
+// ------------------------------------------------------------------ FP64 pipe peak (diagnostic)
+__global__ void __launch_bounds__(256) k_dfma_peak(double* out, int iters, double a, double b) {
+    double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+            x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+        }
+    }
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+}
+
+extern "C" int acmeb200_measure_fp64_peak(double* tflops_out) {
+    if (!tflops_out) return fail(ACMEB200_EINVAL, "null argument");
+    int dev = 0, sms = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int blocks = sms * 8, tpb = 256, iters = 4096;
+    double* d = nullptr;
+    CUDA_TRY(cudaMalloc(&d, sizeof(double) * (size_t)blocks * tpb));
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; rep++) {
+        CUDA_TRY(cudaEventRecord(e0));
+        k_dfma_peak<<<blocks, tpb>>>(d, iters, 0.999999, 1e-9);
+        CUDA_TRY(cudaEventRecord(e1));
+        CUDA_TRY(cudaEventSynchronize(e1));
+        float ms = 0;
+        CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+    const double flops = 2.0 * 64.0 * iters * (double)blocks * tpb;
+    *tflops_out = flops / (best * 1e-3) / 1e12;
+    return ACMEB200_OK;
+}

@@ -282,6 +282,8 @@ def main():
                "checksum": float(hy[0, :, 0].abs().sum())}
 
     if rank == 0:
+        from acme_jl_b200._lib import measure_fp64_peak
+        fp64_peak = measure_fp64_peak()
         peak, peak_src = measured_peak()
         per_gpu_rate = Bper * N_SAMPLES / (kernel_ms / 1e3)
         achieved = ALG_BYTES_PER_SAMPLE * per_gpu_rate / 1e9
@@ -302,6 +304,9 @@ def main():
                          "note": "HBM fraction is the asked-for metric; the kernel is FP64-pipe bound (see DESIGN.md)",
                          "algorithmic_bytes_per_launch": ALG_BYTES_PER_SAMPLE * Bper * N_SAMPLES,
                          "kernel_ms": kernel_ms},
+            "fp64_pipe": {"measured_dfma_peak_tflops": fp64_peak,
+                          "note": "DFMA microbenchmark in this run (acmeb200_measure_fp64_peak); per-sample "
+                                  "flop counts are in DESIGN.md"},
             "newton": {"mean_iters": st["newton_iters"] / max(st["solves"], 1), "hist_1_to_8": st["iter_hist"][:8],
                        "homotopy_solves": st["homotopy_solves"], "not_converged": st["not_converged"],
                        "instances_with_status": status_bad},

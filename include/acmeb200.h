@@ -192,6 +192,10 @@ const char *acmeb200_kernel_name(const acmeb200_model *m);
 /* number of kernels launched by this model since creation */
 int64_t acmeb200_launch_count(const acmeb200_model *m);
 
+/* diagnostic: measured FP64 FMA throughput of the current device in TFLOP/s
+ * (2 flops per DFMA), the denominator of the FP64-pipe roofline in bench.py */
+int acmeb200_measure_fp64_peak(double *tflops_out);
+
 const char *acmeb200_last_error(void);
 int acmeb200_abi_version(void);
 

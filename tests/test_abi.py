@@ -18,7 +18,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def test_header_symbols_exported():
     hdr = open(os.path.join(ROOT, "include", "acmeb200.h")).read()
-    declared = set(re.findall(r"\b(acmeb200_[a-z_]+)\s*\(", hdr))
+    declared = set(re.findall(r"\b(acmeb200_[a-z0-9_]+)\s*\(", hdr))
     assert declared == set(EXPORTS)
     L = lib()
     for name in declared:
