@@ -22,6 +22,70 @@ namespace acme {
 
 #define ACME_DI __host__ __device__ __forceinline__
 
+// exp(double) for the element laws.  Same algorithm and coefficients as the CUDA
+// math library's exp (Cody-Waite reduction by ln2 with the 2^52+2^51 rounding
+// trick, degree-11 Horner polynomial, exponent splice; two-step scaling near the
+// overflow/underflow limits), but every constant is a __constant__-bank operand
+// of the DFMA instead of a pair of immediate moves -- the library version spends
+// ~40 of its ~65 issue slots materialising immediates when registers are tight.
+// tests/test_gpu_parity.py::test_device_exp checks it against the library exp.
+#ifdef __CUDACC__
+__constant__ double ACME_EXPC[16] = {
+    // log2(e), 2^52+2^51, -ln2_hi, -ln2_lo, then the degree-11 minimax coefficients c11..c2
+    0x1.71547652b82fep+0,
+    0x1.8000000000000p+52,
+    -0x1.62e42fefa39efp-1,
+    -0x1.abc9e3b39803fp-56,
+    0x1.ade1569ce2bdfp-26,
+    0x1.28af3fca213eap-22,
+    0x1.71dee62401315p-19,
+    0x1.a01997c89eb71p-16,
+    0x1.a01a014761f65p-13,
+    0x1.6c16c1852b7afp-10,
+    0x1.1111111122322p-7,
+    0x1.55555555502a1p-5,
+    0x1.5555555555511p-3,
+    0x1.000000000000bp-1,
+    1.0, 0.0};
+
+__device__ __forceinline__ double acme_exp(double x) {
+    const double* K = ACME_EXPC;
+    double t = fma(x, K[0], K[1]);
+    const int i = __double2loint(t);
+    t = t - K[1];
+    double r = fma(t, K[2], x);
+    r = fma(t, K[3], r);
+    double p = fma(K[4], r, K[5]);
+    p = fma(p, r, K[6]);
+    p = fma(p, r, K[7]);
+    p = fma(p, r, K[8]);
+    p = fma(p, r, K[9]);
+    p = fma(p, r, K[10]);
+    p = fma(p, r, K[11]);
+    p = fma(p, r, K[12]);
+    p = fma(p, r, K[13]);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    const int hx = __double2hiint(x) & 0x7fffffff;
+    if (hx < 0x40862e42) {  // |x| < ~708.39: the result is a normal number
+        return __hiloint2double(__double2hiint(p) + (i << 20), __double2loint(p));
+    }
+    if (hx < 0x40874800) {  // |x| < 745: scale in two steps (subnormal / near-overflow results)
+        const int k = i / 2;
+        const double a = __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
+        return a * __hiloint2double((0x3ff + (i - k)) << 20, 0);
+    }
+    if (x != x) return x + x;
+    return x < 0 ? 0.0 : __longlong_as_double(0x7ff0000000000000ll);
+}
+#endif
+// host passes of the __host__ __device__ element code never evaluate laws (the host only runs prep)
+#ifdef __CUDA_ARCH__
+#define ACME_EXPD(x) acme_exp(x)
+#else
+#define ACME_EXPD(x) exp(x)
+#endif
+
 struct Diode {  // elements.jl:236-245
     static constexpr int KIND = ACMEB200_ELEM_DIODE, NN = 1, NQ = 2, NPAR = 2, NC = 3, NJ = 1;
     ACME_DI static void prep(const double* P, double* C) {
@@ -31,7 +95,7 @@ struct Diode {  // elements.jl:236-245
         C[2] = is / (25e-3 * eta);
     }
     ACME_DI static void eval(const double* C, const double* q, double* res, double* jv) {
-        const double ex = exp(q[0] * C[1]);
+        const double ex = ACME_EXPD(q[0] * C[1]);
         res[0] = C[0] * (ex - 1) - q[1];
         jv[0] = C[2] * ex;
     }
@@ -128,8 +192,8 @@ struct Bjt {  // elements.jl:309-406
     ACME_DI static void eval(const double* C, const double* q, double* res, double* jv) {
         const int flags = (int)C[19];
         const double vE = q[0], vC = q[1], iE = q[2], iC = q[3];
-        const double expE = exp(vE * C[0]);
-        const double expC = exp(vC * C[1]);
+        const double expE = ACME_EXPD(vE * C[0]);
+        const double expC = ACME_EXPD(vC * C[1]);
         const double i_f = C[2] * (expE - 1);
         const double i_r = C[3] * (expC - 1);
         const double di_f1 = C[4] * expE;
@@ -168,13 +232,13 @@ struct Bjt {  // elements.jl:309-406
         }
         double iBE = C[6] * i_f, diBE1 = C[6] * di_f1;
         if (flags & 4) {
-            const double expEl = (flags & 8) ? exp(vE * C[10]) : expE;
+            const double expEl = (flags & 8) ? ACME_EXPD(vE * C[10]) : expE;
             iBE += C[8] * (expEl - 1);
             diBE1 += C[12] * expEl;
         }
         double iBC = C[7] * i_r, diBC2 = C[7] * di_r2;
         if (flags & 16) {
-            const double expCl = (flags & 32) ? exp(vC * C[11]) : expC;
+            const double expCl = (flags & 32) ? ACME_EXPD(vC * C[11]) : expC;
             iBC += C[9] * (expCl - 1);
             diBC2 += C[13] * expCl;
         }

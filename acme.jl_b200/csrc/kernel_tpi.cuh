@@ -179,8 +179,11 @@ __device__ __forceinline__ double tpi_evaluate(const M& m, const double (&Cn)[di
         });
         q[i] = acc;
     });
-    double resmax = 0.0, jsum = 0.0;
-    bool nan = false;
+    // max|res| plus ONE finiteness test for everything the reference checks
+    // (isfinite(resmaxabs) && all(isfinite, J), solvers.jl:220): the sum of the
+    // absolute residuals and variable Jacobian entries is finite iff all of them are
+    // (J = Jq*fq is a finite-coefficient combination of those entries).
+    double resmax = 0.0, rsum = 0.0, jsum = 0.0;
     for_each_elem<0, 0, 0, 0>(typename C::Elems{}, [&](auto e, auto row, auto qoff, auto coff, auto joff) {
         using E = decltype(e);
         constexpr int ROW = decltype(row)::value, QOFF = decltype(qoff)::value, COFF = decltype(coff)::value,
@@ -190,8 +193,8 @@ __device__ __forceinline__ double tpi_evaluate(const M& m, const double (&Cn)[di
         static_for<0, E::NN>([&](auto rr) {
             constexpr int r = decltype(rr)::value;
             const double ar = fabs(res[ROW + r]);
-            if (ar != ar) nan = true;
-            if (ar > resmax) resmax = ar;
+            rsum += ar;
+            resmax = fmax(resmax, ar);
             static_for<0, C::NN>([&](auto cc) {
                 constexpr int c = decltype(cc)::value;
                 J[c * C::NN + ROW + r] =
@@ -199,8 +202,10 @@ __device__ __forceinline__ double tpi_evaluate(const M& m, const double (&Cn)[di
             });
         });
     });
-    Jfinite = isfinite(jsum);
-    return nan ? NAN : resmax;
+    const double dmax = 1.7976931348623157e308;
+    Jfinite = (rsum + jsum) <= dmax;        // false for NaN and Inf
+    if (!Jfinite && !(rsum <= dmax)) return NAN;  // non-finite residual: hasconverged() is false
+    return resmax;
 }
 
 // Mx = LU \ (Jq*pexp)  (calc_Jp! ACME.jl:246-251 followed by the solve of solvers.jl:213)
@@ -260,7 +265,7 @@ __device__ __forceinline__ bool tpi_simple_solve(const M& m, const double (&Cn)[
     for (iters = 1; iters <= sc.maxiter; iters++) {
         bool Jfin;
         const double resmax = tpi_evaluate<C>(m, Cn, pfull, z, res, jv, J, Jfin);
-        if (!isfinite(resmax) || !Jfin) return resmax < sc.tol;
+        if (!Jfin) return resmax < sc.tol;
         if (!lu_reg<C::NN>(J, piv)) return resmax < sc.tol;
         if (resmax < sc.tol) { converged = true; break; }
         lu_solve_reg<C::NN>(J, piv, res);
@@ -362,26 +367,196 @@ __device__ __noinline__ bool tpi_cold_solve(const M* mp, TpiCold<C>* kp, SolverC
     return conv;
 }
 
-constexpr int TPI_T = 16;    // samples per staged tile
-constexpr int TPI_TPB = 64;  // threads per block (2 warps): small CTAs balance 148 SMs
+#ifndef ACME_TPI_TPB
+#define ACME_TPI_TPB 64
+#endif
+#ifndef ACME_TPI_MINB
+#define ACME_TPI_MINB 8
+#endif
+#ifndef ACME_TPI_T
+#define ACME_TPI_T 8
+#endif
+constexpr int TPI_T = ACME_TPI_T;      // samples per staged tile
+constexpr int TPI_TPB = ACME_TPI_TPB;  // threads per block (2 warps): small CTAs balance 148 SMs
+
+// ---- TMA (bulk async copy) + mbarrier primitives, PTX ISA 8.x --------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+// global -> shared bulk copy (TMA, UBLKCP in SASS), completion counted on an mbarrier
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+// shared -> global bulk copy, tracked by the thread's bulk async-group
+__device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// per-warp shared memory: 2 input buffers (TMA double buffering), 1 output buffer, 2 mbarriers,
+// 8 histogram counters per lane.  Rows are padded by 16 B: TMA needs 16-byte aligned rows and the
+// pad spreads the lanes' own-row accesses over the banks.
+template <class C>
+struct TpiSmem {
+    static constexpr int IROW = TPI_T * C::NU * 8 + 16;  // bytes per instance row, input
+    static constexpr int OROW = TPI_T * C::NY * 8 + 16;
+    static constexpr int IN_BYTES = 32 * IROW, OUT_BYTES = 32 * OROW;
+    static constexpr int HIST_OFF = 2 * IN_BYTES + OUT_BYTES;
+    static constexpr int BAR_OFF = HIST_OFF + 32 * 8 * 4;
+    static constexpr int PER_WARP = BAR_OFF + 16;
+};
 
 template <class C>
 constexpr size_t tpi_smem_bytes() {
-    return (size_t)(TPI_TPB / 32) * 32 * ((TPI_T * C::NU + 1) + (TPI_T * C::NY + 1)) * sizeof(double);
+    return (size_t)(TPI_TPB / 32) * TpiSmem<C>::PER_WARP;
+}
+
+// one sample of one instance: step! (ACME.jl:666-715).  Returns the Newton iteration count
+// (0 for linear models); `conv` is false if the solve failed.
+template <class C, class M>
+__device__ __forceinline__ int tpi_step(const M& m, const double (&Cn)[dim1(C::NC)], TpiState<C>& S,
+                                        const double (&u)[dim1(C::NU)], double (&y)[dim1(C::NY)],
+                                        const SolverCfg& sc, const DevSub& cache, const RunArgs& a, int64_t inst,
+                                        bool& conv, bool& homotopy, bool& finite) {
+    constexpr int NX = C::NX, NU = C::NU, NY = C::NY, NN = C::NN, NP = C::NP;
+    double zall[dim1(NN)];
+    int iters = 0;
+    conv = true;
+    homotopy = false;
+    finite = true;
+    if constexpr (NN > 0) {
+        // p = dq*x + eq*u   (ACME.jl:678-686)
+        double p[dim1(NP)];
+        static_for<0, NP>([&](auto ii) {
+            constexpr int i = decltype(ii)::value;
+            double acc = 0.0;
+            static_for<0, NX>([&](auto jj) { acc = fma(m.dq[decltype(jj)::value * NP + i], S.x[decltype(jj)::value], acc); });
+            static_for<0, NU>([&](auto jj) { acc = fma(m.eq[decltype(jj)::value * NP + i], u[decltype(jj)::value], acc); });
+            p[i] = acc;
+        });
+        bool need_cold = false;
+        int cold_mode = 0;
+        if (sc.solver == ACMEB200_SOLVER_HOMOTOPY_CACHING) {
+            // cheap inline test for the common case "the current origin is the nearest start point"
+            if (cache.cache_n > 0) {
+                need_cold = true;
+            } else {
+                double best = 0.0, d0 = 0.0;
+                static_for<0, NP>([&](auto ii) {
+                    constexpr int i = decltype(ii)::value;
+                    const double d = p[i] - S.lp[i];
+                    best = fma(d, d, best);
+                    d0 = fma(p[i], p[i], d0);
+                });
+                need_cold = d0 < best;
+            }
+        }
+        if (!need_cold) {
+            conv = tpi_simple_solve<C>(m, Cn, S, p, zall, sc, iters);
+            if (!conv && sc.solver != ACMEB200_SOLVER_SIMPLE) { need_cold = true; cold_mode = 1; }
+        }
+        if (need_cold) {
+            TpiCold<C> k;
+            k.S = S;
+            static_for<0, C::NC>([&](auto i) { k.Cn[decltype(i)::value] = Cn[decltype(i)::value]; });
+            static_for<0, NP>([&](auto i) { k.p[decltype(i)::value] = p[decltype(i)::value]; });
+            static_for<0, NN>([&](auto i) {
+                k.z[decltype(i)::value] = zall[decltype(i)::value];
+                k.initz[decltype(i)::value] = a.initz[(int64_t)decltype(i)::value * a.ld + inst];
+            });
+            k.iters = iters;
+            conv = tpi_cold_solve<C>(&m, &k, sc, &cache, cold_mode);
+            homotopy = k.used_homotopy != 0;
+            S = k.S;
+            static_for<0, NN>([&](auto i) { zall[decltype(i)::value] = k.z[decltype(i)::value]; });
+            iters = k.iters;
+        }
+        if (!conv) static_for<0, NN>([&](auto i) { finite = finite && isfinite(zall[decltype(i)::value]); });
+        if (!finite) return iters;
+    }
+    // y = y0 + dy*x + ey*u + fy*z   (ACME.jl:699-706, x before the update)
+    static_for<0, NY>([&](auto ii) {
+        constexpr int i = decltype(ii)::value;
+        double acc = m.y0[i];
+        static_for<0, NX>([&](auto jj) { acc = fma(m.dy[decltype(jj)::value * NY + i], S.x[decltype(jj)::value], acc); });
+        static_for<0, NU>([&](auto jj) { acc = fma(m.ey[decltype(jj)::value * NY + i], u[decltype(jj)::value], acc); });
+        static_for<0, NN>([&](auto jj) { acc = fma(m.fy[decltype(jj)::value * NY + i], zall[decltype(jj)::value], acc); });
+        y[i] = acc;
+    });
+    // x = x0 + a*x + b*u + c*z      (ACME.jl:708-714)
+    double xn[dim1(NX)];
+    static_for<0, NX>([&](auto ii) {
+        constexpr int i = decltype(ii)::value;
+        double acc = m.x0[i];
+        static_for<0, NX>([&](auto jj) { acc = fma(m.a[decltype(jj)::value * NX + i], S.x[decltype(jj)::value], acc); });
+        static_for<0, NU>([&](auto jj) { acc = fma(m.b[decltype(jj)::value * NX + i], u[decltype(jj)::value], acc); });
+        static_for<0, NN>([&](auto jj) { acc = fma(m.c[decltype(jj)::value * NX + i], zall[decltype(jj)::value], acc); });
+        xn[i] = acc;
+    });
+    static_for<0, NX>([&](auto i) { S.x[decltype(i)::value] = xn[decltype(i)::value]; });
+    return iters;
+}
+
+// rare events (failed solve, homotopy, > 8 iterations) go straight to global memory so that the
+// hot loop carries no bookkeeping registers for them
+template <class C>
+__device__ __noinline__ void tpi_note_event(const RunArgs a, int64_t inst, int64_t n, int iters, bool conv,
+                                            bool homotopy, bool finite) {
+    if (homotopy) atomicAdd(&a.stats->homotopy_solves, 1ull);
+    if (iters > 8) {
+        int bin = iters > ACMEB200_HIST_BINS ? ACMEB200_HIST_BINS : iters;
+        atomicAdd(&a.stats->iter_hist[bin - 1], 1ull);
+        atomicAdd(&a.stats->newton_iters, (unsigned long long)iters);
+    }
+    if (!conv) {
+        if (a.first_fail[inst] < 0) a.first_fail[inst] = a.n_done + n;
+        if (finite) {
+            a.status[inst] |= ACMEB200_STATUS_NOT_CONVERGED;
+            atomicAdd(&a.stats->not_converged, 1ull);
+        } else {
+            a.status[inst] |= ACMEB200_STATUS_NONFINITE;
+        }
+    }
 }
 
 template <class C, bool PERINST>
-__global__ void __launch_bounds__(TPI_TPB) k_tpi(const __grid_constant__ TpiMats<C> Msh, const RunArgs a,
+__global__ void __launch_bounds__(TPI_TPB, ACME_TPI_MINB) k_tpi(const __grid_constant__ TpiMats<C> Msh, const RunArgs a,
                                                  const SolverCfg sc, const __grid_constant__ DevSub cache) {
     constexpr int NX = C::NX, NU = C::NU, NY = C::NY, NN = C::NN, NP = C::NP;
-    constexpr int T = TPI_T, IW = T * NU, IS = IW + 1, OW = T * NY, OS = OW + 1;
-    extern __shared__ double smem[];
+    constexpr int T = TPI_T;
+    using SM = TpiSmem<C>;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double* tin = smem + (size_t)warp * 32 * (IS + OS);
-    double* tout = tin + 32 * IS;
+    unsigned char* wsm = smem_raw + (size_t)warp * SM::PER_WARP;
+    unsigned char* const in_row0 = wsm + lane * SM::IROW;  // buffer b of this lane: in_row0 + b*IN_BYTES
+    unsigned char* out_row = wsm + 2 * SM::IN_BYTES + lane * SM::OROW;
+    unsigned int* hist_s = reinterpret_cast<unsigned int*>(wsm + SM::HIST_OFF);  // [bin][lane]
+    const uint32_t bar0 = smem_u32(wsm + SM::BAR_OFF), bar1 = bar0 + 8;
 
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // launch-local instance
-    const int64_t wbase = t - lane;
     const bool active = t < a.ninst;
     const int64_t inst = a.inst0 + (active ? t : 0);
 
@@ -391,7 +566,7 @@ __global__ void __launch_bounds__(TPI_TPB) k_tpi(const __grid_constant__ TpiMats
         const double* src = a.blob + inst * a.blob_stride;
         double* dst = reinterpret_cast<double*>(&Mown);
         for (int i = 0; i < (int)(sizeof(TpiMats<C>) / sizeof(double)); i++) dst[i] = 0.0;
-        // blob order == TpiMats field order with true (unpadded) lengths
+        // blob order: a b c x0 dy ey fy y0 | dq eq fqprev pexp q0 fq (true, unpadded lengths)
         int o = 0;
         auto take = [&](double* f, int n) { for (int i = 0; i < n; i++) f[i] = __ldg(src + o + i); o += n; };
         take(Mown.a, NX * NX); take(Mown.b, NX * NU); take(Mown.c, NX * NN); take(Mown.x0, NX);
@@ -406,6 +581,12 @@ __global__ void __launch_bounds__(TPI_TPB) k_tpi(const __grid_constant__ TpiMats
     static_for<0, C::NC>([&](auto i) { Cn[decltype(i)::value] = a.consts[(int64_t)decltype(i)::value * a.ld + inst]; });
     TpiState<C> S;
     double* st = a.ws + inst;
+    auto store_state = [&]() {
+        static_for<0, NX>([&](auto i) { st[(int64_t)(C::S_X + decltype(i)::value) * a.ld] = S.x[decltype(i)::value]; });
+        static_for<0, NP>([&](auto i) { st[(int64_t)(C::S_LP + decltype(i)::value) * a.ld] = S.lp[decltype(i)::value]; });
+        static_for<0, NN>([&](auto i) { st[(int64_t)(C::S_LZ + decltype(i)::value) * a.ld] = S.lz[decltype(i)::value]; });
+        static_for<0, NN * NP>([&](auto i) { st[(int64_t)(C::S_MX + decltype(i)::value) * a.ld] = S.Mx[decltype(i)::value]; });
+    };
 
     if (a.init) {
         if (!active) return;
@@ -416,10 +597,7 @@ __global__ void __launch_bounds__(TPI_TPB) k_tpi(const __grid_constant__ TpiMats
             static_for<0, NN>([&](auto i) { z0[decltype(i)::value] = a.initz[(int64_t)decltype(i)::value * a.ld + inst]; });
             tpi_set_origin<C>(m, Cn, S, p0, z0);
         }
-        static_for<0, NX>([&](auto i) { st[(int64_t)(C::S_X + decltype(i)::value) * a.ld] = S.x[decltype(i)::value]; });
-        static_for<0, NP>([&](auto i) { st[(int64_t)(C::S_LP + decltype(i)::value) * a.ld] = S.lp[decltype(i)::value]; });
-        static_for<0, NN>([&](auto i) { st[(int64_t)(C::S_LZ + decltype(i)::value) * a.ld] = S.lz[decltype(i)::value]; });
-        static_for<0, NN * NP>([&](auto i) { st[(int64_t)(C::S_MX + decltype(i)::value) * a.ld] = S.Mx[decltype(i)::value]; });
+        store_state();
         a.status[inst] = 0;
         a.first_fail[inst] = -1;
         return;
@@ -430,175 +608,125 @@ __global__ void __launch_bounds__(TPI_TPB) k_tpi(const __grid_constant__ TpiMats
     static_for<0, NN>([&](auto i) { S.lz[decltype(i)::value] = st[(int64_t)(C::S_LZ + decltype(i)::value) * a.ld]; });
     static_for<0, NN * NP>([&](auto i) { S.Mx[decltype(i)::value] = st[(int64_t)(C::S_MX + decltype(i)::value) * a.ld]; });
 
-    uint32_t status = active ? a.status[inst] : 0u;
-    bool dead = !active || (status & ACMEB200_STATUS_NONFINITE);
-    const bool shared_u = (a.u_stride == 0);
-    const bool cold_cache = (sc.solver == ACMEB200_SOLVER_HOMOTOPY_CACHING);
-    unsigned long long n_iters = 0, hpack = 0;
-    unsigned int hist[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    unsigned int n_samples = 0, n_homotopy = 0, n_notconv = 0;
-    long long first_fail = -1;
+    bool dead = !active || (a.status[inst] & ACMEB200_STATUS_NONFINITE);
+    int64_t n_alive = 0;  // samples processed before the instance died (if it did)
+    const bool shared_u = (a.u_stride == 0) || NU == 0;
+    // TMA needs 16-byte aligned row segments: even strides, 16-byte aligned bases
+    const bool tma_in = !shared_u && ((reinterpret_cast<uintptr_t>(a.U) & 15) == 0) && ((a.u_stride & 1) == 0) &&
+                        ((T * NU) % 2 == 0);
+    const bool tma_out = NY > 0 && ((reinterpret_cast<uintptr_t>(a.Y) & 15) == 0) && ((a.y_stride & 1) == 0) &&
+                         ((T * NY) % 2 == 0);
+    const double* urow = a.U + (shared_u ? 0 : t * a.u_stride);  // this lane's own stream
+    double* yrow = a.Y + t * a.y_stride;
+    const int64_t n_full = a.N / T;  // full tiles; a trailing partial tile takes the synchronous path
 
-    for (int64_t n0 = 0; n0 < a.N; n0 += T) {
-        const int cnt = (int)((a.N - n0) < T ? (a.N - n0) : T);
-        // ---- stage the input tile: 32 instances x T samples, coalesced row segments
-        if (!shared_u && NU > 0) {
-            __syncwarp();
-#pragma unroll 4
-            for (int f = lane; f < 32 * IW; f += 32) {
-                const int r = f / dim1(IW), col = f % dim1(IW);
-                const int64_t ti = wbase + r;
-                if (ti < a.ninst && col < cnt * NU)
-                    tin[r * IS + col] = __ldcs(a.U + ti * a.u_stride + n0 * NU + col);
+#pragma unroll
+    for (int b = 0; b < 8; b++) hist_s[b * 32 + lane] = 0u;
+    if (tma_in) {
+        if (lane == 0) { mbar_init(bar0, 32); mbar_init(bar1, 32); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        __syncwarp();
+        // prologue: tiles 0 and 1 in flight
+        for (int k = 0; k < 2 && k < n_full; k++) {
+            const uint32_t bar = k ? bar1 : bar0;
+            if (active) {
+                mbar_arrive_expect_tx(bar, T * NU * 8);
+                bulk_g2s(smem_u32(in_row0 + k * SM::IN_BYTES), urow + (int64_t)k * T * NU, T * NU * 8, bar);
+            } else {
+                mbar_arrive(bar);
             }
-            __syncwarp();
         }
+    }
+
+    unsigned long long hpack = 0;
+    for (int64_t n0 = 0, k = 0; n0 < a.N; n0 += T, k++) {
+        const int cnt = (int)((a.N - n0) < T ? (a.N - n0) : T);
+        const bool full = cnt == T;
+        const int buf = (int)(k & 1);
+        unsigned char* const in_cur = in_row0 + buf * SM::IN_BYTES;
+        const double* urow_s = reinterpret_cast<const double*>(in_cur);
+        if (!shared_u) {
+            if (tma_in && full) {
+                mbar_wait(buf ? bar1 : bar0, (uint32_t)((k >> 1) & 1));
+            } else {
+                // synchronous fallback (unaligned streams, trailing partial tile): own-row loads
+                __syncwarp();
+                if (active)
+                    for (int c = 0; c < cnt * NU; c++) reinterpret_cast<double*>(in_cur)[c] = __ldcs(urow + n0 * NU + c);
+            }
+        }
+        if (tma_out) bulk_wait_read0();  // the previous tile's bulk store has drained this lane's row
+        double* yrow_s = reinterpret_cast<double*>(out_row);
         for (int tt = 0; tt < cnt; tt++) {
-            double u[dim1(NU)], y[dim1(NY)], zall[dim1(NN)];
+            double u[dim1(NU)], y[dim1(NY)];
             static_for<0, NU>([&](auto kk) {
-                constexpr int k = decltype(kk)::value;
-                u[k] = shared_u ? __ldg(a.U + (n0 + tt) * NU + k) : tin[lane * IS + tt * NU + k];
+                constexpr int q = decltype(kk)::value;
+                u[q] = shared_u ? __ldg(a.U + (n0 + tt) * NU + q) : urow_s[tt * NU + q];
             });
             if (!dead) {
-                if constexpr (NN > 0) {
-                    // p = dq*x + eq*u   (ACME.jl:678-686)
-                    double p[dim1(NP)];
-                    static_for<0, NP>([&](auto ii) {
-                        constexpr int i = decltype(ii)::value;
-                        double acc = 0.0;
-                        static_for<0, NX>([&](auto jj) { acc = fma(m.dq[decltype(jj)::value * NP + i], S.x[decltype(jj)::value], acc); });
-                        static_for<0, NU>([&](auto jj) { acc = fma(m.eq[decltype(jj)::value * NP + i], u[decltype(jj)::value], acc); });
-                        p[i] = acc;
-                    });
-                    int iters = 0;
-                    bool conv;
-                    bool homotopy = false;
-                    bool need_cold = false;
-                    int cold_mode = 0;
-                    if (cold_cache) {
-                        // cheap inline test for the common case "the origin is the nearest start point"
-                        if (cache.cache_n > 0) {
-                            need_cold = true;
-                        } else {
-                            double best = 0.0, d0 = 0.0;
-                            static_for<0, NP>([&](auto ii) {
-                                constexpr int i = decltype(ii)::value;
-                                const double d = p[i] - S.lp[i];
-                                best = fma(d, d, best);
-                                d0 = fma(p[i], p[i], d0);
-                            });
-                            need_cold = d0 < best;
-                        }
-                    }
-                    if (!need_cold) {
-                        conv = tpi_simple_solve<C>(m, Cn, S, p, zall, sc, iters);
-                        if (!conv && sc.solver != ACMEB200_SOLVER_SIMPLE) { need_cold = true; cold_mode = 1; }
-                    }
-                    if (need_cold) {
-                        TpiCold<C> k;
-                        k.S = S;
-                        static_for<0, C::NC>([&](auto i) { k.Cn[decltype(i)::value] = Cn[decltype(i)::value]; });
-                        static_for<0, NP>([&](auto i) { k.p[decltype(i)::value] = p[decltype(i)::value]; });
-                        static_for<0, NN>([&](auto i) {
-                            k.z[decltype(i)::value] = zall[decltype(i)::value];
-                            k.initz[decltype(i)::value] = a.initz[(int64_t)decltype(i)::value * a.ld + inst];
-                        });
-                        k.iters = iters;
-                        conv = tpi_cold_solve<C>(&m, &k, sc, &cache, cold_mode);
-                        homotopy = k.used_homotopy != 0;
-                        S = k.S;
-                        static_for<0, NN>([&](auto i) { zall[decltype(i)::value] = k.z[decltype(i)::value]; });
-                        iters = k.iters;
-                    }
-                    n_iters += (unsigned)iters;
-                    n_homotopy += homotopy ? 1u : 0u;
-                    {
-                        int bin = iters < 1 ? 1 : iters;
-                        if (bin > ACMEB200_HIST_BINS) bin = ACMEB200_HIST_BINS;
-                        if (bin <= 8) hpack += 1ull << (8 * (bin - 1));
-                        else atomicAdd(&a.stats->iter_hist[bin - 1], 1ull);
-                    }
-                    if (!conv) {
-                        if (first_fail < 0) first_fail = a.n_done + n0 + tt;
-                        bool fin = true;
-                        static_for<0, NN>([&](auto i) { fin = fin && isfinite(zall[decltype(i)::value]); });
-                        if (fin) { status |= ACMEB200_STATUS_NOT_CONVERGED; n_notconv++; }
-                        else { status |= ACMEB200_STATUS_NONFINITE; dead = true; }
+                bool conv, homotopy, finite;
+                const int iters = tpi_step<C>(m, Cn, S, u, y, sc, cache, a, inst, conv, homotopy, finite);
+                if (NN > 0) {
+                    if (iters <= 8) hpack += 1ull << (8 * ((iters < 1 ? 1 : iters) - 1));
+                    if (iters > 8 || !conv || homotopy) {
+                        tpi_note_event<C>(a, inst, n0 + tt, iters, conv, homotopy, finite);
+                        if (!finite) dead = true;
                     }
                 }
+                if (!dead) n_alive++;
             }
-            if (!dead) {
-                // y = y0 + dy*x + ey*u + fy*z   (ACME.jl:699-706, x before the update)
-                static_for<0, NY>([&](auto ii) {
-                    constexpr int i = decltype(ii)::value;
-                    double acc = m.y0[i];
-                    static_for<0, NX>([&](auto jj) { acc = fma(m.dy[decltype(jj)::value * NY + i], S.x[decltype(jj)::value], acc); });
-                    static_for<0, NU>([&](auto jj) { acc = fma(m.ey[decltype(jj)::value * NY + i], u[decltype(jj)::value], acc); });
-                    static_for<0, NN>([&](auto jj) { acc = fma(m.fy[decltype(jj)::value * NY + i], zall[decltype(jj)::value], acc); });
-                    y[i] = acc;
-                });
-                // x = x0 + a*x + b*u + c*z      (ACME.jl:708-714)
-                double xn[dim1(NX)];
-                static_for<0, NX>([&](auto ii) {
-                    constexpr int i = decltype(ii)::value;
-                    double acc = m.x0[i];
-                    static_for<0, NX>([&](auto jj) { acc = fma(m.a[decltype(jj)::value * NX + i], S.x[decltype(jj)::value], acc); });
-                    static_for<0, NU>([&](auto jj) { acc = fma(m.b[decltype(jj)::value * NX + i], u[decltype(jj)::value], acc); });
-                    static_for<0, NN>([&](auto jj) { acc = fma(m.c[decltype(jj)::value * NX + i], zall[decltype(jj)::value], acc); });
-                    xn[i] = acc;
-                });
-                static_for<0, NX>([&](auto i) { S.x[decltype(i)::value] = xn[decltype(i)::value]; });
-                n_samples++;
-            } else {
-                static_for<0, NY>([&](auto i) { y[decltype(i)::value] = NAN; });
-            }
-            static_for<0, NY>([&](auto kk) { tout[lane * OS + tt * NY + decltype(kk)::value] = y[decltype(kk)::value]; });
+            if (dead) static_for<0, NY>([&](auto i) { y[decltype(i)::value] = NAN; });
+            static_for<0, NY>([&](auto kk) { yrow_s[tt * NY + decltype(kk)::value] = y[decltype(kk)::value]; });
         }
-        // fold the packed per-tile histogram (<= 16 per 8-bit field) into the 32-bit bins
-        static_for<0, 8>([&](auto i) { hist[decltype(i)::value] += (unsigned)((hpack >> (8 * decltype(i)::value)) & 0xffu); });
+        // fold the packed per-tile histogram (<= T <= 255 per 8-bit field) into shared memory
+#pragma unroll
+        for (int b = 0; b < 8; b++) hist_s[b * 32 + lane] += (unsigned)((hpack >> (8 * b)) & 0xffu);
         hpack = 0;
-        // ---- write the output tile back, coalesced
-        if (NY > 0) {
-            __syncwarp();
-#pragma unroll 4
-            for (int f = lane; f < 32 * OW; f += 32) {
-                const int r = f / dim1(OW), col = f % dim1(OW);
-                const int64_t ti = wbase + r;
-                if (ti < a.ninst && col < cnt * NY)
-                    __stcs(a.Y + ti * a.y_stride + n0 * NY + col, tout[r * OS + col]);
+        // ---- output tile
+        if (NY > 0 && active) {
+            if (tma_out && full) {
+                fence_async_smem();
+                bulk_s2g(yrow + n0 * NY, smem_u32(out_row), T * NY * 8);
+                bulk_commit();
+            } else {
+                for (int c = 0; c < cnt * NY; c++) __stcs(yrow + n0 * NY + c, yrow_s[c]);
+            }
+        }
+        // ---- refill this input buffer with tile k+2
+        if (tma_in && k + 2 < n_full) {
+            const uint32_t bar = buf ? bar1 : bar0;
+            if (active) {
+                mbar_arrive_expect_tx(bar, T * NU * 8);
+                bulk_g2s(smem_u32(in_cur), urow + (k + 2) * T * NU, T * NU * 8, bar);
+            } else {
+                mbar_arrive(bar);
             }
         }
     }
+    if (tma_out) bulk_wait_all();
 
-    if (active) {
-        static_for<0, NX>([&](auto i) { st[(int64_t)(C::S_X + decltype(i)::value) * a.ld] = S.x[decltype(i)::value]; });
-        static_for<0, NP>([&](auto i) { st[(int64_t)(C::S_LP + decltype(i)::value) * a.ld] = S.lp[decltype(i)::value]; });
-        static_for<0, NN>([&](auto i) { st[(int64_t)(C::S_LZ + decltype(i)::value) * a.ld] = S.lz[decltype(i)::value]; });
-        static_for<0, NN * NP>([&](auto i) { st[(int64_t)(C::S_MX + decltype(i)::value) * a.ld] = S.Mx[decltype(i)::value]; });
-        a.status[inst] = status;
-        if (first_fail >= 0 && a.first_fail[inst] < 0) a.first_fail[inst] = first_fail;
-    }
+    if (active) store_state();
     // warp-reduce the counters, one set of atomics per warp
-    const unsigned full = 0xffffffffu;
-    unsigned s_samples = __reduce_add_sync(full, n_samples);
-    unsigned s_hom = __reduce_add_sync(full, n_homotopy);
-    unsigned s_nc = __reduce_add_sync(full, n_notconv);
-    unsigned it_lo = __reduce_add_sync(full, (unsigned)(n_iters & 0xffffu));
-    unsigned it_hi = __reduce_add_sync(full, (unsigned)(n_iters >> 16));
+    const unsigned full_mask = 0xffffffffu;
     unsigned hsum[8];
-    static_for<0, 8>([&](auto i) { hsum[decltype(i)::value] = __reduce_add_sync(full, hist[decltype(i)::value]); });
+    unsigned long long it_sum = 0;
+#pragma unroll
+    for (int b = 0; b < 8; b++) {
+        hsum[b] = __reduce_add_sync(full_mask, hist_s[b * 32 + lane]);
+        it_sum += (unsigned long long)hsum[b] * (b + 1);
+    }
+    const unsigned na_lo = __reduce_add_sync(full_mask, (unsigned)(n_alive & 0xffffff));
+    const unsigned na_hi = __reduce_add_sync(full_mask, (unsigned)(n_alive >> 24));
     if (lane == 0) {
-        if (s_samples) {
-            atomicAdd(&a.stats->samples, (unsigned long long)s_samples);
-            if (NN > 0) atomicAdd(&a.stats->solves, (unsigned long long)s_samples);
+        const unsigned long long ns = (unsigned long long)na_lo + ((unsigned long long)na_hi << 24);
+        if (ns) {
+            atomicAdd(&a.stats->samples, ns);
+            if (NN > 0) atomicAdd(&a.stats->solves, ns);
         }
-        const unsigned long long its = (unsigned long long)it_lo + ((unsigned long long)it_hi << 16);
-        if (its) atomicAdd(&a.stats->newton_iters, its);
-        if (s_hom) atomicAdd(&a.stats->homotopy_solves, (unsigned long long)s_hom);
-        if (s_nc) atomicAdd(&a.stats->not_converged, (unsigned long long)s_nc);
-        static_for<0, 8>([&](auto i) {
-            if (hsum[decltype(i)::value]) atomicAdd(&a.stats->iter_hist[decltype(i)::value], (unsigned long long)hsum[decltype(i)::value]);
-        });
+        if (it_sum) atomicAdd(&a.stats->newton_iters, it_sum);
+#pragma unroll
+        for (int b = 0; b < 8; b++)
+            if (hsum[b]) atomicAdd(&a.stats->iter_hist[b], (unsigned long long)hsum[b]);
     }
 }
 

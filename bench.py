@@ -170,6 +170,7 @@ def run_reference(args, rank: int, world: int):
 
 
 def main():
+    global N_SAMPLES
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -183,7 +184,6 @@ def main():
                     "smaller values are for profiling under ncu only, such a line is not a bench value)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
-    global N_SAMPLES
     N_SAMPLES = args.samples
 
     rank = int(os.environ.get("RANK", 0))
