@@ -97,7 +97,7 @@ template <class C>
 static cudaError_t launch_tpi(const acmeb200_model* m, const RunArgs& a, cudaStream_t stream) {
     TpiMats<C> M;
     fill_tpi_mats<C>(m->dm, m->h_blob.data(), M);
-    SolverCfg sc{m->dm.tol, m->dm.maxiter, m->dm.solver};
+    SolverCfg sc{m->dm.tol, m->dm.maxiter, m->dm.solver, make_exp_table()};
     DevSub cache;
     memset(&cache, 0, sizeof cache);
     if (m->dm.nsub > 0) cache = m->dm.subs[0];

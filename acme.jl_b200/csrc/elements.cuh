@@ -48,8 +48,7 @@ __constant__ double ACME_EXPC[16] = {
     0x1.000000000000bp-1,
     1.0, 0.0};
 
-__device__ __forceinline__ double acme_exp(double x) {
-    const double* K = ACME_EXPC;
+__device__ __forceinline__ double acme_exp(double x, const double* __restrict__ K) {
     double t = fma(x, K[0], K[1]);
     const int i = __double2loint(t);
     t = t - K[1];
@@ -81,10 +80,19 @@ __device__ __forceinline__ double acme_exp(double x) {
 #endif
 // host passes of the __host__ __device__ element code never evaluate laws (the host only runs prep)
 #ifdef __CUDA_ARCH__
-#define ACME_EXPD(x) acme_exp(x)
+#define ACME_EXPD(x) acme_exp(x, K)
 #else
 #define ACME_EXPD(x) exp(x)
 #endif
+// the table as a plain struct so kernels can also receive it as a __grid_constant__ parameter
+// (param-space constants are eligible for uniform-register operands)
+struct ExpTable { double k[16]; };
+inline ExpTable make_exp_table() {
+    return ExpTable{{0x1.71547652b82fep+0, 0x1.8000000000000p+52, -0x1.62e42fefa39efp-1, -0x1.abc9e3b39803fp-56,
+                     0x1.ade1569ce2bdfp-26, 0x1.28af3fca213eap-22, 0x1.71dee62401315p-19, 0x1.a01997c89eb71p-16,
+                     0x1.a01a014761f65p-13, 0x1.6c16c1852b7afp-10, 0x1.1111111122322p-7, 0x1.55555555502a1p-5,
+                     0x1.5555555555511p-3, 0x1.000000000000bp-1, 1.0, 0.0}};
+}
 
 struct Diode {  // elements.jl:236-245
     static constexpr int KIND = ACMEB200_ELEM_DIODE, NN = 1, NQ = 2, NPAR = 2, NC = 3, NJ = 1;
@@ -94,7 +102,7 @@ struct Diode {  // elements.jl:236-245
         C[1] = 1 / (25e-3 * eta);
         C[2] = is / (25e-3 * eta);
     }
-    ACME_DI static void eval(const double* C, const double* q, double* res, double* jv) {
+    ACME_DI static void eval(const double* C, const double* q, double* res, double* jv, const double* K = nullptr) {
         const double ex = ACME_EXPD(q[0] * C[1]);
         res[0] = C[0] * (ex - 1) - q[1];
         jv[0] = C[2] * ex;
@@ -107,7 +115,7 @@ struct Diode {  // elements.jl:236-245
 struct Pot {  // elements.jl:20-31
     static constexpr int KIND = ACMEB200_ELEM_POT, NN = 2, NQ = 5, NPAR = 1, NC = 1, NJ = 4;
     ACME_DI static void prep(const double* P, double* C) { C[0] = P[0]; }
-    ACME_DI static void eval(const double* C, const double* q, double* res, double* jv) {
+    ACME_DI static void eval(const double* C, const double* q, double* res, double* jv, const double* K = nullptr) {
         const double r = C[0];
         const double v1 = q[0], v2 = q[1], i1 = q[2], i2 = q[3], pos = q[4];
         res[0] = v1 - r * pos * i1;
@@ -130,7 +138,7 @@ struct OpampTanh {  // elements.jl:536-551
         C[1] = P[1];         // scale
         C[2] = P[0] / P[1];  // gain/scale
     }
-    ACME_DI static void eval(const double* C, const double* q, double* res, double* jv) {
+    ACME_DI static void eval(const double* C, const double* q, double* res, double* jv, const double* K = nullptr) {
         const double vs = q[0] * C[2];
         const double ch = cosh(vs);
         res[0] = tanh(vs) * C[1] - q[1];
@@ -144,7 +152,7 @@ struct OpampTanh {  // elements.jl:536-551
 struct TestQuad {  // test/runtests.jl:207-219
     static constexpr int KIND = ACMEB200_ELEM_TEST_QUAD, NN = 1, NQ = 2, NPAR = 0, NC = 1, NJ = 1;
     ACME_DI static void prep(const double*, double* C) { C[0] = 0; }
-    ACME_DI static void eval(const double*, const double* q, double* res, double* jv) {
+    ACME_DI static void eval(const double*, const double* q, double* res, double* jv, const double* K = nullptr) {
         res[0] = q[0] * q[0] - 1 + q[1];
         jv[0] = 2 * q[0];
     }
@@ -189,7 +197,7 @@ struct Bjt {  // elements.jl:309-406
         if (ncl != nc) flags |= 32;
         C[19] = (double)flags;
     }
-    ACME_DI static void eval(const double* C, const double* q, double* res, double* jv) {
+    ACME_DI static void eval(const double* C, const double* q, double* res, double* jv, const double* K = nullptr) {
         const int flags = (int)C[19];
         const double vE = q[0], vC = q[1], iE = q[2], iC = q[3];
         const double expE = ACME_EXPD(vE * C[0]);
@@ -265,7 +273,7 @@ struct Mosfet {  // elements.jl:436-481
         for (int i = n - 2; i >= 0; i--) acc = fma(x, acc, c[i]);
         return acc;
     }
-    ACME_DI static void eval(const double* C, const double* q, double* res, double* jv) {
+    ACME_DI static void eval(const double* C, const double* q, double* res, double* jv, const double* K = nullptr) {
         const double pol = C[0], lam = C[1];
         const int nvt = (int)C[2], nal = (int)C[3];
         const double *vt = C + 4, *al = C + 8;
@@ -307,7 +315,7 @@ struct JilesAtherton {  // elements.jl:104-135
         for (int i = 0; i < 5; i++) C[i] = P[i];
     }
     ACME_DI static double sgn(double x) { return (double)((x > 0) - (x < 0)); }
-    ACME_DI static void eval(const double* C, const double* q, double* res, double* jv) {
+    ACME_DI static void eval(const double* C, const double* q, double* res, double* jv, const double* K = nullptr) {
         const double Ms = C[0], a = C[1], alpha = C[2], c = C[3], k = C[4];
         const double q1 = q[0], q2 = q[1], q3 = q[2], q4 = q[3];
         const double coth_q1 = 1 / tanh(q1);

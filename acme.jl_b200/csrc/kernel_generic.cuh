@@ -45,8 +45,8 @@ __device__ __forceinline__ double elem_row(int kind, int r, const double* jv, F 
 __device__ __forceinline__ void elem_eval(int kind, const double* C, const double* q, double* res,
                                           double* jv) {
     switch (kind) {
-        case Diode::KIND: Diode::eval(C, q, res, jv); break;
-        case Bjt::KIND: Bjt::eval(C, q, res, jv); break;
+        case Diode::KIND: Diode::eval(C, q, res, jv, ACME_EXPC); break;
+        case Bjt::KIND: Bjt::eval(C, q, res, jv, ACME_EXPC); break;
         case Pot::KIND: Pot::eval(C, q, res, jv); break;
         case Mosfet::KIND: Mosfet::eval(C, q, res, jv); break;
         case OpampTanh::KIND: OpampTanh::eval(C, q, res, jv); break;
@@ -141,7 +141,8 @@ __device__ inline bool g_lu(const GCtx& g, int n, int A, int piv) {
         }
         for (int j = k + 1; j < n; j++) {
             const double akj = g.w(A + j * n + k);
-            for (int i = k + 1; i < n; i++) g.w(A + j * n + i) = fma(-g.w(A + k * n + i), akj, g.w(A + j * n + i));
+            for (int i = k + 1; i < n; i++)  // not fused, like the reference's scalar LU (exact zero pivots)
+                g.w(A + j * n + i) = __dsub_rn(g.w(A + j * n + i), __dmul_rn(g.w(A + k * n + i), akj));
         }
     }
     return true;
@@ -157,12 +158,12 @@ __device__ inline void g_lusolve(const GCtx& g, int n, int A, int piv, int xr) {
     }
     for (int j = 0; j < n; j++) {
         const double xj = g.w(xr + j);
-        for (int i = j + 1; i < n; i++) g.w(xr + i) = fma(-g.w(A + j * n + i), xj, g.w(xr + i));
+        for (int i = j + 1; i < n; i++) g.w(xr + i) = __dsub_rn(g.w(xr + i), __dmul_rn(g.w(A + j * n + i), xj));
     }
     for (int j = n - 1; j >= 0; j--) {
         const double xj = g.w(A + j * n + j) * g.w(xr + j);
         g.w(xr + j) = xj;
-        for (int i = 0; i < j; i++) g.w(xr + i) = fma(-g.w(A + j * n + i), xj, g.w(xr + i));
+        for (int i = 0; i < j; i++) g.w(xr + i) = __dsub_rn(g.w(xr + i), __dmul_rn(g.w(A + j * n + i), xj));
     }
 }
 

@@ -74,6 +74,7 @@ struct SolverCfg {
     double tol;
     int maxiter;
     int solver;
+    ExpTable ek;  // exp() constants in parameter space (uniform-register operands)
 };
 
 template <class C>
@@ -81,7 +82,10 @@ struct TpiState {  // what persists from sample to sample
     double x[dim1(C::NX)], lp[dim1(C::NP)], lz[dim1(C::NN)], Mx[dim1(C::NN * C::NP)];
 };
 
-// ---- small dense LU in registers: setlhs!/solve! (solvers.jl:46-132), fully unrolled ----
+// ---- small dense LU in registers: setlhs!/solve! (solvers.jl:46-132), fully unrolled.
+// Deliberately NOT fused (no FMA): the reference's LU is plain scalar Julia, and an exactly
+// singular Jacobian has to give an exactly zero pivot so that Newton bails out into the homotopy
+// (with FMA the pivot becomes rounding noise and Newton wanders for hundreds of iterations). ----
 template <int N>
 __device__ __forceinline__ bool lu_reg(double (&A)[dim1(N * N)], int (&piv)[dim1(N)]) {
     bool ok = true;
@@ -115,7 +119,7 @@ __device__ __forceinline__ bool lu_reg(double (&A)[dim1(N * N)], int (&piv)[dim1
             const double akj = A[j * N + k];
             static_for<k + 1, N>([&](auto ii) {
                 constexpr int i = decltype(ii)::value;
-                A[j * N + i] = fma(-A[k * N + i], akj, A[j * N + i]);
+                A[j * N + i] = __dsub_rn(A[j * N + i], __dmul_rn(A[k * N + i], akj));
             });
         });
     });
@@ -136,7 +140,7 @@ __device__ __forceinline__ void lu_solve_reg(const double (&A)[dim1(N * N)], con
         constexpr int j = decltype(jj)::value;
         static_for<j + 1, N>([&](auto ii) {
             constexpr int i = decltype(ii)::value;
-            x[i] = fma(-A[j * N + i], x[j], x[i]);
+            x[i] = __dsub_rn(x[i], __dmul_rn(A[j * N + i], x[j]));
         });
     });
     static_for<0, N>([&](auto jr) {
@@ -144,7 +148,7 @@ __device__ __forceinline__ void lu_solve_reg(const double (&A)[dim1(N * N)], con
         x[j] = A[j * N + j] * x[j];
         static_for<0, j>([&](auto ii) {
             constexpr int i = decltype(ii)::value;
-            x[i] = fma(-A[j * N + i], x[j], x[i]);
+            x[i] = __dsub_rn(x[i], __dmul_rn(A[j * N + i], x[j]));
         });
     });
 }
@@ -168,7 +172,7 @@ template <class C, class M>
 __device__ __forceinline__ double tpi_evaluate(const M& m, const double (&Cn)[dim1(C::NC)],
                                                const double (&pfull)[dim1(C::NQ)], const double (&z)[dim1(C::NN)],
                                                double (&res)[dim1(C::NN)], double (&jv)[dim1(C::NJ)],
-                                               double (&J)[dim1(C::NN * C::NN)], bool& Jfinite) {
+                                               double (&J)[dim1(C::NN * C::NN)], bool& Jfinite, const SolverCfg& sc) {
     double q[dim1(C::NQ)];
     static_for<0, C::NQ>([&](auto ii) {
         constexpr int i = decltype(ii)::value;
@@ -188,7 +192,7 @@ __device__ __forceinline__ double tpi_evaluate(const M& m, const double (&Cn)[di
         using E = decltype(e);
         constexpr int ROW = decltype(row)::value, QOFF = decltype(qoff)::value, COFF = decltype(coff)::value,
                       JOFF = decltype(joff)::value;
-        E::eval(&Cn[COFF], &q[QOFF], &res[ROW], &jv[JOFF]);
+        E::eval(&Cn[COFF], &q[QOFF], &res[ROW], &jv[JOFF], sc.ek.k);
         static_for<0, E::NJ>([&](auto kk) { jsum += fabs(jv[JOFF + decltype(kk)::value]); });
         static_for<0, E::NN>([&](auto rr) {
             constexpr int r = decltype(rr)::value;
@@ -232,39 +236,61 @@ __device__ __forceinline__ void tpi_update_Mx(const M& m, const double (&jv)[dim
 // set_extrapolation_origin(solver, p, z)  (solvers.jl:183-196)
 template <class C, class M>
 __device__ __forceinline__ void tpi_set_origin(const M& m, const double (&Cn)[dim1(C::NC)], TpiState<C>& S,
-                                               const double (&p)[dim1(C::NP)], const double (&z)[dim1(C::NN)]) {
+                                               const double (&p)[dim1(C::NP)], const double (&z)[dim1(C::NN)],
+                                               const SolverCfg& sc) {
     double pfull[dim1(C::NQ)], res[dim1(C::NN)], jv[dim1(C::NJ)], J[dim1(C::NN * C::NN)];
     int piv[dim1(C::NN)];
     bool Jfin;
     tpi_set_p<C>(m, p, pfull);
-    tpi_evaluate<C>(m, Cn, pfull, z, res, jv, J, Jfin);
+    tpi_evaluate<C>(m, Cn, pfull, z, res, jv, J, Jfin, sc);
     lu_reg<C::NN>(J, piv);
     tpi_update_Mx<C>(m, jv, J, piv, S.Mx);
     static_for<0, C::NP>([&](auto i) { S.lp[decltype(i)::value] = p[decltype(i)::value]; });
     static_for<0, C::NN>([&](auto i) { S.lz[decltype(i)::value] = z[decltype(i)::value]; });
 }
 
-// solve(::SimpleSolver, p)  (solvers.jl:207-236)
+// solve(::SimpleSolver, p)  (solvers.jl:207-236).  With `reorigin` the solve is preceded by
+// set_extrapolation_origin(solver, 0, init_z) (solvers.jl:183-196): that is what a fresh
+// CachingSolver does when p is nearer to its only cached point (p = 0) than to the current origin
+// (solvers.jl:347-371).  The origin evaluation runs as "iteration 0" of the same loop so that the
+// element laws and the LU exist once in the instruction stream.
 template <class C, class M>
 __device__ __forceinline__ bool tpi_simple_solve(const M& m, const double (&Cn)[dim1(C::NC)], TpiState<C>& S,
                                                  const double (&p)[dim1(C::NP)], double (&z)[dim1(C::NN)],
-                                                 const SolverCfg& sc, int& iters) {
+                                                 const SolverCfg& sc, int& iters, bool reorigin = false,
+                                                 const double* iz = nullptr, int64_t iz_ld = 0) {
     double pfull[dim1(C::NQ)], res[dim1(C::NN)], jv[dim1(C::NJ)], J[dim1(C::NN * C::NN)];
     int piv[dim1(C::NN)];
-    tpi_set_p<C>(m, p, pfull);
-    static_for<0, C::NN>([&](auto ii) {
-        constexpr int i = decltype(ii)::value;
-        double acc = S.lz[i];
-        static_for<0, C::NP>([&](auto jj) {
-            constexpr int j = decltype(jj)::value;
-            acc = fma(-S.Mx[j * C::NN + i], p[j] - S.lp[j], acc);
+    auto start_from_origin = [&]() {
+        tpi_set_p<C>(m, p, pfull);
+        static_for<0, C::NN>([&](auto ii) {
+            constexpr int i = decltype(ii)::value;
+            double acc = S.lz[i];
+            static_for<0, C::NP>([&](auto jj) {
+                constexpr int j = decltype(jj)::value;
+                acc = fma(-S.Mx[j * C::NN + i], p[j] - S.lp[j], acc);
+            });
+            z[i] = acc;
         });
-        z[i] = acc;
-    });
+    };
+    if (reorigin) {
+        static_for<0, C::NQ>([&](auto i) { pfull[decltype(i)::value] = m.q0[decltype(i)::value]; });  // set_p!(0)
+        static_for<0, C::NN>([&](auto i) { z[decltype(i)::value] = iz[(int64_t)decltype(i)::value * iz_ld]; });
+    } else {
+        start_from_origin();
+    }
     bool converged = false;
-    for (iters = 1; iters <= sc.maxiter; iters++) {
+    for (iters = reorigin ? 0 : 1; iters <= sc.maxiter; iters++) {
         bool Jfin;
-        const double resmax = tpi_evaluate<C>(m, Cn, pfull, z, res, jv, J, Jfin);
+        const double resmax = tpi_evaluate<C>(m, Cn, pfull, z, res, jv, J, Jfin, sc);
+        if (iters == 0) {
+            lu_reg<C::NN>(J, piv);
+            tpi_update_Mx<C>(m, jv, J, piv, S.Mx);
+            static_for<0, C::NP>([&](auto i) { S.lp[decltype(i)::value] = 0.0; });
+            static_for<0, C::NN>([&](auto i) { S.lz[decltype(i)::value] = z[decltype(i)::value]; });
+            start_from_origin();
+            continue;
+        }
         if (!Jfin) return resmax < sc.tol;
         if (!lu_reg<C::NN>(J, piv)) return resmax < sc.tol;
         if (resmax < sc.tol) { converged = true; break; }
@@ -317,7 +343,7 @@ __device__ __forceinline__ bool tpi_base_solve_cold(const M& m, TpiCold<C>& k, c
                 for (int i = 0; i < C::NN; i++) cz[i] = k.initz[i];
             }
         }
-        if (take) tpi_set_origin<C>(m, k.Cn, k.S, cp, cz);
+        if (take) tpi_set_origin<C>(m, k.Cn, k.S, cp, cz, sc);
     }
     return tpi_simple_solve<C>(m, k.Cn, k.S, p, k.z, sc, iters);
 }
@@ -326,8 +352,9 @@ __device__ __forceinline__ bool tpi_base_solve_cold(const M& m, TpiCold<C>& k, c
 // (solve(::HomotopySolver, p), solvers.jl:268-296); mode 1 = the base solve has
 // already failed in the hot path, go straight to the homotopy.
 template <class C, class M>
-__device__ __noinline__ bool tpi_cold_solve(const M* mp, TpiCold<C>* kp, SolverCfg sc, const DevSub* cache,
+__device__ __noinline__ bool tpi_cold_solve(const M* mp, TpiCold<C>* kp, const SolverCfg* scp, const DevSub* cache,
                                             int mode) {
+    const SolverCfg& sc = *scp;
     const M& m = *mp;
     TpiCold<C>& k = *kp;
     bool conv = false;
@@ -434,70 +461,25 @@ constexpr size_t tpi_smem_bytes() {
     return (size_t)(TPI_TPB / 32) * TpiSmem<C>::PER_WARP;
 }
 
-// one sample of one instance: step! (ACME.jl:666-715).  Returns the Newton iteration count
-// (0 for linear models); `conv` is false if the solve failed.
+// p = dq*x + eq*u   (ACME.jl:678-686)
 template <class C, class M>
-__device__ __forceinline__ int tpi_step(const M& m, const double (&Cn)[dim1(C::NC)], TpiState<C>& S,
-                                        const double (&u)[dim1(C::NU)], double (&y)[dim1(C::NY)],
-                                        const SolverCfg& sc, const DevSub& cache, const RunArgs& a, int64_t inst,
-                                        bool& conv, bool& homotopy, bool& finite) {
-    constexpr int NX = C::NX, NU = C::NU, NY = C::NY, NN = C::NN, NP = C::NP;
-    double zall[dim1(NN)];
-    int iters = 0;
-    conv = true;
-    homotopy = false;
-    finite = true;
-    if constexpr (NN > 0) {
-        // p = dq*x + eq*u   (ACME.jl:678-686)
-        double p[dim1(NP)];
-        static_for<0, NP>([&](auto ii) {
-            constexpr int i = decltype(ii)::value;
-            double acc = 0.0;
-            static_for<0, NX>([&](auto jj) { acc = fma(m.dq[decltype(jj)::value * NP + i], S.x[decltype(jj)::value], acc); });
-            static_for<0, NU>([&](auto jj) { acc = fma(m.eq[decltype(jj)::value * NP + i], u[decltype(jj)::value], acc); });
-            p[i] = acc;
-        });
-        bool need_cold = false;
-        int cold_mode = 0;
-        if (sc.solver == ACMEB200_SOLVER_HOMOTOPY_CACHING) {
-            // cheap inline test for the common case "the current origin is the nearest start point"
-            if (cache.cache_n > 0) {
-                need_cold = true;
-            } else {
-                double best = 0.0, d0 = 0.0;
-                static_for<0, NP>([&](auto ii) {
-                    constexpr int i = decltype(ii)::value;
-                    const double d = p[i] - S.lp[i];
-                    best = fma(d, d, best);
-                    d0 = fma(p[i], p[i], d0);
-                });
-                need_cold = d0 < best;
-            }
-        }
-        if (!need_cold) {
-            conv = tpi_simple_solve<C>(m, Cn, S, p, zall, sc, iters);
-            if (!conv && sc.solver != ACMEB200_SOLVER_SIMPLE) { need_cold = true; cold_mode = 1; }
-        }
-        if (need_cold) {
-            TpiCold<C> k;
-            k.S = S;
-            static_for<0, C::NC>([&](auto i) { k.Cn[decltype(i)::value] = Cn[decltype(i)::value]; });
-            static_for<0, NP>([&](auto i) { k.p[decltype(i)::value] = p[decltype(i)::value]; });
-            static_for<0, NN>([&](auto i) {
-                k.z[decltype(i)::value] = zall[decltype(i)::value];
-                k.initz[decltype(i)::value] = a.initz[(int64_t)decltype(i)::value * a.ld + inst];
-            });
-            k.iters = iters;
-            conv = tpi_cold_solve<C>(&m, &k, sc, &cache, cold_mode);
-            homotopy = k.used_homotopy != 0;
-            S = k.S;
-            static_for<0, NN>([&](auto i) { zall[decltype(i)::value] = k.z[decltype(i)::value]; });
-            iters = k.iters;
-        }
-        if (!conv) static_for<0, NN>([&](auto i) { finite = finite && isfinite(zall[decltype(i)::value]); });
-        if (!finite) return iters;
-    }
-    // y = y0 + dy*x + ey*u + fy*z   (ACME.jl:699-706, x before the update)
+__device__ __forceinline__ void tpi_calc_p(const M& m, const TpiState<C>& S, const double (&u)[dim1(C::NU)],
+                                           double (&p)[dim1(C::NP)]) {
+    constexpr int NX = C::NX, NU = C::NU, NP = C::NP;
+    static_for<0, NP>([&](auto ii) {
+        constexpr int i = decltype(ii)::value;
+        double acc = 0.0;
+        static_for<0, NX>([&](auto jj) { acc = fma(m.dq[decltype(jj)::value * NP + i], S.x[decltype(jj)::value], acc); });
+        static_for<0, NU>([&](auto jj) { acc = fma(m.eq[decltype(jj)::value * NP + i], u[decltype(jj)::value], acc); });
+        p[i] = acc;
+    });
+}
+
+// y = y0 + dy*x + ey*u + fy*z (x before the update) and x = x0 + a*x + b*u + c*z  (ACME.jl:699-714)
+template <class C, class M>
+__device__ __forceinline__ void tpi_output_update(const M& m, TpiState<C>& S, const double (&u)[dim1(C::NU)],
+                                                  const double (&zall)[dim1(C::NN)], double (&y)[dim1(C::NY)]) {
+    constexpr int NX = C::NX, NU = C::NU, NY = C::NY, NN = C::NN;
     static_for<0, NY>([&](auto ii) {
         constexpr int i = decltype(ii)::value;
         double acc = m.y0[i];
@@ -506,7 +488,6 @@ __device__ __forceinline__ int tpi_step(const M& m, const double (&Cn)[dim1(C::N
         static_for<0, NN>([&](auto jj) { acc = fma(m.fy[decltype(jj)::value * NY + i], zall[decltype(jj)::value], acc); });
         y[i] = acc;
     });
-    // x = x0 + a*x + b*u + c*z      (ACME.jl:708-714)
     double xn[dim1(NX)];
     static_for<0, NX>([&](auto ii) {
         constexpr int i = decltype(ii)::value;
@@ -517,17 +498,81 @@ __device__ __forceinline__ int tpi_step(const M& m, const double (&Cn)[dim1(C::N
         xn[i] = acc;
     });
     static_for<0, NX>([&](auto i) { S.x[decltype(i)::value] = xn[decltype(i)::value]; });
+}
+
+// Hot step: the common case of step! (ACME.jl:666-715) -- the origin is the nearest start point
+// and plain Newton converges.  Returns the iteration count (>= 1; 0 for linear models) when the
+// sample was completed, or -(iters+1) when the cold path has to take this sample over (cache
+// lookup says another start point is nearer, or Newton failed); the state is untouched then.
+template <class C, class M>
+__device__ __forceinline__ int tpi_step_hot(const M& m, const double (&Cn)[dim1(C::NC)], TpiState<C>& S,
+                                            const double (&u)[dim1(C::NU)], double (&y)[dim1(C::NY)],
+                                            const SolverCfg& sc, const DevSub& cache, const double* iz, int64_t iz_ld) {
+    constexpr int NN = C::NN, NP = C::NP;
+    double zall[dim1(NN)];
+    int iters = 0;
+    if constexpr (NN > 0) {
+        double p[dim1(NP)];
+        tpi_calc_p<C>(m, S, u, p);
+        bool reorigin = false;
+        if (sc.solver == ACMEB200_SOLVER_HOMOTOPY_CACHING) {
+            if (cache.cache_n > 0) return -1;  // frozen k-d tree: the cold path does the lookup
+            double best = 0.0, d0 = 0.0;
+            static_for<0, NP>([&](auto ii) {
+                constexpr int i = decltype(ii)::value;
+                const double d = p[i] - S.lp[i];
+                best = fma(d, d, best);
+                d0 = fma(p[i], p[i], d0);
+            });
+            reorigin = d0 < best;  // the cached (0, init_z) is the nearer start point
+        }
+        if (!tpi_simple_solve<C>(m, Cn, S, p, zall, sc, iters, reorigin, iz, iz_ld)) {
+            if (sc.solver != ACMEB200_SOLVER_SIMPLE) return -(iters + 1);
+            return -(iters + 1) - (1 << 20);  // SimpleSolver only: no homotopy, the failure is final
+        }
+    }
+    tpi_output_update<C>(m, S, u, zall, y);
     return iters;
 }
 
-// rare events (failed solve, homotopy, > 8 iterations) go straight to global memory so that the
-// hot loop carries no bookkeeping registers for them
-template <class C>
-__device__ __noinline__ void tpi_note_event(const RunArgs a, int64_t inst, int64_t n, int iters, bool conv,
-                                            bool homotopy, bool finite) {
-    if (homotopy) atomicAdd(&a.stats->homotopy_solves, 1ull);
+// Cold step: everything else (frozen-cache start points, homotopy, failures).  `code` is the
+// negative value the hot step returned.  Out of line on purpose: its register needs must not
+// shape the hot loop.
+template <class C, class M>
+__device__ __noinline__ int tpi_step_cold(const M* mp, const double* Cn_, TpiState<C>* Sp, const double* u_,
+                                          double* y_, const SolverCfg* scp, const DevSub* cachep, const RunArgs* ap,
+                                          int64_t inst, int n, int code) {
+    constexpr int NN = C::NN, NP = C::NP, NU = C::NU, NY = C::NY;
+    const M& m = *mp;
+    const SolverCfg& sc = *scp;
+    const RunArgs& a = *ap;
+    TpiCold<C> k;
+    k.S = *Sp;
+    for (int i = 0; i < C::NC; i++) k.Cn[i] = Cn_[i];
+    double u[dim1(NU)], y[dim1(NY)];
+    for (int i = 0; i < NU; i++) u[i] = u_[i];
+    tpi_calc_p<C>(m, k.S, u, k.p);
+    for (int i = 0; i < NN; i++) { k.z[i] = 0.0; k.initz[i] = a.initz[(int64_t)i * a.ld + inst]; }
+    const bool final_fail = code <= -(1 << 20);
+    const int failed_iters = final_fail ? (-(code + (1 << 20)) - 1) : (-code - 1);
+    bool conv = false;
+    k.used_homotopy = 0;
+    if (final_fail) {
+        k.iters = failed_iters;
+        // recompute the last iterate for the finite/non-finite distinction
+        int it;
+        conv = tpi_simple_solve<C>(m, k.Cn, k.S, k.p, k.z, sc, it);
+        k.iters = it;
+    } else {
+        k.iters = failed_iters;
+        conv = tpi_cold_solve<C>(&m, &k, &sc, cachep, failed_iters > 0 ? 1 : 0);
+    }
+    const int iters = k.iters;
+    bool finite = true;
+    if (!conv) for (int i = 0; i < NN; i++) finite = finite && isfinite(k.z[i]);
+    if (k.used_homotopy) atomicAdd(&a.stats->homotopy_solves, 1ull);
     if (iters > 8) {
-        int bin = iters > ACMEB200_HIST_BINS ? ACMEB200_HIST_BINS : iters;
+        const int bin = iters > ACMEB200_HIST_BINS ? ACMEB200_HIST_BINS : iters;
         atomicAdd(&a.stats->iter_hist[bin - 1], 1ull);
         atomicAdd(&a.stats->newton_iters, (unsigned long long)iters);
     }
@@ -538,23 +583,24 @@ __device__ __noinline__ void tpi_note_event(const RunArgs a, int64_t inst, int64
             atomicAdd(&a.stats->not_converged, 1ull);
         } else {
             a.status[inst] |= ACMEB200_STATUS_NONFINITE;
+            return -1;  // instance halts (the reference throws, ACME.jl:692)
         }
     }
+    tpi_output_update<C>(m, k.S, u, k.z, y);
+    *Sp = k.S;
+    for (int i = 0; i < NY; i++) y_[i] = y[i];
+    return iters;
 }
 
 template <class C, bool PERINST>
 __global__ void __launch_bounds__(TPI_TPB, ACME_TPI_MINB) k_tpi(const __grid_constant__ TpiMats<C> Msh, const RunArgs a,
-                                                 const SolverCfg sc, const __grid_constant__ DevSub cache) {
+                                                 const __grid_constant__ SolverCfg sc, const __grid_constant__ DevSub cache) {
     constexpr int NX = C::NX, NU = C::NU, NY = C::NY, NN = C::NN, NP = C::NP;
     constexpr int T = TPI_T;
     using SM = TpiSmem<C>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned char* wsm = smem_raw + (size_t)warp * SM::PER_WARP;
-    unsigned char* const in_row0 = wsm + lane * SM::IROW;  // buffer b of this lane: in_row0 + b*IN_BYTES
-    unsigned char* out_row = wsm + 2 * SM::IN_BYTES + lane * SM::OROW;
-    unsigned int* hist_s = reinterpret_cast<unsigned int*>(wsm + SM::HIST_OFF);  // [bin][lane]
-    const uint32_t bar0 = smem_u32(wsm + SM::BAR_OFF), bar1 = bar0 + 8;
 
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // launch-local instance
     const bool active = t < a.ninst;
@@ -595,7 +641,7 @@ __global__ void __launch_bounds__(TPI_TPB, ACME_TPI_MINB) k_tpi(const __grid_con
             double p0[dim1(NP)], z0[dim1(NN)];
             static_for<0, NP>([&](auto i) { p0[decltype(i)::value] = 0.0; });
             static_for<0, NN>([&](auto i) { z0[decltype(i)::value] = a.initz[(int64_t)decltype(i)::value * a.ld + inst]; });
-            tpi_set_origin<C>(m, Cn, S, p0, z0);
+            tpi_set_origin<C>(m, Cn, S, p0, z0, sc);
         }
         store_state();
         a.status[inst] = 0;
@@ -609,97 +655,112 @@ __global__ void __launch_bounds__(TPI_TPB, ACME_TPI_MINB) k_tpi(const __grid_con
     static_for<0, NN * NP>([&](auto i) { S.Mx[decltype(i)::value] = st[(int64_t)(C::S_MX + decltype(i)::value) * a.ld]; });
 
     bool dead = !active || (a.status[inst] & ACMEB200_STATUS_NONFINITE);
-    int64_t n_alive = 0;  // samples processed before the instance died (if it did)
+    int dead_at = dead ? 0 : -1;  // sample index (this call) at which the instance halted, -1 = alive
     const bool shared_u = (a.u_stride == 0) || NU == 0;
     // TMA needs 16-byte aligned row segments: even strides, 16-byte aligned bases
     const bool tma_in = !shared_u && ((reinterpret_cast<uintptr_t>(a.U) & 15) == 0) && ((a.u_stride & 1) == 0) &&
                         ((T * NU) % 2 == 0);
     const bool tma_out = NY > 0 && ((reinterpret_cast<uintptr_t>(a.Y) & 15) == 0) && ((a.y_stride & 1) == 0) &&
                          ((T * NY) % 2 == 0);
-    const double* urow = a.U + (shared_u ? 0 : t * a.u_stride);  // this lane's own stream
-    double* yrow = a.Y + t * a.y_stride;
-    const int64_t n_full = a.N / T;  // full tiles; a trailing partial tile takes the synchronous path
+    const int t32 = (int)t;                 // launch-local instance (ninst < 2^31)
+    const int n_samp = (int)a.N;            // N < 2^27 (checked by the host)
+    const int n_tiles = (n_samp + T - 1) / T, n_full = n_samp / T;
+    auto urow = [&](int n) { return a.U + (shared_u ? 0 : (int64_t)t32 * a.u_stride) + (int64_t)n * NU; };
+    auto yrow = [&](int n) { return a.Y + (int64_t)t32 * a.y_stride + (int64_t)n * NY; };
+    unsigned char* const in_base = wsm + lane * SM::IROW;  // + buf*IN_BYTES
+    unsigned char* const out_row = wsm + 2 * SM::IN_BYTES + lane * SM::OROW;
+    unsigned int* const hist_s = reinterpret_cast<unsigned int*>(wsm + SM::HIST_OFF) + lane;  // [bin*32]
+    const uint32_t bar0 = smem_u32(wsm + SM::BAR_OFF);  // bar1 = bar0 + 8
 
 #pragma unroll
-    for (int b = 0; b < 8; b++) hist_s[b * 32 + lane] = 0u;
+    for (int b = 0; b < 8; b++) hist_s[b * 32] = 0u;
     if (tma_in) {
-        if (lane == 0) { mbar_init(bar0, 32); mbar_init(bar1, 32); }
+        if (lane == 0) { mbar_init(bar0, 32); mbar_init(bar0 + 8, 32); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         __syncwarp();
         // prologue: tiles 0 and 1 in flight
         for (int k = 0; k < 2 && k < n_full; k++) {
-            const uint32_t bar = k ? bar1 : bar0;
             if (active) {
-                mbar_arrive_expect_tx(bar, T * NU * 8);
-                bulk_g2s(smem_u32(in_row0 + k * SM::IN_BYTES), urow + (int64_t)k * T * NU, T * NU * 8, bar);
+                mbar_arrive_expect_tx(bar0 + 8 * k, T * NU * 8);
+                bulk_g2s(smem_u32(in_base + k * SM::IN_BYTES), urow(k * T), T * NU * 8, bar0 + 8 * k);
             } else {
-                mbar_arrive(bar);
+                mbar_arrive(bar0 + 8 * k);
             }
         }
     }
 
-    unsigned long long hpack = 0;
-    for (int64_t n0 = 0, k = 0; n0 < a.N; n0 += T, k++) {
-        const int cnt = (int)((a.N - n0) < T ? (a.N - n0) : T);
+#pragma unroll 1
+    for (int k = 0; k < n_tiles; k++) {
+        const int n0 = k * T;
+        const int cnt = (n_samp - n0) < T ? (n_samp - n0) : T;
         const bool full = cnt == T;
-        const int buf = (int)(k & 1);
-        unsigned char* const in_cur = in_row0 + buf * SM::IN_BYTES;
-        const double* urow_s = reinterpret_cast<const double*>(in_cur);
+        const int buf = k & 1;
+        double* const in_cur = reinterpret_cast<double*>(in_base + buf * SM::IN_BYTES);
         if (!shared_u) {
             if (tma_in && full) {
-                mbar_wait(buf ? bar1 : bar0, (uint32_t)((k >> 1) & 1));
+                mbar_wait(bar0 + 8 * buf, (uint32_t)((k >> 1) & 1));
             } else {
                 // synchronous fallback (unaligned streams, trailing partial tile): own-row loads
                 __syncwarp();
                 if (active)
-                    for (int c = 0; c < cnt * NU; c++) reinterpret_cast<double*>(in_cur)[c] = __ldcs(urow + n0 * NU + c);
+                    for (int c = 0; c < cnt * NU; c++) in_cur[c] = __ldcs(urow(n0) + c);
             }
         }
         if (tma_out) bulk_wait_read0();  // the previous tile's bulk store has drained this lane's row
-        double* yrow_s = reinterpret_cast<double*>(out_row);
-        for (int tt = 0; tt < cnt; tt++) {
-            double u[dim1(NU)], y[dim1(NY)];
-            static_for<0, NU>([&](auto kk) {
-                constexpr int q = decltype(kk)::value;
-                u[q] = shared_u ? __ldg(a.U + (n0 + tt) * NU + q) : urow_s[tt * NU + q];
-            });
-            if (!dead) {
-                bool conv, homotopy, finite;
-                const int iters = tpi_step<C>(m, Cn, S, u, y, sc, cache, a, inst, conv, homotopy, finite);
+        double* const yrow_s = reinterpret_cast<double*>(out_row);
+        int code = 0;
+        int tt = 0;
+        while (tt < cnt && !dead) {
+            // hot loop: no calls, no cold-path state
+#pragma unroll 1
+            for (; tt < cnt; tt++) {
+                double u[dim1(NU)], y[dim1(NY)];
+                static_for<0, NU>([&](auto kk) {
+                    constexpr int q = decltype(kk)::value;
+                    u[q] = shared_u ? __ldg(a.U + (int64_t)(n0 + tt) * NU + q) : in_cur[tt * NU + q];
+                });
+                code = tpi_step_hot<C>(m, Cn, S, u, y, sc, cache, a.initz + inst, a.ld);
+                if (code < 0) break;
                 if (NN > 0) {
-                    if (iters <= 8) hpack += 1ull << (8 * ((iters < 1 ? 1 : iters) - 1));
-                    if (iters > 8 || !conv || homotopy) {
-                        tpi_note_event<C>(a, inst, n0 + tt, iters, conv, homotopy, finite);
-                        if (!finite) dead = true;
-                    }
+                    if (code <= 8) hist_s[(code - 1) * 32] += 1u;
+                    else atomicAdd(&a.stats->iter_hist[(code > ACMEB200_HIST_BINS ? ACMEB200_HIST_BINS : code) - 1], 1ull),
+                         atomicAdd(&a.stats->newton_iters, (unsigned long long)code);
                 }
-                if (!dead) n_alive++;
+                static_for<0, NY>([&](auto kk) { yrow_s[tt * NY + decltype(kk)::value] = y[decltype(kk)::value]; });
             }
-            if (dead) static_for<0, NY>([&](auto i) { y[decltype(i)::value] = NAN; });
-            static_for<0, NY>([&](auto kk) { yrow_s[tt * NY + decltype(kk)::value] = y[decltype(kk)::value]; });
+            if (tt < cnt) {
+                // this lane's sample tt needs the cold path
+                double u[dim1(NU)], y[dim1(NY)];
+                static_for<0, NU>([&](auto kk) {
+                    constexpr int q = decltype(kk)::value;
+                    u[q] = shared_u ? __ldg(a.U + (int64_t)(n0 + tt) * NU + q) : in_cur[tt * NU + q];
+                });
+                const int it = tpi_step_cold<C>(&m, Cn, &S, u, y, &sc, &cache, &a, inst, n0 + tt, code);
+                if (it < 0) { dead = true; dead_at = n0 + tt; break; }
+                if (it >= 1 && it <= 8) hist_s[(it - 1) * 32] += 1u;
+                static_for<0, NY>([&](auto kk) { yrow_s[tt * NY + decltype(kk)::value] = y[decltype(kk)::value]; });
+                tt++;
+            }
         }
-        // fold the packed per-tile histogram (<= T <= 255 per 8-bit field) into shared memory
-#pragma unroll
-        for (int b = 0; b < 8; b++) hist_s[b * 32 + lane] += (unsigned)((hpack >> (8 * b)) & 0xffu);
-        hpack = 0;
+        for (; tt < cnt; tt++)  // halted instance: the reference throws (ACME.jl:692); mark the rest
+            static_for<0, NY>([&](auto kk) { yrow_s[tt * NY + decltype(kk)::value] = NAN; });
         // ---- output tile
         if (NY > 0 && active) {
             if (tma_out && full) {
                 fence_async_smem();
-                bulk_s2g(yrow + n0 * NY, smem_u32(out_row), T * NY * 8);
+                bulk_s2g(yrow(n0), smem_u32(out_row), T * NY * 8);
                 bulk_commit();
             } else {
-                for (int c = 0; c < cnt * NY; c++) __stcs(yrow + n0 * NY + c, yrow_s[c]);
+                for (int c = 0; c < cnt * NY; c++) __stcs(yrow(n0) + c, yrow_s[c]);
             }
         }
         // ---- refill this input buffer with tile k+2
         if (tma_in && k + 2 < n_full) {
-            const uint32_t bar = buf ? bar1 : bar0;
             if (active) {
-                mbar_arrive_expect_tx(bar, T * NU * 8);
-                bulk_g2s(smem_u32(in_cur), urow + (k + 2) * T * NU, T * NU * 8, bar);
+                mbar_arrive_expect_tx(bar0 + 8 * buf, T * NU * 8);
+                bulk_g2s(smem_u32(in_cur), urow((k + 2) * T), T * NU * 8, bar0 + 8 * buf);
             } else {
-                mbar_arrive(bar);
+                mbar_arrive(bar0 + 8 * buf);
             }
         }
     }
@@ -712,16 +773,15 @@ __global__ void __launch_bounds__(TPI_TPB, ACME_TPI_MINB) k_tpi(const __grid_con
     unsigned long long it_sum = 0;
 #pragma unroll
     for (int b = 0; b < 8; b++) {
-        hsum[b] = __reduce_add_sync(full_mask, hist_s[b * 32 + lane]);
+        hsum[b] = __reduce_add_sync(full_mask, hist_s[b * 32]);
         it_sum += (unsigned long long)hsum[b] * (b + 1);
     }
-    const unsigned na_lo = __reduce_add_sync(full_mask, (unsigned)(n_alive & 0xffffff));
-    const unsigned na_hi = __reduce_add_sync(full_mask, (unsigned)(n_alive >> 24));
+    const unsigned n_alive = active ? (unsigned)(dead_at < 0 ? n_samp : dead_at) : 0u;  // < 2^27
+    const unsigned na = __reduce_add_sync(full_mask, n_alive);
     if (lane == 0) {
-        const unsigned long long ns = (unsigned long long)na_lo + ((unsigned long long)na_hi << 24);
-        if (ns) {
-            atomicAdd(&a.stats->samples, ns);
-            if (NN > 0) atomicAdd(&a.stats->solves, ns);
+        if (na) {
+            atomicAdd(&a.stats->samples, (unsigned long long)na);
+            if (NN > 0) atomicAdd(&a.stats->solves, (unsigned long long)na);
         }
         if (it_sum) atomicAdd(&a.stats->newton_iters, it_sum);
 #pragma unroll
