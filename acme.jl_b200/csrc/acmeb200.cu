@@ -74,7 +74,9 @@ struct acmeb200_model {
     double* d_stage_y[2] = {nullptr, nullptr};
     size_t stage_u_bytes = 0, stage_y_bytes = 0, hstage_bytes = 0;
     cudaStream_t copy_streams[2] = {nullptr, nullptr};
+    cudaStream_t compute_stream = nullptr;
     cudaEvent_t ev[2] = {nullptr, nullptr};
+    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_k[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
 };
 
 // ------------------------------------------------------------------ specialised kernels registry
@@ -179,7 +181,11 @@ extern "C" void acmeb200_model_destroy(acmeb200_model* m) {
         cudaFree(m->d_stage_u[i]); cudaFree(m->d_stage_y[i]);
         if (m->copy_streams[i]) cudaStreamDestroy(m->copy_streams[i]);
         if (m->ev[i]) cudaEventDestroy(m->ev[i]);
+        if (m->ev_in[i]) cudaEventDestroy(m->ev_in[i]);
+        if (m->ev_k[i]) cudaEventDestroy(m->ev_k[i]);
+        if (m->ev_out[i]) cudaEventDestroy(m->ev_out[i]);
     }
+    if (m->compute_stream) cudaStreamDestroy(m->compute_stream);
     delete m;
 }
 
@@ -457,51 +463,72 @@ extern "C" int acmeb200_run(acmeb200_model* m, const double* U, int64_t u_stride
         return ACMEB200_OK;
     }
 
-    // ---- host streams: chunks of instances, double-buffered H2D / kernel / D2H
-    const size_t u_per = (size_t)dm.nu * N * sizeof(double), y_per = (size_t)dm.ny * N * sizeof(double);
-    const size_t target = (size_t)256 << 20;
-    int64_t chunk = (int64_t)std::max<size_t>(1, target / std::max<size_t>(1, std::max(u_per, y_per)));
-    chunk = std::min<int64_t>(chunk, m->B);
-    if (chunk >= 64) chunk -= chunk % 64;
+    // ---- host streams: chunks of TIME (all instances per chunk keep the whole GPU busy and the
+    // per-instance state simply persists from chunk to chunk), three-stage pipeline
+    // H2D(c+1) | kernel(c) | D2H(c-1) on separate streams with double-buffered staging
+    const size_t row_u = (size_t)dm.nu * sizeof(double), row_y = (size_t)dm.ny * sizeof(double);
     const bool shared_u = (u_stride == 0) || dm.nu == 0;
-    int rc = ensure_staging(m, udev ? 8 : (shared_u ? std::max<size_t>(u_per, 8) : u_per * chunk), ydev ? 8 : y_per * chunk);
+    const size_t per_sample = std::max<size_t>(8, (size_t)m->B * std::max(shared_u ? 0 : row_u, row_y));
+    int64_t Tc = (int64_t)(((size_t)256 << 20) / per_sample);
+    Tc -= Tc % 16;
+    Tc = std::max<int64_t>(16, std::min<int64_t>(Tc, N));
+    const size_t ubytes = udev ? 8 : (shared_u ? std::max<size_t>(8, row_u * Tc) : row_u * Tc * m->B);
+    const size_t ybytes = ydev ? 8 : std::max<size_t>(8, row_y * Tc * m->B);
+    int rc = ensure_staging(m, ubytes, ybytes);
     if (rc) return rc;
-    // pageable host memory is staged through the driver; pinned memory is DMA'd directly
-    (void)is_pinned_or_managed;
+    if (!m->compute_stream) CUDA_TRY(cudaStreamCreateWithFlags(&m->compute_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) {
+        if (!m->ev_in[i]) CUDA_TRY(cudaEventCreateWithFlags(&m->ev_in[i], cudaEventDisableTiming));
+        if (!m->ev_k[i]) CUDA_TRY(cudaEventCreateWithFlags(&m->ev_k[i], cudaEventDisableTiming));
+        if (!m->ev_out[i]) CUDA_TRY(cudaEventCreateWithFlags(&m->ev_out[i], cudaEventDisableTiming));
+    }
     CUDA_TRY(cudaStreamSynchronize(stream));
-    if (!udev && shared_u && dm.nu > 0)
-        CUDA_TRY(cudaMemcpyAsync(m->d_stage_u[0], U, u_per, cudaMemcpyHostToDevice, m->copy_streams[0]));
-    if (!udev && shared_u && dm.nu > 0) {
-        CUDA_TRY(cudaStreamSynchronize(m->copy_streams[0]));
-    }
-    int buf = 0;
-    for (int64_t b0 = 0; b0 < m->B; b0 += chunk, buf ^= 1) {
-        const int64_t nb = std::min(chunk, m->B - b0);
-        cudaStream_t cs = m->copy_streams[buf];
+    cudaStream_t s_in = m->copy_streams[0], s_out = m->copy_streams[1], s_k = m->compute_stream;
+    int64_t c = 0;
+    for (int64_t n0 = 0; n0 < N; n0 += Tc, c++) {
+        const int buf = (int)(c & 1);
+        const int64_t nt = std::min<int64_t>(Tc, N - n0);
         RunArgs a = base_args(m);
-        a.N = N; a.inst0 = b0; a.ninst = nb;
-        if (udev) { a.U = U + (u_stride ? b0 * u_stride : 0); a.u_stride = u_stride; }
-        else if (shared_u) { a.U = m->d_stage_u[0]; a.u_stride = 0; }
-        else {
-            if (u_stride == (int64_t)dm.nu * N)
-                CUDA_TRY(cudaMemcpyAsync(m->d_stage_u[buf], U + b0 * u_stride, u_per * nb, cudaMemcpyHostToDevice, cs));
+        a.N = nt; a.inst0 = 0; a.ninst = m->B;
+        a.n_done = m->n_done + n0;
+        // ---- H2D of chunk c into staging buffer `buf` (free once kernel c-2 has consumed it)
+        if (!udev && dm.nu > 0) {
+            if (c >= 2) CUDA_TRY(cudaStreamWaitEvent(s_in, m->ev_k[buf], 0));
+            if (shared_u)
+                CUDA_TRY(cudaMemcpyAsync(m->d_stage_u[buf], U + n0 * dm.nu, row_u * nt, cudaMemcpyHostToDevice, s_in));
             else
-                CUDA_TRY(cudaMemcpy2DAsync(m->d_stage_u[buf], u_per, U + b0 * u_stride, u_stride * sizeof(double), u_per, nb, cudaMemcpyHostToDevice, cs));
-            a.U = m->d_stage_u[buf]; a.u_stride = (int64_t)dm.nu * N;
+                CUDA_TRY(cudaMemcpy2DAsync(m->d_stage_u[buf], row_u * nt, U + n0 * dm.nu, (size_t)u_stride * sizeof(double),
+                                           row_u * nt, (size_t)m->B, cudaMemcpyHostToDevice, s_in));
+            CUDA_TRY(cudaEventRecord(m->ev_in[buf], s_in));
+            CUDA_TRY(cudaStreamWaitEvent(s_k, m->ev_in[buf], 0));
+            a.U = m->d_stage_u[buf];
+            a.u_stride = shared_u ? 0 : dm.nu * nt;
+        } else {
+            a.U = U ? U + n0 * dm.nu : nullptr;
+            a.u_stride = u_stride;
         }
-        if (ydev) { a.Y = Y + b0 * y_stride; a.y_stride = y_stride; }
-        else { a.Y = m->d_stage_y[buf]; a.y_stride = (int64_t)dm.ny * N; }
-        CUDA_TRY(launch(m, a, cs));
-        if (!ydev) {
-            if (y_stride == (int64_t)dm.ny * N)
-                CUDA_TRY(cudaMemcpyAsync(Y + b0 * y_stride, m->d_stage_y[buf], y_per * nb, cudaMemcpyDeviceToHost, cs));
-            else
-                CUDA_TRY(cudaMemcpy2DAsync(Y + b0 * y_stride, y_stride * sizeof(double), m->d_stage_y[buf], y_per, y_per, nb, cudaMemcpyDeviceToHost, cs));
+        // ---- kernel c (needs the output staging buffer `buf` drained by D2H c-2)
+        if (!ydev && dm.ny > 0) {
+            if (c >= 2) CUDA_TRY(cudaStreamWaitEvent(s_k, m->ev_out[buf], 0));
+            a.Y = m->d_stage_y[buf];
+            a.y_stride = dm.ny * nt;
+        } else {
+            a.Y = Y ? Y + n0 * dm.ny : nullptr;
+            a.y_stride = y_stride;
         }
-        // the buffer pair `buf` is reused two chunks later: stream order on cs protects it
+        CUDA_TRY(launch(m, a, s_k));
+        CUDA_TRY(cudaEventRecord(m->ev_k[buf], s_k));
+        // ---- D2H of chunk c
+        if (!ydev && dm.ny > 0) {
+            CUDA_TRY(cudaStreamWaitEvent(s_out, m->ev_k[buf], 0));
+            CUDA_TRY(cudaMemcpy2DAsync(Y + n0 * dm.ny, (size_t)y_stride * sizeof(double), m->d_stage_y[buf], row_y * nt,
+                                       row_y * nt, (size_t)m->B, cudaMemcpyDeviceToHost, s_out));
+            CUDA_TRY(cudaEventRecord(m->ev_out[buf], s_out));
+        }
     }
-    CUDA_TRY(cudaStreamSynchronize(m->copy_streams[0]));
-    CUDA_TRY(cudaStreamSynchronize(m->copy_streams[1]));
+    CUDA_TRY(cudaStreamSynchronize(s_in));
+    CUDA_TRY(cudaStreamSynchronize(s_k));
+    CUDA_TRY(cudaStreamSynchronize(s_out));
     m->n_done += N;
     return ACMEB200_OK;
 }

@@ -198,7 +198,7 @@ __device__ __forceinline__ double tpi_evaluate(const M& m, const double (&Cn)[di
             constexpr int r = decltype(rr)::value;
             const double ar = fabs(res[ROW + r]);
             rsum += ar;
-            resmax = fmax(resmax, ar);
+            resmax = ar > resmax ? ar : resmax;
             static_for<0, C::NN>([&](auto cc) {
                 constexpr int c = decltype(cc)::value;
                 J[c * C::NN + ROW + r] =
@@ -291,8 +291,10 @@ __device__ __forceinline__ bool tpi_simple_solve(const M& m, const double (&Cn)[
             start_from_origin();
             continue;
         }
-        if (!Jfin) return resmax < sc.tol;
-        if (!lu_reg<C::NN>(J, piv)) return resmax < sc.tol;
+        // one exit test after the factorisation: non-finite residual/Jacobian (solvers.jl:220) or an
+        // exactly singular Jacobian (solvers.jl:223) end the solve; hasconverged() is resmax < tol
+        const bool lu_ok = lu_reg<C::NN>(J, piv);
+        if (!(Jfin && lu_ok)) return resmax < sc.tol;
         if (resmax < sc.tol) { converged = true; break; }
         lu_solve_reg<C::NN>(J, piv, res);
         static_for<0, C::NN>([&](auto i) { z[decltype(i)::value] -= res[decltype(i)::value]; });

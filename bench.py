@@ -98,13 +98,25 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def host_cores() -> int:
+    """usable host cores: CPU affinity, capped by the cgroup CPU quota if there is one"""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            n = max(1, min(n, int(np.ceil(int(quota) / int(period)))))
+    except Exception:
+        pass
+    return n
+
+
 def cpu_baseline(budget_s: float = 12.0, threads: int = 0) -> dict:
     """The oracle (CPU restatement of the reference's run! path) on all host cores, on a
     bounded sample of the same workload: the first `b` instances of the sweep, full 1 s signal."""
     from acme_jl_b200 import examples as ex
     from oracle import oracle
     from oracle.oracle import OracleModel
-    cores = threads or oracle.lib().oracle_num_threads()
+    cores = threads or host_cores()
     m = ex.diodeclipper()
     u = sine_row().reshape(1, -1)
     b = 4 * cores
@@ -204,10 +216,16 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     from acme_jl_b200 import BatchRunner, examples as ex
+    from acme_jl_b200.distributed import ShardedBatchRunner
     Bper = args.batch
     model = ex.diodeclipper()
-    P = sweep_params(Bper * world, rank * Bper, Bper)
-    runner = BatchRunner(model, Bper, params=[P], solver=SOLVER, kernel=args.kernel)
+    # one descriptor for the global batch; every rank uploads only its contiguous shard
+    Pglobal = sweep_params(Bper * world, 0, Bper * world)
+    sharded = ShardedBatchRunner(model, Bper * world, rank=rank, world=world, params=[Pglobal], solver=SOLVER,
+                                 kernel=args.kernel)
+    assert sharded.count == Bper and sharded.first == rank * Bper
+    runner = sharded.runner
+    P = Pglobal[:, rank * Bper:(rank + 1) * Bper]
 
     row = torch.from_numpy(sine_row()).to(dev)
     U = row.reshape(1, N_SAMPLES, 1).expand(Bper, N_SAMPLES, 1).contiguous()  # (B, N, nu): per-instance streams in HBM
