@@ -1,0 +1,145 @@
+# ACMEB200.jl -- the binding a maintainer of HSU-ANT/ACME.jl would add to drive the
+# B200 library (include/acmeb200.h) from the reference's own API.
+#
+# NOT RUNNABLE IN THIS REPOSITORY'S IMAGE (no Julia toolchain); it documents the intended
+# integration.  It keeps `@circuit` / `DiscreteModel` / `run!` untouched: the model is derived by
+# ACME exactly as before, then `BatchRunner(model; batch, params)` uploads the derived matrices and
+# `run!(runner, Y, U)` replaces the per-sample loop of src/ACME.jl:650-715.
+module ACMEB200
+
+using ACME
+using ACME: DiscreteModel, nx, nu, ny, nn, np, nq
+
+const libacmeb200 = get(ENV, "ACMEB200_LIB", "libacmeb200.so")
+
+# ---- mirrors of the C structs (include/acmeb200.h)
+struct CArray;  ptr::Ptr{Float64}; stride::Int64; end
+struct CElem;   kind::Int32; q_offset::Int32; param_offset::Int32; nparam::Int32; end
+struct CCache
+    n_points::Int32; n_columns::Int32
+    cut_dim::Ptr{Int32}; cut_val::Ptr{Float64}; ps_idx::Ptr{Int32}; ps::Ptr{Float64}; zs::Ptr{Float64}
+end
+struct CSubDesc
+    nn::Int32; nq::Int32; np::Int32; nelem::Int32
+    dq::CArray; eq::CArray; fqprev::CArray; pexp::CArray; q0::CArray; fq::CArray; init_z::CArray
+    elems::Ptr{CElem}; params::CArray; nparams::Int32; reserved::Int32; cache::CCache
+end
+struct CModelDesc
+    abi_version::Int32; nx::Int32; nu::Int32; ny::Int32; nsub::Int32; solver::Int32; maxiter::Int32
+    reserved::Int32; tol::Float64
+    a::CArray; b::CArray; c::CArray; x0::CArray; dy::CArray; ey::CArray; fy::CArray; y0::CArray
+    subs::Ptr{CSubDesc}
+end
+
+const ELEM_DIODE, ELEM_BJT, ELEM_POT, ELEM_MOSFET, ELEM_OPAMP_TANH, ELEM_JA = Int32.(1:6)
+
+check(rc) = rc == 0 || error(unsafe_string(ccall((:acmeb200_last_error, libacmeb200), Cstring, ())))
+
+"""
+Element table of one sub-problem: walks the closures ACME built
+(`model.nonlinear_eq_funcs[i]` captures `circ_nl_func::CircuitNLFunc`, src/ACME.jl:177;
+each entry of `.fs` captures `q_indices` and `nleqfunc`, src/circuit.jl:76-80) and classifies
+every element closure by its captured variables (src/elements.jl: diode `(is, η)` :236-244,
+bjt `βf…` :309-401, potentiometer `(r,)` :20-30, mosfet `vt, polarity` :448-479,
+tanh op-amp `(gain, scale)` :537-546, Jiles-Atherton `Ms…` :104-129).
+"""
+function element_table(nleq)
+    cnl = getfield(nleq, :circ_nl_func)
+    elems = CElem[]; params = Float64[]
+    for f in cnl.fs
+        qidx = getfield(f, :q_indices); law = getfield(f, :nleqfunc)
+        names = fieldnames(typeof(law))
+        kind, p = if names == (:is, :η)
+            ELEM_DIODE, Float64[law.is, law.η]
+        elseif :βf in names
+            ELEM_BJT, Float64[law.ise, law.isc, law.ηe, law.ηc, law.βf, law.βr, law.ile, law.ilc,
+                              law.ηel, law.ηcl, law.vaf, law.var, law.ikf, law.ikr]
+        elseif names == (:r,)
+            ELEM_POT, Float64[law.r]
+        elseif :polarity in names && :vt in names
+            vt = collect(Float64, law.vt); α = collect(Float64, law.α)
+            ELEM_MOSFET, Float64[law.polarity, law.λ, length(vt), length(α),
+                                 vcat(vt, zeros(4 - length(vt)))..., vcat(α, zeros(4 - length(α)))...]
+        elseif names == (:gain, :scale)
+            ELEM_OPAMP_TANH, Float64[law.gain, law.scale]
+        elseif :Ms in names
+            ELEM_JA, Float64[law.Ms, law.a, law.α, law.c, law.k]
+        else
+            error("unsupported non-linear element closure $(typeof(law))")
+        end
+        push!(elems, CElem(kind, first(qidx) - 1, length(params), length(p)))
+        append!(params, p)
+    end
+    return elems, params
+end
+
+mutable struct BatchRunner
+    model::DiscreteModel
+    batch::Int
+    handle::Ptr{Cvoid}
+end
+
+shared(a::Array{Float64}) = CArray(pointer(a), 0)
+perinst(a::Array{Float64}, len) = CArray(pointer(a), len)
+
+"""
+    BatchRunner(model; batch=1, params=nothing)
+
+`params[i]` is an `nparams × batch` matrix of element parameters for sub-problem `i`
+(parameter sweeps); `nothing` shares the model's own parameters.
+"""
+function BatchRunner(model::DiscreteModel; batch::Integer=1, params=nothing, solver::Integer=2)
+    nsub = length(model.solvers)
+    keep = Any[]                      # everything the descriptor points into
+    subs = Vector{CSubDesc}(undef, nsub)
+    for i in 1:nsub
+        elems, p = element_table(model.nonlinear_eq_funcs[i])
+        pm = params === nothing || params[i] === nothing ? p : Matrix{Float64}(params[i])
+        base = model.solvers[i]      # HomotopySolver{CachingSolver{SimpleSolver}} (src/solvers.jl:247, 319)
+        while hasproperty(base, :basesolver); base = base.basesolver; end
+        init_z = copy(base.last_z)   # origin of the SimpleSolver (src/solvers.jl:155)
+        push!(keep, elems, pm, init_z)
+        subs[i] = CSubDesc(nn(model, i), nq(model, i), np(model, i), length(elems),
+            shared(model.dqs[i]), shared(model.eqs[i]), shared(model.fqprevs[i]), shared(model.pexps[i]),
+            shared(model.q0s[i]), shared(model.fqs[i]), shared(init_z), pointer(elems),
+            pm isa Matrix ? perinst(pm, size(pm, 1)) : shared(pm), length(p), 0,
+            CCache(0, 0, C_NULL, C_NULL, C_NULL, C_NULL, C_NULL))
+    end
+    desc = Ref(CModelDesc(1, nx(model), nu(model), ny(model), nsub, solver, 0, 0, 0.0,
+        shared(model.a), shared(model.b), shared(model.c), shared(model.x0),
+        shared(model.dy), shared(model.ey), shared(model.fy), shared(model.y0), pointer(subs)))
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    GC.@preserve keep subs model begin
+        check(ccall((:acmeb200_model_create, libacmeb200), Cint,
+                    (Ref{CModelDesc}, Int64, Int64, Ref{Ptr{Cvoid}}), desc, 0, batch, h))
+    end
+    r = BatchRunner(model, batch, h[])
+    finalizer(r -> ccall((:acmeb200_model_destroy, libacmeb200), Cvoid, (Ptr{Cvoid},), r.handle), r)
+    return r
+end
+
+"""
+    run!(runner::BatchRunner, Y::Array{Float64,3}, U::Array{Float64,3})
+
+`size(U) == (nu, N, B)`, `size(Y) == (ny, N, B)`: instance `b` sees exactly the `nu × N` matrix the
+reference's `run!` takes (src/ACME.jl:658-664).  Raises the reference's own messages.
+"""
+function ACME.run!(r::BatchRunner, Y::Array{Float64,3}, U::Array{Float64,3})
+    m = r.model
+    size(U, 1) == nu(m) || throw(DimensionMismatch("input matrix has $(size(U,1)) rows, but model has $(nu(m)) inputs"))
+    size(Y, 1) == ny(m) || throw(DimensionMismatch("output matrix has $(size(Y,1)) rows, but model has $(ny(m)) outputs"))
+    size(U, 2) == size(Y, 2) || throw(DimensionMismatch("input matrix has $(size(U,2)) columns, output matrix has $(size(Y,2)) columns"))
+    N = size(U, 2)
+    GC.@preserve U Y check(ccall((:acmeb200_run, libacmeb200), Cint,
+        (Ptr{Cvoid}, Ptr{Float64}, Int64, Ptr{Float64}, Int64, Int64, UInt32, Ptr{Cvoid}),
+        r.handle, U, nu(m) * N, Y, ny(m) * N, N, 0, C_NULL))
+    status = Vector{UInt32}(undef, r.batch)
+    check(ccall((:acmeb200_get_status, libacmeb200), Cint, (Ptr{Cvoid}, Ptr{UInt32}, Ptr{Int64}), r.handle, status, C_NULL))
+    any(s -> s & 0x2 != 0, status) && error("Failed to converge while solving non-linear equation, got non-finite result.")
+    any(s -> s & 0x1 != 0, status) && @warn "Failed to converge while solving non-linear equation."
+    return Y
+end
+
+ACME.run!(r::BatchRunner, U::Array{Float64,3}) = ACME.run!(r, Array{Float64,3}(undef, ny(r.model), size(U, 2), r.batch), U)
+
+end # module
