@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.environ.get("ACMEB200_LIB") or os.path.join(HERE, "libacmeb200.so")
 SOURCES = ["acmeb200.cu"]
-DEPS = ["acmeb200.cu", "devmodel.h", "elements.cuh", "kernel_generic.cuh", "kernel_tpi.cuh",
+DEPS = ["acmeb200.cu", "devmodel.h", "elements.cuh", "kernel_generic.cuh", "kernel_tpi.cuh", "kernel_coop.cuh",
         os.path.join("..", "..", "include", "acmeb200.h")]
 
 NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",

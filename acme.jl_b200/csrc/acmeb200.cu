@@ -18,6 +18,7 @@
 #include "elements.cuh"
 #include "kernel_generic.cuh"
 #include "kernel_tpi.cuh"
+#include "kernel_coop.cuh"
 
 using namespace acme;
 
@@ -64,6 +65,9 @@ struct acmeb200_model {
     // host copies needed to (re)build kernel parameters
     std::vector<double> h_blob;  // blob of instance 0 (or the shared blob)
     const TpiEntry* tpi = nullptr;
+    int coop_lanes = 0;  // 0: not the cooperative kernel
+    bool has_cache = false;
+    int max_nn = 0, max_nelem = 0;
     int kernel_mode = 0;
     std::string kernel_name;
     int64_t launches = 0;
@@ -248,6 +252,8 @@ extern "C" int acmeb200_model_create(const acmeb200_model_desc* d, int64_t first
             if (el.q_offset < 0 || el.q_offset + elem_nq(el.kind) > sd.nq) { delete m; return fail(ACMEB200_EINVAL, "element %d of sub %d: q range outside the sub", e, i); }
             DevElem& de = dm.elems[elem_total + e];
             de.kind = el.kind; de.q_off = el.q_offset; de.c_off = const_total; de.row = row; de.j_off = joff;
+            for (int r = 0; r < elem_nn(el.kind); r++)
+                if (row + r < MAX_ROWS) dm.row_elem[i][row + r] = (unsigned char)e;
             // derived constants for every instance
             const int nc = elem_nc(el.kind);
             for (int k = 0; k < nc; k++) h_consts.emplace_back((size_t)count);
@@ -273,6 +279,8 @@ extern "C" int acmeb200_model_create(const acmeb200_model_desc* d, int64_t first
         if (sd.init_z.stride || sd.params.stride) { /* per-instance state only; matrices may still be shared */ }
     }
     dm.nelem_total = elem_total;
+    m->max_nn = max_nn;
+    for (int i = 0; i < d->nsub; i++) m->max_nelem = std::max(m->max_nelem, d->subs[i].nelem);
     dm.nconst = const_total;
     dm.ninitz = initz_total;
     dm.blob_len = off;
@@ -297,7 +305,7 @@ extern "C" int acmeb200_model_create(const acmeb200_model_desc* d, int64_t first
     // ---- pack + upload
     auto destroy_fail = [&](int code) { acmeb200_model_destroy(m); return code; };
     const int64_t nblob = per_instance ? count : 1;
-    std::vector<double> blob((size_t)std::max<int64_t>(1, (int64_t)off * nblob));
+    std::vector<double> blob((size_t)std::max<int64_t>(2, (int64_t)off * nblob + 2));  // +pad: TMA copies an even count
     for (int64_t b = 0; b < nblob; b++)
         for (const Piece& p : pieces) {
             if (p.len == 0) continue;
@@ -350,6 +358,7 @@ extern "C" int acmeb200_model_create(const acmeb200_model_desc* d, int64_t first
         CT(up(c.zs, sizeof(double) * (size_t)s.nn * c.n_columns, (const void**)&s.zs));
         s.cache_n = c.n_points;
         s.cache_cols = c.n_columns;
+        m->has_cache = true;
     }
     CT(cudaMalloc(&m->d_status, sizeof(uint32_t) * (size_t)count));
     CT(cudaMalloc(&m->d_first_fail, sizeof(long long) * (size_t)count));
@@ -363,10 +372,33 @@ extern "C" int acmeb200_model_create(const acmeb200_model_desc* d, int64_t first
 }
 
 // picks the kernel, (re)allocates its state and initialises it
+static int coop_lanes_for(const acmeb200_model* m) {
+    if (m->blob_stride != 0 || m->has_cache || m->dm.nsub == 0 || m->max_nn > MAX_ROWS) return 0;
+    const int need = std::max(m->max_nn, m->max_nelem);
+    int lanes = need <= 8 ? 8 : (need <= 16 ? 16 : 32);
+    size_t smem = lanes == 8 ? coop_smem_bytes<8>(m->dm) : lanes == 16 ? coop_smem_bytes<16>(m->dm) : coop_smem_bytes<32>(m->dm);
+    while (smem > 200 * 1024 && lanes < 32) {  // fewer groups per CTA
+        lanes *= 2;
+        smem = lanes == 16 ? coop_smem_bytes<16>(m->dm) : coop_smem_bytes<32>(m->dm);
+    }
+    return smem <= 200 * 1024 ? lanes : 0;
+}
+
 static int select_kernel(acmeb200_model* m) {
-    m->tpi = m->kernel_mode == 1 ? nullptr : find_tpi(m->dm);
+    m->tpi = nullptr;
+    m->coop_lanes = 0;
+    if (m->kernel_mode == 0) m->tpi = find_tpi(m->dm);
+    if (!m->tpi && m->kernel_mode != 1) {
+        const int lanes = coop_lanes_for(m);
+        // automatic choice: large non-linear systems profit from lanes sharing one instance
+        if (lanes && (m->kernel_mode == 2 || m->max_nn >= 4)) m->coop_lanes = lanes;
+        if (m->kernel_mode == 2 && !m->coop_lanes)
+            return fail(ACMEB200_EUNSUPPORTED, "the cooperative kernel needs shared matrices, no frozen cache and nn <= %d", MAX_ROWS);
+    }
     m->ws_rows = m->tpi ? m->tpi->state_rows : m->dm.w_rows;
-    m->kernel_name = m->tpi ? m->tpi->name : "generic<thread-per-instance, runtime dims>";
+    if (m->tpi) m->kernel_name = m->tpi->name;
+    else if (m->coop_lanes) m->kernel_name = "coop<" + std::to_string(m->coop_lanes) + " lanes per instance, runtime dims, state in shared memory>";
+    else m->kernel_name = "generic<thread-per-instance, runtime dims>";
     cudaFree(m->d_ws);
     m->d_ws = nullptr;
     CUDA_TRY(cudaMalloc(&m->d_ws, sizeof(double) * (size_t)std::max<int64_t>(1, m->ws_rows * m->B)));
@@ -383,9 +415,28 @@ static RunArgs base_args(acmeb200_model* m) {
     return a;
 }
 
+template <int L>
+static cudaError_t launch_coop(const acmeb200_model* m, const RunArgs& a, cudaStream_t stream) {
+    const size_t smem = coop_smem_bytes<L>(m->dm);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(k_coop<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    constexpr int GPC = COOP_TPB / L;
+    k_coop<L><<<(unsigned)((a.ninst + GPC - 1) / GPC), COOP_TPB, smem, stream>>>(m->dm, a);
+    return cudaGetLastError();
+}
+
 static cudaError_t launch(acmeb200_model* m, const RunArgs& a, cudaStream_t stream) {
     m->launches++;
     if (m->tpi) return m->tpi->launch(m, a, stream);
+    if (m->coop_lanes && !a.init) {  // the generic kernel initialises the (shared) state layout
+        if (m->coop_lanes == 8) return launch_coop<8>(m, a, stream);
+        if (m->coop_lanes == 16) return launch_coop<16>(m, a, stream);
+        return launch_coop<32>(m, a, stream);
+    }
     const int tpb = 128;
     k_generic<<<(unsigned)((a.ninst + tpb - 1) / tpb), tpb, 0, stream>>>(m->dm, a);
     return cudaGetLastError();
@@ -409,7 +460,7 @@ extern "C" int acmeb200_reset(acmeb200_model* m) {
 
 extern "C" int acmeb200_set_kernel(acmeb200_model* m, int32_t mode) {
     if (!m) return fail(ACMEB200_EINVAL, "null model");
-    if (mode != 0 && mode != 1) return fail(ACMEB200_EINVAL, "kernel mode must be 0 (auto) or 1 (generic)");
+    if (mode < 0 || mode > 2) return fail(ACMEB200_EINVAL, "kernel mode must be 0 (auto), 1 (generic) or 2 (cooperative)");
     CUDA_TRY(cudaSetDevice(m->device));
     m->kernel_mode = mode;
     return select_kernel(m);
@@ -534,7 +585,7 @@ extern "C" int acmeb200_run(acmeb200_model* m, const double* U, int64_t u_stride
 }
 
 // ------------------------------------------------------------------ state / statistics
-static int state_row_of_x(const acmeb200_model* m) { return m->tpi ? 0 : m->dm.w_x; }
+static int state_row_of_x(const acmeb200_model* m) { return m->tpi ? 0 : m->dm.w_x; }  // generic and coop share the layout
 
 extern "C" int acmeb200_get_state(acmeb200_model* m, double* x_host) {
     if (!m || !x_host) return fail(ACMEB200_EINVAL, "null argument");

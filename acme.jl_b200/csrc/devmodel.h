@@ -7,6 +7,7 @@ namespace acme {
 
 constexpr int MAX_SUBS = 8;
 constexpr int MAX_ELEMS = 48;
+constexpr int MAX_ROWS = 32;  // nn per sub-problem supported by the cooperative kernel
 
 struct DevElem {
     int kind;
@@ -39,6 +40,7 @@ struct DevModel {
     int w_x, w_u, w_zall, w_xnew, w_p, w_pfull, w_q, w_res, w_jv, w_z, w_tmp, w_startp, w_pa, w_cp, w_rows;
     DevSub subs[MAX_SUBS];
     DevElem elems[MAX_ELEMS];
+    unsigned char row_elem[MAX_SUBS][MAX_ROWS];  // residual row -> element index within the sub
 };
 
 // device statistics block (mirrors acmeb200_stats, all 64-bit counters)

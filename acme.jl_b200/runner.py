@@ -56,8 +56,10 @@ class BatchRunner:
         self._h = h
         if kernel == "generic":
             check(lib().acmeb200_set_kernel(self._h, 1))
+        elif kernel == "coop":
+            check(lib().acmeb200_set_kernel(self._h, 2))
         elif kernel != "auto":
-            raise ValueError("kernel must be 'auto' or 'generic'")
+            raise ValueError("kernel must be 'auto', 'generic' or 'coop'")
 
     def close(self):
         if getattr(self, "_h", None):

@@ -185,8 +185,8 @@ int acmeb200_reset(acmeb200_model *m);
 int acmeb200_get_status(acmeb200_model *m, uint32_t *status_host, int64_t *first_fail_host);
 int acmeb200_get_stats(acmeb200_model *m, acmeb200_stats *out);
 
-/* kernel selection: 0 = automatic, 1 = force the generic (runtime-dimension)
- * kernel; returns the name of the kernel the next run will launch */
+/* kernel selection: 0 = automatic, 1 = force the generic thread-per-instance
+ * kernel, 2 = force the cooperative (lanes-per-instance) kernel; solver state is reset */
 int acmeb200_set_kernel(acmeb200_model *m, int32_t mode);
 const char *acmeb200_kernel_name(const acmeb200_model *m);
 /* number of kernels launched by this model since creation */

@@ -20,7 +20,7 @@ import cases
 
 pytestmark = pytest.mark.gpu
 
-KERNELS = ["auto", "generic"]
+KERNELS = ["auto", "generic", "coop"]
 H = "HomotopySolver{SimpleSolver}"
 HC = "HomotopySolver{CachingSolver{SimpleSolver}}"
 
@@ -55,7 +55,14 @@ def assert_parity_within_reference_accuracy(y, yref, yexact, yref2=None, rtol=1e
         f"GPU error vs converged {np.max(np.abs(y - yexact)):.3e}, E_ref {e_ref:.3e}"
 
 
+def coop_ok(model, **kw):
+    """the cooperative kernel needs a non-linear sub-problem, shared matrices and no frozen cache"""
+    return len(model.subs) > 0 and not kw.get("overrides") and not kw.get("caches")
+
+
 def gpu_run(model, u, kernel="auto", **kw):
+    if kernel == "coop" and not coop_ok(model, **kw):
+        pytest.skip("cooperative kernel not applicable")
     r = BatchRunner(model, 1, kernel=kernel, **kw)
     try:
         return r.run(np.asarray(u, dtype=float))[:, :, 0]
@@ -109,6 +116,8 @@ EXAMPLES = {
 def test_examples_match_oracle(name, kernel):
     mk, mu = EXAMPLES[name]
     m = mk()
+    if kernel == "coop" and not coop_ok(m):
+        pytest.skip("cooperative kernel not applicable")
     n = 4410 if "superover" not in name else 1000
     u = mu(n)
     yref = cpu_run(m, u, solver=H)
@@ -293,7 +302,7 @@ def sallenkey_sweep(B):
     return {k: np.stack(v, axis=-1) for k, v in mats.items()}
 
 
-@pytest.mark.parametrize("kernel", KERNELS)
+@pytest.mark.parametrize("kernel", ["auto", "generic"])
 def test_config3_sallenkey_per_instance_matrices(kernel):
     B, N = 64, 9600
     base = ex.sallenkey(fs=96000)
@@ -305,7 +314,8 @@ def test_config3_sallenkey_per_instance_matrices(kernel):
     r.close()
 
 
-def test_config4_superover_pots_as_inputs():
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_config4_superover_pots_as_inputs(kernel):
     B, N = 16, 1000
     m = ex.superover()
     u = np.zeros((4, N, B), order="F")
@@ -314,7 +324,9 @@ def test_config4_superover_pots_as_inputs():
     u[2] = (np.arange(B) // 4 + 0.5)[None, :] / 4
     u[3] = 1.0
     yref = OracleModel(m, B, solver=H).run(u, threads=0)
-    r = BatchRunner(m, B, solver=H)
+    r = BatchRunner(m, B, solver=H, kernel=kernel)
+    if kernel == "auto":
+        assert r.kernel_name.startswith("coop<16")
     assert_parity(r.run(u), yref)
     r.close()
 
@@ -396,7 +408,7 @@ def test_frozen_cache_lookup():
     yexact = cpu_run(m, u2, solver=H, tol=1e-13)
     yref = cpu_run(m, u2, solver=H)
     yref2 = cpu_run(m, u2, solver=HC)
-    for kernel in KERNELS:
+    for kernel in ("auto", "generic"):
         # different start points, same solution: strict parity once both sides converge fully
         r = BatchRunner(m, 1, kernel=kernel, solver=HC, caches=[cache], tol=1e-13)
         assert_parity(r.run(u2)[:, :, 0], yexact)
