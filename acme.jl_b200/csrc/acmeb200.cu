@@ -62,10 +62,12 @@ struct acmeb200_model {
     long long* d_first_fail = nullptr;
     DevStats* d_stats = nullptr;
     std::vector<void*> d_cache;  // device copies of the frozen caches
+    std::vector<void*> d_dyn;    // dynamic per-instance caches of the cooperative kernel
     // host copies needed to (re)build kernel parameters
     std::vector<double> h_blob;  // blob of instance 0 (or the shared blob)
     const TpiEntry* tpi = nullptr;
     int coop_lanes = 0;  // 0: not the cooperative kernel
+    bool rows_ok = true;
     bool has_cache = false;
     int max_nn = 0, max_nelem = 0;
     int kernel_mode = 0;
@@ -171,6 +173,35 @@ static void prep_consts(int kind, const double* P, double* C) {
     }
 }
 
+template <class E, int R>
+static void probe_row(RowProg& rp, int q_off, int j_off) {
+    double jv[8];
+    for (int t = 0; t < 8; t++) jv[t] = 1000.0 + 7.5 * t;
+    rp.n = 0;
+    for (int k = 0; k < E::NQ; k++) {
+        const double v = E::template row<R>(jv, [&](int kk) { return kk == k ? 1.0 : 0.0; });
+        if (v == 0.0) continue;
+        int which = -1;
+        for (int t = 0; t < E::NJ; t++) if (v == jv[t]) which = t;
+        rp.q[rp.n] = (unsigned char)(q_off + k);
+        rp.jv[rp.n] = (signed char)(which >= 0 ? j_off + which : -1);
+        rp.c[rp.n] = which >= 0 ? 0.0f : (float)v;
+        rp.n++;
+    }
+}
+template <class E>
+static void probe_elem(RowProg* rows, int q_off, int j_off) {
+    probe_row<E, 0>(rows[0], q_off, j_off);
+    if constexpr (E::NN > 1) probe_row<E, 1>(rows[1], q_off, j_off);
+}
+static void probe_rows(int kind, RowProg* rows, int q_off, int j_off) {
+    switch (kind) {
+#define X(E) case E::KIND: probe_elem<E>(rows, q_off, j_off); break;
+        ACME_FOR_EACH_ELEM(X)
+#undef X
+    }
+}
+
 static int select_kernel(acmeb200_model* m);
 static int run_init(acmeb200_model* m);
 
@@ -180,6 +211,7 @@ extern "C" void acmeb200_model_destroy(acmeb200_model* m) {
     cudaFree(m->d_blob); cudaFree(m->d_consts); cudaFree(m->d_initz); cudaFree(m->d_ws);
     cudaFree(m->d_status); cudaFree(m->d_first_fail); cudaFree(m->d_stats);
     for (void* p : m->d_cache) cudaFree(p);
+    for (void* p : m->d_dyn) cudaFree(p);
     for (int i = 0; i < 2; i++) {
         if (m->h_stage[i]) cudaFreeHost(m->h_stage[i]);
         cudaFree(m->d_stage_u[i]); cudaFree(m->d_stage_y[i]);
@@ -254,6 +286,10 @@ extern "C" int acmeb200_model_create(const acmeb200_model_desc* d, int64_t first
             de.kind = el.kind; de.q_off = el.q_offset; de.c_off = const_total; de.row = row; de.j_off = joff;
             for (int r = 0; r < elem_nn(el.kind); r++)
                 if (row + r < MAX_ROWS) dm.row_elem[i][row + r] = (unsigned char)e;
+            if (zoff + row + elem_nn(el.kind) <= MAX_TOTAL_ROWS && joff + elem_nj(el.kind) <= 127 && el.q_offset + elem_nq(el.kind) <= 255)
+                probe_rows(el.kind, &dm.rows[zoff + row], el.q_offset, joff);
+            else
+                m->rows_ok = false;
             // derived constants for every instance
             const int nc = elem_nc(el.kind);
             for (int k = 0; k < nc; k++) h_consts.emplace_back((size_t)count);
@@ -373,9 +409,12 @@ extern "C" int acmeb200_model_create(const acmeb200_model_desc* d, int64_t first
 
 // picks the kernel, (re)allocates its state and initialises it
 static int coop_lanes_for(const acmeb200_model* m) {
-    if (m->blob_stride != 0 || m->has_cache || m->dm.nsub == 0 || m->max_nn > MAX_ROWS) return 0;
+    if (m->blob_stride != 0 || m->has_cache || m->dm.nsub == 0 || m->max_nn > MAX_ROWS || !m->rows_ok) return 0;
     const int need = std::max(m->max_nn, m->max_nelem);
     int lanes = need <= 8 ? 8 : (need <= 16 ? 16 : 32);
+    // small batches are latency-bound: one instance per warp avoids the two groups of a warp
+    // serialising when their Newton iteration counts differ, and doubles the warps in flight
+    if (m->B * lanes < (int64_t)148 * 32 * 24) lanes = std::min(32, lanes * 2);
     size_t smem = lanes == 8 ? coop_smem_bytes<8>(m->dm) : lanes == 16 ? coop_smem_bytes<16>(m->dm) : coop_smem_bytes<32>(m->dm);
     while (smem > 200 * 1024 && lanes < 32) {  // fewer groups per CTA
         lanes *= 2;
@@ -397,8 +436,29 @@ static int select_kernel(acmeb200_model* m) {
     }
     m->ws_rows = m->tpi ? m->tpi->state_rows : m->dm.w_rows;
     if (m->tpi) m->kernel_name = m->tpi->name;
-    else if (m->coop_lanes) m->kernel_name = "coop<" + std::to_string(m->coop_lanes) + " lanes per instance, runtime dims, state in shared memory>";
+    else if (m->coop_lanes) m->kernel_name = "coop<" + std::to_string(m->coop_lanes) + " lanes per instance, runtime dims, state in shared memory" +
+                                            (m->dm.solver == ACMEB200_SOLVER_HOMOTOPY_CACHING ? ", dynamic solution cache>" : ">");
     else m->kernel_name = "generic<thread-per-instance, runtime dims>";
+    // dynamic solution caches (cooperative kernel + CachingSolver only)
+    for (void* p : m->d_dyn) cudaFree(p);
+    m->d_dyn.clear();
+    for (int i = 0; i < m->dm.nsub; i++) {
+        DevSub& s = m->dm.subs[i];
+        s.dyn_ps = nullptr; s.dyn_zs = nullptr; s.dyn_n = nullptr; s.dyn_cap = 0;
+        if (!m->coop_lanes || m->dm.solver != ACMEB200_SOLVER_HOMOTOPY_CACHING) continue;
+        size_t free_b = 0, total_b = 0;
+        CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+        int cap = 1024;
+        while (cap > 32 && (size_t)m->B * (s.np + s.nn) * cap * 8 > free_b / 8) cap /= 2;
+        void *ps = nullptr, *zs = nullptr, *nn_ = nullptr;
+        CUDA_TRY(cudaMalloc(&ps, std::max<size_t>(8, (size_t)m->B * s.np * cap * 8)));
+        m->d_dyn.push_back(ps);
+        CUDA_TRY(cudaMalloc(&zs, std::max<size_t>(8, (size_t)m->B * s.nn * cap * 8)));
+        m->d_dyn.push_back(zs);
+        CUDA_TRY(cudaMalloc(&nn_, sizeof(int) * (size_t)m->B));
+        m->d_dyn.push_back(nn_);
+        s.dyn_ps = (double*)ps; s.dyn_zs = (double*)zs; s.dyn_n = (int*)nn_; s.dyn_cap = cap;
+    }
     cudaFree(m->d_ws);
     m->d_ws = nullptr;
     CUDA_TRY(cudaMalloc(&m->d_ws, sizeof(double) * (size_t)std::max<int64_t>(1, m->ws_rows * m->B)));

@@ -8,6 +8,19 @@ namespace acme {
 constexpr int MAX_SUBS = 8;
 constexpr int MAX_ELEMS = 48;
 constexpr int MAX_ROWS = 32;  // nn per sub-problem supported by the cooperative kernel
+constexpr int MAX_TOTAL_ROWS = 64;
+
+// One row of the block-diagonal element Jacobian Jq as a short list of terms
+// coef * e_q, coef either a variable entry jv[j] of the element evaluation or a
+// constant (+-1).  Derived on the host by probing the elements' row<R>() functions, so
+// the cooperative kernel forms J = Jq*fq and Jp = Jq*pexp without a per-entry switch
+// over element kinds.
+struct RowProg {
+    unsigned char n;
+    unsigned char q[5];   // q index within the sub
+    signed char jv[5];    // index into the sub's jv scratch, or -1 for a constant
+    float c[5];           // the constant when jv < 0
+};
 
 struct DevElem {
     int kind;
@@ -30,6 +43,12 @@ struct DevSub {
     const int* ps_idx;
     const double* ps;
     const double* zs;
+    // dynamic per-instance solution cache of the cooperative kernel (CachingSolver, solvers.jl:319-396):
+    // ps [inst][np][cap], zs [inst][nn][cap], n [inst]; entry 0 is the initial (0, init_z)
+    double* dyn_ps;
+    double* dyn_zs;
+    int* dyn_n;
+    int dyn_cap;
 };
 
 struct DevModel {
@@ -41,6 +60,7 @@ struct DevModel {
     DevSub subs[MAX_SUBS];
     DevElem elems[MAX_ELEMS];
     unsigned char row_elem[MAX_SUBS][MAX_ROWS];  // residual row -> element index within the sub
+    RowProg rows[MAX_TOTAL_ROWS];                // sparse rows of Jq, indexed by sub.zoff + row
 };
 
 // device statistics block (mirrors acmeb200_stats, all 64-bit counters)

@@ -94,9 +94,12 @@ __device__ inline double c_evaluate(const CCtx<L>& g, const DevSub& s, int si, i
     const int nn2 = s.nn * s.nn;
     for (int idx = g.lane; idx < nn2; idx += L) {  // J = Jq*fq, one entry per lane and pass
         const int r = idx % s.nn, c = idx / s.nn;
-        const DevElem& el = m.elems[s.elem0 + m.row_elem[si][r]];
-        const double v = elem_row(el.kind, r - el.row, &g.W(m.w_jv + el.j_off),
-                                  [&](int k) { return g.mat(s.o_fq, s.nq, el.q_off + k, c); });
+        const RowProg& rp = m.rows[s.zoff + r];
+        double v = 0.0;
+        for (int t = 0; t < rp.n; t++) {
+            const double coef = rp.jv[t] >= 0 ? g.W(m.w_jv + rp.jv[t]) : (double)rp.c[t];
+            v = fma(coef, g.mat(s.o_fq, s.nq, rp.q[t], c), v);
+        }
         g.W(Jrow + idx) = v;
         if (!isfinite(v)) bad = true;
     }
@@ -115,9 +118,13 @@ __device__ inline void c_calc_Jp(const CCtx<L>& g, const DevSub& s, int si, int 
     const int n = s.nn * s.np;
     for (int idx = g.lane; idx < n; idx += L) {
         const int r = idx % s.nn, c = idx / s.nn;
-        const DevElem& el = m.elems[s.elem0 + m.row_elem[si][r]];
-        g.W(Jprow + idx) = elem_row(el.kind, r - el.row, &g.W(m.w_jv + el.j_off),
-                                    [&](int k) { return g.mat(s.o_pexp, s.nq, el.q_off + k, c); });
+        const RowProg& rp = m.rows[s.zoff + r];
+        double v = 0.0;
+        for (int t = 0; t < rp.n; t++) {
+            const double coef = rp.jv[t] >= 0 ? g.W(m.w_jv + rp.jv[t]) : (double)rp.c[t];
+            v = fma(coef, g.mat(s.o_pexp, s.nq, rp.q[t], c), v);
+        }
+        g.W(Jprow + idx) = v;
     }
     g.sync();
 }
@@ -254,33 +261,71 @@ __device__ inline GSolveResult c_simple_solve(const CCtx<L>& g, const DevSub& s,
     return r;
 }
 
-// solve(::CachingSolver, p) with the fresh one-point cache (0, init_z)  (solvers.jl:327-373)
+// solve(::CachingSolver, p)  (solvers.jl:347-396) with a DYNAMIC per-instance cache: the start
+// point is the nearest of {current origin, every stored solution}; solutions that needed more
+// than 5 iterations are appended (solvers.jl:374-386).  The reference finds the nearest stored
+// point with a k-d tree plus a linear scan of the newest entries; here all stored points are
+// scanned, the lanes of the group taking one point each -- the same exact nearest neighbour (up to
+// distance ties), no tree to rebuild.  Capacity is fixed (dyn_cap); once full nothing is added.
 template <int L>
-__device__ inline GSolveResult c_base_solve(const CCtx<L>& g, const DevSub& s, int si, int prow) {
+__device__ inline GSolveResult c_base_solve(const CCtx<L>& g, const DevSub& s, int si, int prow, int64_t inst) {
     const DevModel& m = g.m;
-    if (m.solver == ACMEB200_SOLVER_HOMOTOPY_CACHING) {
-        double best = 0.0, d0 = 0.0;
+    const bool caching = m.solver == ACMEB200_SOLVER_HOMOTOPY_CACHING && s.dyn_cap > 0;
+    double* cps = nullptr;
+    double* czs = nullptr;
+    int n = 0;
+    if (caching) {
+        cps = s.dyn_ps + inst * (int64_t)s.np * s.dyn_cap;
+        czs = s.dyn_zs + inst * (int64_t)s.nn * s.dyn_cap;
+        n = s.dyn_n[inst];
+        double best = 0.0;
         for (int i = 0; i < s.np; i++) {
-            const double pi = g.W(prow + i), d = pi - g.W(s.w_lastp + i);
+            const double d = g.W(prow + i) - g.W(s.w_lastp + i);
             best = fma(d, d, best);
-            d0 = fma(pi, pi, d0);
         }
-        if (d0 < best) {
+        double lbest = best;
+        int lidx = -1;
+        for (int idx = g.lane; idx < n; idx += L) {
+            double d2 = 0.0;
+            for (int d = 0; d < s.np; d++) {
+                const double df = cps[(int64_t)d * s.dyn_cap + idx] - g.W(prow + d);
+                d2 = fma(df, df, d2);
+            }
+            if (d2 < lbest) { lbest = d2; lidx = idx; }
+        }
+#pragma unroll
+        for (int o = L / 2; o > 0; o >>= 1) {
+            const double ob = __shfl_xor_sync(g.gmask, lbest, o, L);
+            const int oi = __shfl_xor_sync(g.gmask, lidx, o, L);
+            // ties: the current origin (-1) wins over stored points (the reference replaces it only on
+            // a strictly smaller distance), among stored points the older one wins
+            if (ob < lbest || (ob == lbest && (oi < 0 ? lidx >= 0 : (lidx >= 0 && oi < lidx)))) { lbest = ob; lidx = oi; }
+        }
+        if (lidx >= 0) {  // uniform within the group
             g.sync();
-            for (int i = g.lane; i < s.np; i += L) g.W(m.w_cp + i) = 0.0;
-            for (int i = g.lane; i < s.nn; i += L) g.W(m.w_z + i) = g.iz(s.o_initz + i);
+            for (int i = g.lane; i < s.np; i += L) g.W(m.w_cp + i) = cps[(int64_t)i * s.dyn_cap + lidx];
+            for (int i = g.lane; i < s.nn; i += L) g.W(m.w_z + i) = czs[(int64_t)i * s.dyn_cap + lidx];
             g.sync();
             c_set_origin<L>(g, s, si, m.w_cp, m.w_z);
         }
     }
-    return c_simple_solve<L>(g, s, si, prow);
+    const GSolveResult r = c_simple_solve<L>(g, s, si, prow);
+    if (caching && r.iters > 5 && r.converged && n < s.dyn_cap) {
+        for (int i = g.lane; i < s.np; i += L) cps[(int64_t)i * s.dyn_cap + n] = g.W(prow + i);
+        for (int i = g.lane; i < s.nn; i += L) czs[(int64_t)i * s.dyn_cap + n] = g.W(m.w_z + i);
+        g.sync();
+        if (g.lane == 0) s.dyn_n[inst] = n + 1;
+        __threadfence_block();
+        g.sync();
+    }
+    return r;
 }
 
 // solve(::HomotopySolver, p)  (solvers.jl:268-296)
 template <int L>
-__device__ inline GSolveResult c_solve(const CCtx<L>& g, const DevSub& s, int si, bool& used_homotopy) {
+__device__ inline GSolveResult c_solve(const CCtx<L>& g, const DevSub& s, int si, bool& used_homotopy, int64_t inst) {
     const DevModel& m = g.m;
-    GSolveResult r = c_base_solve<L>(g, s, si, m.w_p);
+    GSolveResult r = c_base_solve<L>(g, s, si, m.w_p, inst);
     used_homotopy = false;
     if (m.solver == ACMEB200_SOLVER_SIMPLE || r.converged) return r;
     used_homotopy = true;
@@ -297,7 +342,7 @@ __device__ inline GSolveResult c_solve(const CCtx<L>& g, const DevSub& s, int si
             g.W(m.w_pa + i) = pa;
         }
         g.sync();
-        r = c_base_solve<L>(g, s, si, m.w_pa);
+        r = c_base_solve<L>(g, s, si, m.w_pa, inst);
         iters += r.iters;
         if (r.converged) {
             best_a = a;
@@ -383,7 +428,7 @@ __global__ void __launch_bounds__(COOP_TPB) k_coop(const __grid_constant__ DevMo
                 }
                 g.sync();
                 bool used_h;
-                const GSolveResult r = c_solve<L>(g, s, si, used_h);
+                const GSolveResult r = c_solve<L>(g, s, si, used_h, inst);
                 if (lane == 0) {
                     st_solves++;
                     st_iters += (unsigned)r.iters;

@@ -351,6 +351,11 @@ __global__ void __launch_bounds__(128) k_generic(const __grid_constant__ DevMode
             for (int i = 0; i < s.np; i++) g.w(m.w_cp + i) = 0.0;
             for (int i = 0; i < s.nn; i++) g.w(m.w_z + i) = g.iz(s.o_initz + i);
             g_set_origin(g, s, m.w_cp, m.w_z);
+            if (s.dyn_cap > 0) {  // CachingSolver ctor: the cache holds (0, init_z)  (solvers.jl:327-333)
+                for (int i = 0; i < s.np; i++) s.dyn_ps[(inst * s.np + i) * (int64_t)s.dyn_cap] = 0.0;
+                for (int i = 0; i < s.nn; i++) s.dyn_zs[(inst * s.nn + i) * (int64_t)s.dyn_cap] = g.iz(s.o_initz + i);
+                s.dyn_n[inst] = 1;
+            }
         }
         a.status[inst] = 0;
         a.first_fail[inst] = -1;
