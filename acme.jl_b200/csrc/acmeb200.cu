@@ -9,6 +9,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -580,7 +581,9 @@ extern "C" int acmeb200_run(acmeb200_model* m, const double* U, int64_t u_stride
     const size_t row_u = (size_t)dm.nu * sizeof(double), row_y = (size_t)dm.ny * sizeof(double);
     const bool shared_u = (u_stride == 0) || dm.nu == 0;
     const size_t per_sample = std::max<size_t>(8, (size_t)m->B * std::max(shared_u ? 0 : row_u, row_y));
-    int64_t Tc = (int64_t)(((size_t)256 << 20) / per_sample);
+    size_t chunk_mb = 1024;  // staging chunk size; ACMEB200_CHUNK_MB overrides (tuning knob)
+    if (const char* e = getenv("ACMEB200_CHUNK_MB")) { const long v = atol(e); if (v >= 1 && v <= 8192) chunk_mb = (size_t)v; }
+    int64_t Tc = (int64_t)((chunk_mb << 20) / per_sample);
     Tc -= Tc % 16;
     Tc = std::max<int64_t>(16, std::min<int64_t>(Tc, N));
     const size_t ubytes = udev ? 8 : (shared_u ? std::max<size_t>(8, row_u * Tc) : row_u * Tc * m->B);

@@ -78,7 +78,8 @@ __device__ __forceinline__ double acme_exp(double x, const double* __restrict__ 
     double res = a * sc;
     const int hx = __double2hiint(x) & 0x7fffffff;
     // |x| >= 745 (or NaN): i is meaningless; exp is +Inf / 0 / NaN there
-    const double far = (x != x) ? x + x : (x < 0 ? 0.0 : __longlong_as_double(0x7ff0000000000000ll));
+    // +Inf for large x, NaN for NaN (NaN*Inf), 0 for very negative x -- no branch
+    const double far = x < 0 ? 0.0 : x * __longlong_as_double(0x7ff0000000000000ll);
     res = hx >= 0x40874800 ? far : res;
     return res;
 }

@@ -91,9 +91,11 @@ __device__ __forceinline__ bool lu_reg(double (&A)[dim1(N * N)], int (&piv)[dim1
     bool ok = true;
     static_for<0, N>([&](auto kk) {
         constexpr int k = decltype(kk)::value;
+        // first strict maximum of |A[i][k]|, i >= k (solvers.jl:60-68).  Starting from the diagonal
+        // entry instead of 0.0 only differs for NaN entries, which the caller has already rejected.
         int kp = k;
-        double amax = 0.0;
-        static_for<k, N>([&](auto ii) {
+        double amax = fabs(A[k * N + k]);
+        static_for<k + 1, N>([&](auto ii) {
             constexpr int i = decltype(ii)::value;
             const double absi = fabs(A[k * N + i]);
             if (absi > amax) { kp = i; amax = absi; }
