@@ -157,23 +157,26 @@ def ncu_traffic():
     return None
 
 
-def run_reference(args, rank: int, world: int):
+def run_reference(args, rank: int, world: int, emit=print):
     """--impl reference: the reference's CPU algorithm (restated; see cpu_baseline) on the host cores."""
     if rank != 0:
         return
-    per_step = []
+    per_step, per_ms = [], []
     info = None
     for i in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
         info = cpu_baseline(budget_s=6.0)
         if i >= args.warmup:
             per_step.append(info["value"])
+            per_ms.append((time.perf_counter() - t0) * 1e3)
     v = float(np.mean(per_step)) if per_step else info["value"]
     info["value"] = v
-    print(json.dumps({
+    emit(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": "Msamples/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "diodeclipper.jl, swept Is/eta, 1 s of 1 kHz sine @ 44.1 kHz; bounded sample per step",
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(np.mean(per_ms)) if per_ms else None,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "diodeclipper.jl, swept Is/eta, 1 s of 1 kHz sine @ 44.1 kHz; each step is a bounded "
+                               "sample (a few seconds of host work) of that sweep, calibration run included in ms_per_step",
                    "batch_per_gpu": BATCH_PER_GPU, "samples": N_SAMPLES},
         "cpu_baseline": info,
         "e2e": {"value": v, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -181,8 +184,23 @@ def run_reference(args, rank: int, world: int):
     }))
 
 
+def _stdout_to_stderr():
+    """Everything except the final JSON line goes to stderr (NCCL prints its version banner on
+    stdout during init); returns a function that prints one line on the real stdout."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line: str):
+        sys.stdout.flush()
+        os.write(real, (line + "\n").encode())
+
+    return emit
+
+
 def main():
     global N_SAMPLES
+    emit = _stdout_to_stderr()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -202,7 +220,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
     if args.impl == "reference":
-        run_reference(args, rank, world)
+        run_reference(args, rank, world, emit)
         return
 
     import torch
@@ -333,7 +351,7 @@ def main():
             out["e2e"] = e2e
         if world == 1 and not args.no_cpu:
             out["cpu_baseline"] = cpu_baseline()
-        print(json.dumps(out))
+        emit(json.dumps(out))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
