@@ -23,6 +23,11 @@
 
 using namespace acme;
 
+// compile-time shapes of the cooperative kernel (BASELINE config 4: examples/superover.jl with the
+// three potentiometers as inputs: nx 11, nu 4, ny 1, nn 13, nq 29, np 11, 8 elements, 23 jv entries)
+using CoopSuperover = CoopStatic<11, 4, 1, 13, 29, 11, 8, 23>;
+
+
 // ------------------------------------------------------------------ errors
 static thread_local std::string g_err;
 static int fail(int code, const char* fmt, ...) {
@@ -68,6 +73,7 @@ struct acmeb200_model {
     std::vector<double> h_blob;  // blob of instance 0 (or the shared blob)
     const TpiEntry* tpi = nullptr;
     int coop_lanes = 0;  // 0: not the cooperative kernel
+    int coop_static = 0; // 1: CoopSuperover compile-time shape
     bool rows_ok = true;
     bool has_cache = false;
     int max_nn = 0, max_nelem = 0;
@@ -432,12 +438,14 @@ static int select_kernel(acmeb200_model* m) {
         const int lanes = coop_lanes_for(m);
         // automatic choice: large non-linear systems profit from lanes sharing one instance
         if (lanes && (m->kernel_mode == 2 || m->max_nn >= 4)) m->coop_lanes = lanes;
+        m->coop_static = (m->coop_lanes >= 16 && CoopSuperover::matches(m->dm)) ? 1 : 0;
         if (m->kernel_mode == 2 && !m->coop_lanes)
             return fail(ACMEB200_EUNSUPPORTED, "the cooperative kernel needs shared matrices, no frozen cache and nn <= %d", MAX_ROWS);
     }
     m->ws_rows = m->tpi ? m->tpi->state_rows : m->dm.w_rows;
     if (m->tpi) m->kernel_name = m->tpi->name;
-    else if (m->coop_lanes) m->kernel_name = "coop<" + std::to_string(m->coop_lanes) + " lanes per instance, runtime dims, state in shared memory" +
+    else if (m->coop_lanes) m->kernel_name = "coop<" + std::to_string(m->coop_lanes) + " lanes per instance, " +
+                                            (m->coop_static ? "compile-time dims [superover]" : "runtime dims") + ", state in shared memory" +
                                             (m->dm.solver == ACMEB200_SOLVER_HOMOTOPY_CACHING ? ", dynamic solution cache>" : ">");
     else m->kernel_name = "generic<thread-per-instance, runtime dims>";
     // dynamic solution caches (cooperative kernel + CachingSolver only)
@@ -476,17 +484,17 @@ static RunArgs base_args(acmeb200_model* m) {
     return a;
 }
 
-template <int L>
+template <int L, class P>
 static cudaError_t launch_coop(const acmeb200_model* m, const RunArgs& a, cudaStream_t stream) {
     const size_t smem = coop_smem_bytes<L>(m->dm);
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(k_coop<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(k_coop<L, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
     constexpr int GPC = COOP_TPB / L;
-    k_coop<L><<<(unsigned)((a.ninst + GPC - 1) / GPC), COOP_TPB, smem, stream>>>(m->dm, a);
+    k_coop<L, P><<<(unsigned)((a.ninst + GPC - 1) / GPC), COOP_TPB, smem, stream>>>(m->dm, a);
     return cudaGetLastError();
 }
 
@@ -494,9 +502,13 @@ static cudaError_t launch(acmeb200_model* m, const RunArgs& a, cudaStream_t stre
     m->launches++;
     if (m->tpi) return m->tpi->launch(m, a, stream);
     if (m->coop_lanes && !a.init) {  // the generic kernel initialises the (shared) state layout
-        if (m->coop_lanes == 8) return launch_coop<8>(m, a, stream);
-        if (m->coop_lanes == 16) return launch_coop<16>(m, a, stream);
-        return launch_coop<32>(m, a, stream);
+        if (m->coop_static == 1) {
+            if (m->coop_lanes == 16) return launch_coop<16, CoopSuperover>(m, a, stream);
+            return launch_coop<32, CoopSuperover>(m, a, stream);
+        }
+        if (m->coop_lanes == 8) return launch_coop<8, CoopDyn>(m, a, stream);
+        if (m->coop_lanes == 16) return launch_coop<16, CoopDyn>(m, a, stream);
+        return launch_coop<32, CoopDyn>(m, a, stream);
     }
     const int tpb = 128;
     k_generic<<<(unsigned)((a.ninst + tpb - 1) / tpb), tpb, 0, stream>>>(m->dm, a);

@@ -25,6 +25,51 @@
 
 namespace acme {
 
+// Dimension policy: CoopDyn reads every dimension, blob offset and workspace row from the
+// DevModel at run time; CoopStatic<...> fixes them at compile time (single sub-problem), which
+// turns the index arithmetic of the runtime-dimension code into immediates and lets the loops
+// unroll.  The static layout mirrors the host's packing order (acmeb200.cu) and is verified against
+// the DevModel before such an instantiation is selected.
+#define SD(stat, dyn) (P::STATIC ? (P::stat) : (dyn))
+struct CoopDyn {
+    static constexpr bool STATIC = false;
+    static constexpr int ZERO = 0, ONE = 1, NX = 0, NU = 0, NY = 0, NN = 0, NQ = 0, NP = 0, NE = 0;
+    static constexpr int O_A = 0, O_B = 0, O_C = 0, O_X0 = 0, O_DY = 0, O_EY = 0, O_FY = 0, O_Y0 = 0, O_DQ = 0, O_EQ = 0,
+                         O_FQPREV = 0, O_PEXP = 0, O_Q0 = 0, O_FQ = 0, BLOB_LEN = 0;
+    static constexpr int W_X = 0, W_U = 0, W_ZALL = 0, W_XNEW = 0, W_P = 0, W_PFULL = 0, W_Q = 0, W_RES = 0, W_JV = 0, W_Z = 0,
+                         W_TMP = 0, W_STARTP = 0, W_PA = 0, W_CP = 0, W_LASTP = 0, W_LASTZ = 0, W_LASTJP = 0, W_LU0 = 0,
+                         W_LU1 = 0, W_IPIV0 = 0, W_IPIV1 = 0, W_SEL = 0, W_ROWS = 0;
+};
+template <int NX_, int NU_, int NY_, int NN_, int NQ_, int NP_, int NE_, int NJV_>
+struct CoopStatic {
+    static constexpr bool STATIC = true;
+    static constexpr int ZERO = 0, ONE = 1, NX = NX_, NU = NU_, NY = NY_, NN = NN_, NQ = NQ_, NP = NP_, NE = NE_, NJV = NJV_;
+    static constexpr int O_A = 0, O_B = O_A + NX * NX, O_C = O_B + NX * NU, O_X0 = O_C + NX * NN, O_DY = O_X0 + NX,
+                         O_EY = O_DY + NY * NX, O_FY = O_EY + NY * NU, O_Y0 = O_FY + NY * NN, O_DQ = O_Y0 + NY,
+                         O_EQ = O_DQ + NP * NX, O_FQPREV = O_EQ + NP * NU, O_PEXP = O_FQPREV + NP * NN,
+                         O_Q0 = O_PEXP + NQ * NP, O_FQ = O_Q0 + NQ, BLOB_LEN = O_FQ + NQ * NN;
+    static constexpr int W_X = 0, W_U = W_X + NX, W_ZALL = W_U + NU, W_XNEW = W_ZALL + NN, W_P = W_XNEW + NX,
+                         W_PFULL = W_P + NP, W_Q = W_PFULL + NQ, W_RES = W_Q + NQ, W_JV = W_RES + NN, W_Z = W_JV + NJV,
+                         W_TMP = W_Z + NN, W_STARTP = W_TMP + NN, W_PA = W_STARTP + NP, W_CP = W_PA + NP,
+                         W_LASTP = W_CP + NP, W_LASTZ = W_LASTP + NP, W_LASTJP = W_LASTZ + NN, W_LU0 = W_LASTJP + NN * NP,
+                         W_LU1 = W_LU0 + NN * NN, W_IPIV0 = W_LU1 + NN * NN, W_IPIV1 = W_IPIV0 + NN, W_SEL = W_IPIV1 + NN,
+                         W_ROWS = W_SEL + 1;
+    // does a DevModel have exactly this shape and layout?
+    static bool matches(const DevModel& m) {
+        if (m.nsub != 1 || m.nx != NX || m.nu != NU || m.ny != NY) return false;
+        const DevSub& s = m.subs[0];
+        return s.nn == NN && s.nq == NQ && s.np == NP && s.nelem == NE && s.njv == NJV && s.zoff == 0 && s.elem0 == 0 &&
+               s.o_initz == 0 && m.o_a == O_A && m.o_b == O_B && m.o_c == O_C && m.o_x0 == O_X0 && m.o_dy == O_DY &&
+               m.o_ey == O_EY && m.o_fy == O_FY && m.o_y0 == O_Y0 && s.o_dq == O_DQ && s.o_eq == O_EQ &&
+               s.o_fqprev == O_FQPREV && s.o_pexp == O_PEXP && s.o_q0 == O_Q0 && s.o_fq == O_FQ && m.blob_len == BLOB_LEN &&
+               m.w_x == W_X && m.w_u == W_U && m.w_zall == W_ZALL && m.w_xnew == W_XNEW && m.w_p == W_P &&
+               m.w_pfull == W_PFULL && m.w_q == W_Q && m.w_res == W_RES && m.w_jv == W_JV && m.w_z == W_Z &&
+               m.w_tmp == W_TMP && m.w_startp == W_STARTP && m.w_pa == W_PA && m.w_cp == W_CP && s.w_lastp == W_LASTP &&
+               s.w_lastz == W_LASTZ && s.w_lastJp == W_LASTJP && s.w_LU[0] == W_LU0 && s.w_LU[1] == W_LU1 &&
+               s.w_ipiv[0] == W_IPIV0 && s.w_ipiv[1] == W_IPIV1 && s.w_sel == W_SEL && m.w_rows == W_ROWS;
+    }
+};
+
 template <int L>
 struct CCtx {
     const DevModel& m;
@@ -52,53 +97,53 @@ __device__ __forceinline__ double group_max(const CCtx<L>& g, double v) {
 }
 
 // set_p!: pfull = q0 + pexp*p   (ACME.jl:237-243)
-template <int L>
+template <int L, class P>
 __device__ inline void c_set_p(const CCtx<L>& g, const DevSub& s, int prow) {
-    for (int i = g.lane; i < s.nq; i += L) {
-        double acc = g.mat(s.o_q0, s.nq, i, 0);
-        for (int j = 0; j < s.np; j++) acc = fma(g.mat(s.o_pexp, s.nq, i, j), g.W(prow + j), acc);
-        g.W(g.m.w_pfull + i) = acc;
+    for (int i = g.lane; i < SD(NQ, s.nq); i += L) {
+        double acc = g.mat(SD(O_Q0, s.o_q0), SD(NQ, s.nq), i, 0);
+        for (int j = 0; j < SD(NP, s.np); j++) acc = fma(g.mat(SD(O_PEXP, s.o_pexp), SD(NQ, s.nq), i, j), g.W(prow + j), acc);
+        g.W(SD(W_PFULL, g.m.w_pfull) + i) = acc;
     }
     g.sync();
 }
 
 // evaluate!  (ACME.jl:178-188): returns max|res| (NaN-propagating), J into rows Jrow
-template <int L>
+template <int L, class P>
 __device__ inline double c_evaluate(const CCtx<L>& g, const DevSub& s, int si, int zrow, int Jrow, bool& Jfinite) {
     const DevModel& m = g.m;
-    for (int i = g.lane; i < s.nq; i += L) {
-        double acc = g.W(m.w_pfull + i);
-        for (int j = 0; j < s.nn; j++) acc = fma(g.mat(s.o_fq, s.nq, i, j), g.W(zrow + j), acc);
-        g.W(m.w_q + i) = acc;
+    for (int i = g.lane; i < SD(NQ, s.nq); i += L) {
+        double acc = g.W(SD(W_PFULL, m.w_pfull) + i);
+        for (int j = 0; j < SD(NN, s.nn); j++) acc = fma(g.mat(SD(O_FQ, s.o_fq), SD(NQ, s.nq), i, j), g.W(zrow + j), acc);
+        g.W(SD(W_Q, m.w_q) + i) = acc;
     }
     g.sync();
     double rmax = 0.0;
     bool bad = false, nan = false;
-    for (int e = g.lane; e < s.nelem; e += L) {  // one element per lane
-        const DevElem& el = m.elems[s.elem0 + e];
+    for (int e = g.lane; e < SD(NE, s.nelem); e += L) {  // one element per lane
+        const DevElem& el = m.elems[SD(ZERO, s.elem0) + e];
         double res[2], jv[4];
-        elem_eval(el.kind, g.consts + el.c_off, &g.W(m.w_q + el.q_off), res, jv);
+        elem_eval(el.kind, g.consts + el.c_off, &g.W(SD(W_Q, m.w_q) + el.q_off), res, jv);
         const int nn = elem_nn(el.kind), nj = elem_nj(el.kind);
         for (int k = 0; k < nj; k++) {
-            g.W(m.w_jv + el.j_off + k) = jv[k];
+            g.W(SD(W_JV, m.w_jv) + el.j_off + k) = jv[k];
             if (!isfinite(jv[k])) bad = true;
         }
         for (int r = 0; r < nn; r++) {
-            g.W(m.w_res + el.row + r) = res[r];
+            g.W(SD(W_RES, m.w_res) + el.row + r) = res[r];
             const double a = fabs(res[r]);
             if (a != a) nan = true;
             if (a > rmax) rmax = a;
         }
     }
     g.sync();
-    const int nn2 = s.nn * s.nn;
+    const int nn2 = SD(NN, s.nn) * SD(NN, s.nn);
     for (int idx = g.lane; idx < nn2; idx += L) {  // J = Jq*fq, one entry per lane and pass
-        const int r = idx % s.nn, c = idx / s.nn;
-        const RowProg& rp = m.rows[s.zoff + r];
+        const int r = idx % SD(NN, s.nn), c = idx / SD(NN, s.nn);
+        const RowProg& rp = m.rows[SD(ZERO, s.zoff) + r];
         double v = 0.0;
         for (int t = 0; t < rp.n; t++) {
-            const double coef = rp.jv[t] >= 0 ? g.W(m.w_jv + rp.jv[t]) : (double)rp.c[t];
-            v = fma(coef, g.mat(s.o_fq, s.nq, rp.q[t], c), v);
+            const double coef = rp.jv[t] >= 0 ? g.W(SD(W_JV, m.w_jv) + rp.jv[t]) : (double)rp.c[t];
+            v = fma(coef, g.mat(SD(O_FQ, s.o_fq), SD(NQ, s.nq), rp.q[t], c), v);
         }
         g.W(Jrow + idx) = v;
         if (!isfinite(v)) bad = true;
@@ -112,17 +157,17 @@ __device__ inline double c_evaluate(const CCtx<L>& g, const DevSub& s, int si, i
 }
 
 // calc_Jp!: Jp = Jq*pexp   (ACME.jl:246-251)
-template <int L>
+template <int L, class P>
 __device__ inline void c_calc_Jp(const CCtx<L>& g, const DevSub& s, int si, int Jprow) {
     const DevModel& m = g.m;
-    const int n = s.nn * s.np;
+    const int n = SD(NN, s.nn) * SD(NP, s.np);
     for (int idx = g.lane; idx < n; idx += L) {
-        const int r = idx % s.nn, c = idx / s.nn;
-        const RowProg& rp = m.rows[s.zoff + r];
+        const int r = idx % SD(NN, s.nn), c = idx / SD(NN, s.nn);
+        const RowProg& rp = m.rows[SD(ZERO, s.zoff) + r];
         double v = 0.0;
         for (int t = 0; t < rp.n; t++) {
-            const double coef = rp.jv[t] >= 0 ? g.W(m.w_jv + rp.jv[t]) : (double)rp.c[t];
-            v = fma(coef, g.mat(s.o_pexp, s.nq, rp.q[t], c), v);
+            const double coef = rp.jv[t] >= 0 ? g.W(SD(W_JV, m.w_jv) + rp.jv[t]) : (double)rp.c[t];
+            v = fma(coef, g.mat(SD(O_PEXP, s.o_pexp), SD(NQ, s.nq), rp.q[t], c), v);
         }
         g.W(Jprow + idx) = v;
     }
@@ -130,7 +175,7 @@ __device__ inline void c_calc_Jp(const CCtx<L>& g, const DevSub& s, int si, int 
 }
 
 // setlhs!  (solvers.jl:46-96): rows over lanes, pivot search by group reduction
-template <int L>
+template <int L, class P>
 __device__ inline bool c_lu(const CCtx<L>& g, int n, int A, int piv) {
     for (int k = 0; k < n; k++) {
         // first strict maximum of |A[i][k]|, i >= k
@@ -173,7 +218,7 @@ __device__ inline bool c_lu(const CCtx<L>& g, int n, int A, int piv) {
 }
 
 // solve!  (solvers.jl:98-132)
-template <int L>
+template <int L, class P>
 __device__ inline void c_lusolve(const CCtx<L>& g, int n, int A, int piv, int xr) {
     g.sync();
     if (g.lane == 0)
@@ -201,61 +246,61 @@ __device__ inline void c_lusolve(const CCtx<L>& g, int n, int A, int piv, int xr
 }
 
 // set_extrapolation_origin(solver, p, z)  (solvers.jl:183-196)
-template <int L>
+template <int L, class P>
 __device__ inline void c_set_origin(const CCtx<L>& g, const DevSub& s, int si, int prow, int zrow) {
-    const int sel = (int)g.W(s.w_sel);
+    const int sel = (int)g.W(SD(W_SEL, s.w_sel));
     bool Jfin;
-    c_set_p<L>(g, s, prow);
-    c_evaluate<L>(g, s, si, zrow, s.w_LU[sel], Jfin);
-    c_lu<L>(g, s.nn, s.w_LU[sel], s.w_ipiv[sel]);
-    c_calc_Jp<L>(g, s, si, s.w_lastJp);
-    for (int i = g.lane; i < s.np; i += L) g.W(s.w_lastp + i) = g.W(prow + i);
-    for (int i = g.lane; i < s.nn; i += L) g.W(s.w_lastz + i) = g.W(zrow + i);
+    c_set_p<L, P>(g, s, prow);
+    c_evaluate<L, P>(g, s, si, zrow, (P::STATIC ? ((sel) ? P::W_LU1 : P::W_LU0) : s.w_LU[sel]), Jfin);
+    c_lu<L, P>(g, SD(NN, s.nn), (P::STATIC ? ((sel) ? P::W_LU1 : P::W_LU0) : s.w_LU[sel]), (P::STATIC ? ((sel) ? P::W_IPIV1 : P::W_IPIV0) : s.w_ipiv[sel]));
+    c_calc_Jp<L, P>(g, s, si, SD(W_LASTJP, s.w_lastJp));
+    for (int i = g.lane; i < SD(NP, s.np); i += L) g.W(SD(W_LASTP, s.w_lastp) + i) = g.W(prow + i);
+    for (int i = g.lane; i < SD(NN, s.nn); i += L) g.W(SD(W_LASTZ, s.w_lastz) + i) = g.W(zrow + i);
     g.sync();
 }
 
 // solve(::SimpleSolver, p)  (solvers.jl:207-236)
-template <int L>
+template <int L, class P>
 __device__ inline GSolveResult c_simple_solve(const CCtx<L>& g, const DevSub& s, int si, int prow) {
     const DevModel& m = g.m;
-    const int nn = s.nn, np = s.np;
-    const int sel = (int)g.W(s.w_sel);
-    c_set_p<L>(g, s, prow);
+    const int nn = SD(NN, s.nn), np = SD(NP, s.np);
+    const int sel = (int)g.W(SD(W_SEL, s.w_sel));
+    c_set_p<L, P>(g, s, prow);
     for (int i = g.lane; i < nn; i += L) {
         double acc = 0.0;
         for (int j = 0; j < np; j++)
-            acc = fma(g.W(s.w_lastJp + j * nn + i), g.W(prow + j) - g.W(s.w_lastp + j), acc);
-        g.W(m.w_tmp + i) = acc;
+            acc = fma(g.W(SD(W_LASTJP, s.w_lastJp) + j * nn + i), g.W(prow + j) - g.W(SD(W_LASTP, s.w_lastp) + j), acc);
+        g.W(SD(W_TMP, m.w_tmp) + i) = acc;
     }
-    c_lusolve<L>(g, nn, s.w_LU[sel], s.w_ipiv[sel], m.w_tmp);
-    for (int i = g.lane; i < nn; i += L) g.W(m.w_z + i) = g.W(s.w_lastz + i) - g.W(m.w_tmp + i);
+    c_lusolve<L, P>(g, nn, (P::STATIC ? ((sel) ? P::W_LU1 : P::W_LU0) : s.w_LU[sel]), (P::STATIC ? ((sel) ? P::W_IPIV1 : P::W_IPIV0) : s.w_ipiv[sel]), SD(W_TMP, m.w_tmp));
+    for (int i = g.lane; i < nn; i += L) g.W(SD(W_Z, m.w_z) + i) = g.W(SD(W_LASTZ, s.w_lastz) + i) - g.W(SD(W_TMP, m.w_tmp) + i);
     g.sync();
     const int cur = 1 - sel;
     GSolveResult r{false, 0};
     for (r.iters = 1; r.iters <= m.maxiter; r.iters++) {
         bool Jfin;
-        double resmax = c_evaluate<L>(g, s, si, m.w_z, s.w_LU[cur], Jfin);
+        double resmax = c_evaluate<L, P>(g, s, si, SD(W_Z, m.w_z), (P::STATIC ? ((cur) ? P::W_LU1 : P::W_LU0) : s.w_LU[cur]), Jfin);
         if (nn == 0) resmax = 0.0;
         if (!isfinite(resmax) || !Jfin) {
             r.converged = resmax < m.tol;
             return r;
         }
-        if (!c_lu<L>(g, nn, s.w_LU[cur], s.w_ipiv[cur])) {
+        if (!c_lu<L, P>(g, nn, (P::STATIC ? ((cur) ? P::W_LU1 : P::W_LU0) : s.w_LU[cur]), (P::STATIC ? ((cur) ? P::W_IPIV1 : P::W_IPIV0) : s.w_ipiv[cur]))) {
             r.converged = resmax < m.tol;
             return r;
         }
         if (resmax < m.tol) { r.converged = true; break; }
-        for (int i = g.lane; i < nn; i += L) g.W(m.w_tmp + i) = g.W(m.w_res + i);
-        c_lusolve<L>(g, nn, s.w_LU[cur], s.w_ipiv[cur], m.w_tmp);
-        for (int i = g.lane; i < nn; i += L) g.W(m.w_z + i) -= g.W(m.w_tmp + i);
+        for (int i = g.lane; i < nn; i += L) g.W(SD(W_TMP, m.w_tmp) + i) = g.W(SD(W_RES, m.w_res) + i);
+        c_lusolve<L, P>(g, nn, (P::STATIC ? ((cur) ? P::W_LU1 : P::W_LU0) : s.w_LU[cur]), (P::STATIC ? ((cur) ? P::W_IPIV1 : P::W_IPIV0) : s.w_ipiv[cur]), SD(W_TMP, m.w_tmp));
+        for (int i = g.lane; i < nn; i += L) g.W(SD(W_Z, m.w_z) + i) -= g.W(SD(W_TMP, m.w_tmp) + i);
         g.sync();
     }
     if (r.iters > m.maxiter) r.iters = m.maxiter;
     if (r.converged) {
-        c_calc_Jp<L>(g, s, si, s.w_lastJp);
-        if (g.lane == 0) g.W(s.w_sel) = (double)cur;
-        for (int i = g.lane; i < np; i += L) g.W(s.w_lastp + i) = g.W(prow + i);
-        for (int i = g.lane; i < nn; i += L) g.W(s.w_lastz + i) = g.W(m.w_z + i);
+        c_calc_Jp<L, P>(g, s, si, SD(W_LASTJP, s.w_lastJp));
+        if (g.lane == 0) g.W(SD(W_SEL, s.w_sel)) = (double)cur;
+        for (int i = g.lane; i < np; i += L) g.W(SD(W_LASTP, s.w_lastp) + i) = g.W(prow + i);
+        for (int i = g.lane; i < nn; i += L) g.W(SD(W_LASTZ, s.w_lastz) + i) = g.W(SD(W_Z, m.w_z) + i);
         g.sync();
     }
     return r;
@@ -267,7 +312,7 @@ __device__ inline GSolveResult c_simple_solve(const CCtx<L>& g, const DevSub& s,
 // point with a k-d tree plus a linear scan of the newest entries; here all stored points are
 // scanned, the lanes of the group taking one point each -- the same exact nearest neighbour (up to
 // distance ties), no tree to rebuild.  Capacity is fixed (dyn_cap); once full nothing is added.
-template <int L>
+template <int L, class P>
 __device__ inline GSolveResult c_base_solve(const CCtx<L>& g, const DevSub& s, int si, int prow, int64_t inst) {
     const DevModel& m = g.m;
     const bool caching = m.solver == ACMEB200_SOLVER_HOMOTOPY_CACHING && s.dyn_cap > 0;
@@ -275,19 +320,19 @@ __device__ inline GSolveResult c_base_solve(const CCtx<L>& g, const DevSub& s, i
     double* czs = nullptr;
     int n = 0;
     if (caching) {
-        cps = s.dyn_ps + inst * (int64_t)s.np * s.dyn_cap;
-        czs = s.dyn_zs + inst * (int64_t)s.nn * s.dyn_cap;
+        cps = s.dyn_ps + inst * (int64_t)SD(NP, s.np) * s.dyn_cap;
+        czs = s.dyn_zs + inst * (int64_t)SD(NN, s.nn) * s.dyn_cap;
         n = s.dyn_n[inst];
         double best = 0.0;
-        for (int i = 0; i < s.np; i++) {
-            const double d = g.W(prow + i) - g.W(s.w_lastp + i);
+        for (int i = 0; i < SD(NP, s.np); i++) {
+            const double d = g.W(prow + i) - g.W(SD(W_LASTP, s.w_lastp) + i);
             best = fma(d, d, best);
         }
         double lbest = best;
         int lidx = -1;
         for (int idx = g.lane; idx < n; idx += L) {
             double d2 = 0.0;
-            for (int d = 0; d < s.np; d++) {
+            for (int d = 0; d < SD(NP, s.np); d++) {
                 const double df = cps[(int64_t)d * s.dyn_cap + idx] - g.W(prow + d);
                 d2 = fma(df, df, d2);
             }
@@ -303,16 +348,16 @@ __device__ inline GSolveResult c_base_solve(const CCtx<L>& g, const DevSub& s, i
         }
         if (lidx >= 0) {  // uniform within the group
             g.sync();
-            for (int i = g.lane; i < s.np; i += L) g.W(m.w_cp + i) = cps[(int64_t)i * s.dyn_cap + lidx];
-            for (int i = g.lane; i < s.nn; i += L) g.W(m.w_z + i) = czs[(int64_t)i * s.dyn_cap + lidx];
+            for (int i = g.lane; i < SD(NP, s.np); i += L) g.W(SD(W_CP, m.w_cp) + i) = cps[(int64_t)i * s.dyn_cap + lidx];
+            for (int i = g.lane; i < SD(NN, s.nn); i += L) g.W(SD(W_Z, m.w_z) + i) = czs[(int64_t)i * s.dyn_cap + lidx];
             g.sync();
-            c_set_origin<L>(g, s, si, m.w_cp, m.w_z);
+            c_set_origin<L, P>(g, s, si, SD(W_CP, m.w_cp), SD(W_Z, m.w_z));
         }
     }
-    const GSolveResult r = c_simple_solve<L>(g, s, si, prow);
+    const GSolveResult r = c_simple_solve<L, P>(g, s, si, prow);
     if (caching && r.iters > 5 && r.converged && n < s.dyn_cap) {
-        for (int i = g.lane; i < s.np; i += L) cps[(int64_t)i * s.dyn_cap + n] = g.W(prow + i);
-        for (int i = g.lane; i < s.nn; i += L) czs[(int64_t)i * s.dyn_cap + n] = g.W(m.w_z + i);
+        for (int i = g.lane; i < SD(NP, s.np); i += L) cps[(int64_t)i * s.dyn_cap + n] = g.W(prow + i);
+        for (int i = g.lane; i < SD(NN, s.nn); i += L) czs[(int64_t)i * s.dyn_cap + n] = g.W(SD(W_Z, m.w_z) + i);
         g.sync();
         if (g.lane == 0) s.dyn_n[inst] = n + 1;
         __threadfence_block();
@@ -322,27 +367,27 @@ __device__ inline GSolveResult c_base_solve(const CCtx<L>& g, const DevSub& s, i
 }
 
 // solve(::HomotopySolver, p)  (solvers.jl:268-296)
-template <int L>
+template <int L, class P>
 __device__ inline GSolveResult c_solve(const CCtx<L>& g, const DevSub& s, int si, bool& used_homotopy, int64_t inst) {
     const DevModel& m = g.m;
-    GSolveResult r = c_base_solve<L>(g, s, si, m.w_p, inst);
+    GSolveResult r = c_base_solve<L, P>(g, s, si, SD(W_P, m.w_p), inst);
     used_homotopy = false;
     if (m.solver == ACMEB200_SOLVER_SIMPLE || r.converged) return r;
     used_homotopy = true;
     int iters = r.iters;
     double a = 0.5, best_a = 0.0;
     g.sync();
-    for (int i = g.lane; i < s.np; i += L) g.W(m.w_startp + i) = g.W(s.w_lastp + i);
+    for (int i = g.lane; i < SD(NP, s.np); i += L) g.W(SD(W_STARTP, m.w_startp) + i) = g.W(SD(W_LASTP, s.w_lastp) + i);
     g.sync();
     while (best_a < 1) {
-        for (int i = g.lane; i < s.np; i += L) {
-            double pa = g.W(m.w_startp + i);
+        for (int i = g.lane; i < SD(NP, s.np); i += L) {
+            double pa = g.W(SD(W_STARTP, m.w_startp) + i);
             pa *= (1 - a);
-            pa += a * g.W(m.w_p + i);
-            g.W(m.w_pa + i) = pa;
+            pa += a * g.W(SD(W_P, m.w_p) + i);
+            g.W(SD(W_PA, m.w_pa) + i) = pa;
         }
         g.sync();
-        r = c_base_solve<L>(g, s, si, m.w_pa, inst);
+        r = c_base_solve<L, P>(g, s, si, SD(W_PA, m.w_pa), inst);
         iters += r.iters;
         if (r.converged) {
             best_a = a;
@@ -369,7 +414,7 @@ __host__ __device__ inline size_t coop_smem_bytes(const DevModel& m) {
     return 16 + 8 * (coop_blob_doubles(m) + (COOP_TPB / L) * coop_group_doubles(m));
 }
 
-template <int L>
+template <int L, class P>
 __global__ void __launch_bounds__(COOP_TPB) k_coop(const __grid_constant__ DevModel m, const RunArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* blob_s = reinterpret_cast<double*>(smem_raw + 16);
@@ -378,8 +423,8 @@ __global__ void __launch_bounds__(COOP_TPB) k_coop(const __grid_constant__ DevMo
     constexpr int GPC = COOP_TPB / L;
     const int grp = threadIdx.x / L, lane = threadIdx.x % L;
     double* w = blob_s + nblob + (size_t)grp * ngrp;
-    double* consts_s = w + m.w_rows;
-    unsigned int* hist_s = reinterpret_cast<unsigned int*>(w + ((m.w_rows + m.nconst + 1) & ~1));
+    double* consts_s = w + SD(W_ROWS, m.w_rows);
+    unsigned int* hist_s = reinterpret_cast<unsigned int*>(w + ((SD(W_ROWS, m.w_rows) + m.nconst + 1) & ~1));
 
     // ---- stage the shared model matrices with one TMA bulk copy
     if (threadIdx.x == 0) {
@@ -398,7 +443,7 @@ __global__ void __launch_bounds__(COOP_TPB) k_coop(const __grid_constant__ DevMo
     const unsigned gmask = (L == 32) ? 0xffffffffu : (((1u << L) - 1u) << ((threadIdx.x & 31) / L * L));
     // per-instance constants and persistent state rows -> shared memory
     for (int k = lane; k < m.nconst; k += L) consts_s[k] = a.consts[(int64_t)k * a.ld + inst];
-    for (int r = lane; r < m.w_rows; r += L) w[r] = a.ws[(int64_t)r * a.ld + inst];
+    for (int r = lane; r < SD(W_ROWS, m.w_rows); r += L) w[r] = a.ws[(int64_t)r * a.ld + inst];
     for (int b = lane; b < ACMEB200_HIST_BINS; b += L) hist_s[b] = 0u;
     mbar_wait(bar, 0);
     __syncwarp(gmask);
@@ -412,23 +457,23 @@ __global__ void __launch_bounds__(COOP_TPB) k_coop(const __grid_constant__ DevMo
     if (!(status & ACMEB200_STATUS_NONFINITE)) {
         for (; n < a.N; n++) {
             // ---- step!  (ACME.jl:666-715)
-            for (int k = lane; k < m.nu; k += L) g.W(m.w_u + k) = __ldg(u + n * m.nu + k);
-            for (int k = lane; k < m.nnt; k += L) g.W(m.w_zall + k) = 0.0;
+            for (int k = lane; k < SD(NU, m.nu); k += L) g.W(SD(W_U, m.w_u) + k) = __ldg(u + n * SD(NU, m.nu) + k);
+            for (int k = lane; k < SD(NN, m.nnt); k += L) g.W(SD(W_ZALL, m.w_zall) + k) = 0.0;
             g.sync();
             bool fatal = false;
-            for (int si = 0; si < m.nsub; si++) {
+            for (int si = 0; si < SD(ONE, m.nsub); si++) {
                 const DevSub& s = m.subs[si];
-                for (int i = lane; i < s.np; i += L) {
+                for (int i = lane; i < SD(NP, s.np); i += L) {
                     double acc = 0.0;
-                    for (int j = 0; j < m.nx; j++) acc = fma(g.mat(s.o_dq, s.np, i, j), g.W(m.w_x + j), acc);
-                    for (int j = 0; j < m.nu; j++) acc = fma(g.mat(s.o_eq, s.np, i, j), g.W(m.w_u + j), acc);
+                    for (int j = 0; j < SD(NX, m.nx); j++) acc = fma(g.mat(SD(O_DQ, s.o_dq), SD(NP, s.np), i, j), g.W(SD(W_X, m.w_x) + j), acc);
+                    for (int j = 0; j < SD(NU, m.nu); j++) acc = fma(g.mat(SD(O_EQ, s.o_eq), SD(NP, s.np), i, j), g.W(SD(W_U, m.w_u) + j), acc);
                     if (si > 0)
-                        for (int j = 0; j < m.nnt; j++) acc = fma(g.mat(s.o_fqprev, s.np, i, j), g.W(m.w_zall + j), acc);
-                    g.W(m.w_p + i) = acc;
+                        for (int j = 0; j < SD(NN, m.nnt); j++) acc = fma(g.mat(SD(O_FQPREV, s.o_fqprev), SD(NP, s.np), i, j), g.W(SD(W_ZALL, m.w_zall) + j), acc);
+                    g.W(SD(W_P, m.w_p) + i) = acc;
                 }
                 g.sync();
                 bool used_h;
-                const GSolveResult r = c_solve<L>(g, s, si, used_h, inst);
+                const GSolveResult r = c_solve<L, P>(g, s, si, used_h, inst);
                 if (lane == 0) {
                     st_solves++;
                     st_iters += (unsigned)r.iters;
@@ -440,7 +485,7 @@ __global__ void __launch_bounds__(COOP_TPB) k_coop(const __grid_constant__ DevMo
                 if (!r.converged) {
                     if (lane == 0 && a.first_fail[inst] < 0) a.first_fail[inst] = a.n_done + n;
                     bool fin = true;
-                    for (int i = 0; i < s.nn; i++) fin = fin && isfinite(g.W(m.w_z + i));
+                    for (int i = 0; i < SD(NN, s.nn); i++) fin = fin && isfinite(g.W(SD(W_Z, m.w_z) + i));
                     if (fin) {
                         status |= ACMEB200_STATUS_NOT_CONVERGED;
                         st_nc++;
@@ -450,35 +495,35 @@ __global__ void __launch_bounds__(COOP_TPB) k_coop(const __grid_constant__ DevMo
                         break;
                     }
                 }
-                for (int i = lane; i < s.nn; i += L) g.W(m.w_zall + s.zoff + i) = g.W(m.w_z + i);
+                for (int i = lane; i < SD(NN, s.nn); i += L) g.W(SD(W_ZALL, m.w_zall) + SD(ZERO, s.zoff) + i) = g.W(SD(W_Z, m.w_z) + i);
                 g.sync();
             }
             if (fatal) break;
-            for (int i = lane; i < m.ny; i += L) {
-                double acc = g.mat(m.o_y0, m.ny, i, 0);
-                for (int j = 0; j < m.nx; j++) acc = fma(g.mat(m.o_dy, m.ny, i, j), g.W(m.w_x + j), acc);
-                for (int j = 0; j < m.nu; j++) acc = fma(g.mat(m.o_ey, m.ny, i, j), g.W(m.w_u + j), acc);
-                for (int j = 0; j < m.nnt; j++) acc = fma(g.mat(m.o_fy, m.ny, i, j), g.W(m.w_zall + j), acc);
-                y[n * m.ny + i] = acc;
+            for (int i = lane; i < SD(NY, m.ny); i += L) {
+                double acc = g.mat(SD(O_Y0, m.o_y0), SD(NY, m.ny), i, 0);
+                for (int j = 0; j < SD(NX, m.nx); j++) acc = fma(g.mat(SD(O_DY, m.o_dy), SD(NY, m.ny), i, j), g.W(SD(W_X, m.w_x) + j), acc);
+                for (int j = 0; j < SD(NU, m.nu); j++) acc = fma(g.mat(SD(O_EY, m.o_ey), SD(NY, m.ny), i, j), g.W(SD(W_U, m.w_u) + j), acc);
+                for (int j = 0; j < SD(NN, m.nnt); j++) acc = fma(g.mat(SD(O_FY, m.o_fy), SD(NY, m.ny), i, j), g.W(SD(W_ZALL, m.w_zall) + j), acc);
+                y[n * SD(NY, m.ny) + i] = acc;
             }
-            for (int i = lane; i < m.nx; i += L) {
-                double acc = g.mat(m.o_x0, m.nx, i, 0);
-                for (int j = 0; j < m.nx; j++) acc = fma(g.mat(m.o_a, m.nx, i, j), g.W(m.w_x + j), acc);
-                for (int j = 0; j < m.nu; j++) acc = fma(g.mat(m.o_b, m.nx, i, j), g.W(m.w_u + j), acc);
-                for (int j = 0; j < m.nnt; j++) acc = fma(g.mat(m.o_c, m.nx, i, j), g.W(m.w_zall + j), acc);
-                g.W(m.w_xnew + i) = acc;
+            for (int i = lane; i < SD(NX, m.nx); i += L) {
+                double acc = g.mat(SD(O_X0, m.o_x0), SD(NX, m.nx), i, 0);
+                for (int j = 0; j < SD(NX, m.nx); j++) acc = fma(g.mat(SD(O_A, m.o_a), SD(NX, m.nx), i, j), g.W(SD(W_X, m.w_x) + j), acc);
+                for (int j = 0; j < SD(NU, m.nu); j++) acc = fma(g.mat(SD(O_B, m.o_b), SD(NX, m.nx), i, j), g.W(SD(W_U, m.w_u) + j), acc);
+                for (int j = 0; j < SD(NN, m.nnt); j++) acc = fma(g.mat(SD(O_C, m.o_c), SD(NX, m.nx), i, j), g.W(SD(W_ZALL, m.w_zall) + j), acc);
+                g.W(SD(W_XNEW, m.w_xnew) + i) = acc;
             }
             g.sync();
-            for (int i = lane; i < m.nx; i += L) g.W(m.w_x + i) = g.W(m.w_xnew + i);
+            for (int i = lane; i < SD(NX, m.nx); i += L) g.W(SD(W_X, m.w_x) + i) = g.W(SD(W_XNEW, m.w_xnew) + i);
             g.sync();
             st_samples++;
         }
     }
     if (active) {
         for (; n < a.N; n++)  // the reference throws here (ACME.jl:692); mark the rest
-            for (int i = lane; i < m.ny; i += L) y[n * m.ny + i] = NAN;
+            for (int i = lane; i < SD(NY, m.ny); i += L) y[n * SD(NY, m.ny) + i] = NAN;
         g.sync();
-        for (int r = lane; r < m.w_rows; r += L) a.ws[(int64_t)r * a.ld + inst] = w[r];
+        for (int r = lane; r < SD(W_ROWS, m.w_rows); r += L) a.ws[(int64_t)r * a.ld + inst] = w[r];
         if (lane == 0) {
             a.status[inst] = status;
             if (st_samples) atomicAdd(&a.stats->samples, st_samples);
