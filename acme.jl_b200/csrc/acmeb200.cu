@@ -454,10 +454,11 @@ static int select_kernel(acmeb200_model* m) {
     for (int i = 0; i < m->dm.nsub; i++) {
         DevSub& s = m->dm.subs[i];
         s.dyn_ps = nullptr; s.dyn_zs = nullptr; s.dyn_n = nullptr; s.dyn_cap = 0;
-        if (!m->coop_lanes || m->dm.solver != ACMEB200_SOLVER_HOMOTOPY_CACHING) continue;
+        // dynamic caches: the cooperative and the thread-per-instance kernels (each with its own layout)
+        if (!(m->coop_lanes || m->tpi) || m->dm.solver != ACMEB200_SOLVER_HOMOTOPY_CACHING || s.cache_n > 0) continue;
         size_t free_b = 0, total_b = 0;
         CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
-        int cap = 1024;
+        int cap = m->tpi ? 128 : 1024;
         while (cap > 32 && (size_t)m->B * (s.np + s.nn) * cap * 8 > free_b / 8) cap /= 2;
         void *ps = nullptr, *zs = nullptr, *nn_ = nullptr;
         CUDA_TRY(cudaMalloc(&ps, std::max<size_t>(8, (size_t)m->B * s.np * cap * 8)));

@@ -252,15 +252,16 @@ __device__ __forceinline__ void tpi_set_origin(const M& m, const double (&Cn)[di
 }
 
 // solve(::SimpleSolver, p)  (solvers.jl:207-236).  With `reorigin` the solve is preceded by
-// set_extrapolation_origin(solver, 0, init_z) (solvers.jl:183-196): that is what a fresh
-// CachingSolver does when p is nearer to its only cached point (p = 0) than to the current origin
+// set_extrapolation_origin(solver, pc, zc) (solvers.jl:183-196) for a cached solution (pc, zc):
+// that is what the CachingSolver does when a stored point is nearer to p than the current origin
 // (solvers.jl:347-371).  The origin evaluation runs as "iteration 0" of the same loop so that the
-// element laws and the LU exist once in the instruction stream.
+// element laws and the LU exist once in the instruction stream.  pc/zc are strided (SoA cache).
 template <class C, class M>
 __device__ __forceinline__ bool tpi_simple_solve(const M& m, const double (&Cn)[dim1(C::NC)], TpiState<C>& S,
                                                  const double (&p)[dim1(C::NP)], double (&z)[dim1(C::NN)],
                                                  const SolverCfg& sc, int& iters, bool reorigin = false,
-                                                 const double* iz = nullptr, int64_t iz_ld = 0) {
+                                                 const double* pc = nullptr, const double* zc = nullptr,
+                                                 int64_t cstride = 0) {
     double pfull[dim1(C::NQ)], res[dim1(C::NN)], jv[dim1(C::NJ)], J[dim1(C::NN * C::NN)];
     int piv[dim1(C::NN)];
     auto start_from_origin = [&]() {
@@ -276,8 +277,11 @@ __device__ __forceinline__ bool tpi_simple_solve(const M& m, const double (&Cn)[
         });
     };
     if (reorigin) {
-        static_for<0, C::NQ>([&](auto i) { pfull[decltype(i)::value] = m.q0[decltype(i)::value]; });  // set_p!(0)
-        static_for<0, C::NN>([&](auto i) { z[decltype(i)::value] = iz[(int64_t)decltype(i)::value * iz_ld]; });
+        double pcv[dim1(C::NP)];
+        static_for<0, C::NP>([&](auto i) { pcv[decltype(i)::value] = pc[(int64_t)decltype(i)::value * cstride]; });
+        static_for<0, C::NN>([&](auto i) { z[decltype(i)::value] = zc[(int64_t)decltype(i)::value * cstride]; });
+        tpi_set_p<C>(m, pcv, pfull);
+        static_for<0, C::NP>([&](auto i) { S.lp[decltype(i)::value] = pcv[decltype(i)::value]; });  // origin p, final below
     } else {
         start_from_origin();
     }
@@ -288,7 +292,6 @@ __device__ __forceinline__ bool tpi_simple_solve(const M& m, const double (&Cn)[
         if (iters == 0) {
             lu_reg<C::NN>(J, piv);
             tpi_update_Mx<C>(m, jv, J, piv, S.Mx);
-            static_for<0, C::NP>([&](auto i) { S.lp[decltype(i)::value] = 0.0; });
             static_for<0, C::NN>([&](auto i) { S.lz[decltype(i)::value] = z[decltype(i)::value]; });
             start_from_origin();
             continue;
@@ -310,6 +313,44 @@ __device__ __forceinline__ bool tpi_simple_solve(const M& m, const double (&Cn)[
     return converged;
 }
 
+// ---- dynamic per-instance solution cache (CachingSolver, solvers.jl:319-396), SoA layout
+// ps[(idx*NP + d)*ld + inst], zs[(idx*NN + i)*ld + inst]; entry 0 is the initial (0, init_z).
+// The nearest stored point is found by scanning all entries (the reference uses a k-d tree plus a
+// linear scan of the newest entries: the same exact nearest neighbour up to distance ties).
+template <class C>
+__device__ __forceinline__ int tpi_cache_nearest(const DevSub& c, int64_t inst, int64_t ld,
+                                                 const double (&p)[dim1(C::NP)], const double (&lp)[dim1(C::NP)],
+                                                 int& n_out) {
+    const int n = c.dyn_n[inst];
+    n_out = n;
+    double best = 0.0;
+    static_for<0, C::NP>([&](auto ii) {
+        constexpr int i = decltype(ii)::value;
+        const double d = p[i] - lp[i];
+        best = fma(d, d, best);
+    });
+    int cidx = -1;
+#pragma unroll 1
+    for (int idx = 0; idx < n; idx++) {
+        double d2 = 0.0;
+        static_for<0, C::NP>([&](auto ii) {
+            constexpr int i = decltype(ii)::value;
+            const double d = c.dyn_ps[((int64_t)idx * C::NP + i) * ld + inst] - p[i];
+            d2 = fma(d, d, d2);
+        });
+        if (d2 < best) { best = d2; cidx = idx; }
+    }
+    return cidx;
+}
+template <class C>
+__device__ __forceinline__ void tpi_cache_append(const DevSub& c, int64_t inst, int64_t ld, int n,
+                                                 const double (&p)[dim1(C::NP)], const double (&z)[dim1(C::NN)]) {
+    if (n >= c.dyn_cap) return;
+    static_for<0, C::NP>([&](auto i) { c.dyn_ps[((int64_t)n * C::NP + decltype(i)::value) * ld + inst] = p[decltype(i)::value]; });
+    static_for<0, C::NN>([&](auto i) { c.dyn_zs[((int64_t)n * C::NN + decltype(i)::value) * ld + inst] = z[decltype(i)::value]; });
+    c.dyn_n[inst] = n + 1;
+}
+
 // everything the cold paths need, spilled to local memory on purpose
 template <class C>
 struct TpiCold {
@@ -317,7 +358,7 @@ struct TpiCold {
     double Cn[dim1(C::NC)];
     double p[dim1(C::NP)];
     double z[dim1(C::NN)];
-    double initz[dim1(C::NN)];
+    int64_t inst, ld;
     int iters;
     int used_homotopy;
 };
@@ -338,16 +379,17 @@ __device__ __forceinline__ bool tpi_base_solve_cold(const M& m, TpiCold<C>& k, c
                 for (int i = 0; i < C::NP; i++) cp[i] = cache.ps[(int64_t)(idx - 1) * C::NP + i];
                 for (int i = 0; i < C::NN; i++) cz[i] = cache.zs[(int64_t)(idx - 1) * C::NN + i];
             }
-        } else {
-            double d0 = 0.0;
-            for (int i = 0; i < C::NP; i++) d0 = fma(p[i], p[i], d0);
-            if (d0 < best) {
-                take = true;
-                for (int i = 0; i < C::NP; i++) cp[i] = 0.0;
-                for (int i = 0; i < C::NN; i++) cz[i] = k.initz[i];
-            }
         }
         if (take) tpi_set_origin<C>(m, k.Cn, k.S, cp, cz, sc);
+        if (cache.cache_n == 0 && cache.dyn_cap > 0) {
+            int n;
+            const int cidx = tpi_cache_nearest<C>(cache, k.inst, k.ld, p, k.S.lp, n);
+            const bool conv = tpi_simple_solve<C>(m, k.Cn, k.S, p, k.z, sc, iters, cidx >= 0,
+                                                  cache.dyn_ps + ((int64_t)(cidx < 0 ? 0 : cidx) * C::NP) * k.ld + k.inst,
+                                                  cache.dyn_zs + ((int64_t)(cidx < 0 ? 0 : cidx) * C::NN) * k.ld + k.inst, k.ld);
+            if (conv && iters > 5) tpi_cache_append<C>(cache, k.inst, k.ld, n, p, k.z);
+            return conv;
+        }
     }
     return tpi_simple_solve<C>(m, k.Cn, k.S, p, k.z, sc, iters);
 }
@@ -511,29 +553,26 @@ __device__ __forceinline__ void tpi_output_update(const M& m, TpiState<C>& S, co
 template <class C, class M>
 __device__ __forceinline__ int tpi_step_hot(const M& m, const double (&Cn)[dim1(C::NC)], TpiState<C>& S,
                                             const double (&u)[dim1(C::NU)], double (&y)[dim1(C::NY)],
-                                            const SolverCfg& sc, const DevSub& cache, const double* iz, int64_t iz_ld) {
+                                            const SolverCfg& sc, const DevSub& cache, int64_t inst, int64_t ld) {
     constexpr int NN = C::NN, NP = C::NP;
     double zall[dim1(NN)];
     int iters = 0;
     if constexpr (NN > 0) {
         double p[dim1(NP)];
         tpi_calc_p<C>(m, S, u, p);
-        bool reorigin = false;
-        if (sc.solver == ACMEB200_SOLVER_HOMOTOPY_CACHING) {
+        int cidx = -1, n_cache = 0;
+        const bool caching = sc.solver == ACMEB200_SOLVER_HOMOTOPY_CACHING;
+        if (caching) {
             if (cache.cache_n > 0) return -1;  // frozen k-d tree: the cold path does the lookup
-            double best = 0.0, d0 = 0.0;
-            static_for<0, NP>([&](auto ii) {
-                constexpr int i = decltype(ii)::value;
-                const double d = p[i] - S.lp[i];
-                best = fma(d, d, best);
-                d0 = fma(p[i], p[i], d0);
-            });
-            reorigin = d0 < best;  // the cached (0, init_z) is the nearer start point
+            if (cache.dyn_cap > 0) cidx = tpi_cache_nearest<C>(cache, inst, ld, p, S.lp, n_cache);
         }
-        if (!tpi_simple_solve<C>(m, Cn, S, p, zall, sc, iters, reorigin, iz, iz_ld)) {
+        const int64_t e = cidx < 0 ? 0 : cidx;
+        if (!tpi_simple_solve<C>(m, Cn, S, p, zall, sc, iters, cidx >= 0, cache.dyn_ps + (e * NP) * ld + inst,
+                                 cache.dyn_zs + (e * NN) * ld + inst, ld)) {
             if (sc.solver != ACMEB200_SOLVER_SIMPLE) return -(iters + 1);
             return -(iters + 1) - (1 << 20);  // SimpleSolver only: no homotopy, the failure is final
         }
+        if (caching && iters > 5 && cache.dyn_cap > 0) tpi_cache_append<C>(cache, inst, ld, n_cache, p, zall);
     }
     tpi_output_update<C>(m, S, u, zall, y);
     return iters;
@@ -556,7 +595,9 @@ __device__ __noinline__ int tpi_step_cold(const M* mp, const double* Cn_, TpiSta
     double u[dim1(NU)], y[dim1(NY)];
     for (int i = 0; i < NU; i++) u[i] = u_[i];
     tpi_calc_p<C>(m, k.S, u, k.p);
-    for (int i = 0; i < NN; i++) { k.z[i] = 0.0; k.initz[i] = a.initz[(int64_t)i * a.ld + inst]; }
+    for (int i = 0; i < NN; i++) k.z[i] = 0.0;
+    k.inst = inst;
+    k.ld = a.ld;
     const bool final_fail = code <= -(1 << 20);
     const int failed_iters = final_fail ? (-(code + (1 << 20)) - 1) : (-code - 1);
     bool conv = false;
@@ -646,6 +687,11 @@ __global__ void __launch_bounds__(TPI_TPB, ACME_TPI_MINB) k_tpi(const __grid_con
             static_for<0, NP>([&](auto i) { p0[decltype(i)::value] = 0.0; });
             static_for<0, NN>([&](auto i) { z0[decltype(i)::value] = a.initz[(int64_t)decltype(i)::value * a.ld + inst]; });
             tpi_set_origin<C>(m, Cn, S, p0, z0, sc);
+            if (cache.dyn_cap > 0) {  // CachingSolver ctor: the cache holds (0, init_z)  (solvers.jl:327-333)
+                static_for<0, NP>([&](auto i) { cache.dyn_ps[(int64_t)decltype(i)::value * a.ld + inst] = 0.0; });
+                static_for<0, NN>([&](auto i) { cache.dyn_zs[(int64_t)decltype(i)::value * a.ld + inst] = z0[decltype(i)::value]; });
+                cache.dyn_n[inst] = 1;
+            }
         }
         store_state();
         a.status[inst] = 0;
@@ -723,7 +769,7 @@ __global__ void __launch_bounds__(TPI_TPB, ACME_TPI_MINB) k_tpi(const __grid_con
                     constexpr int q = decltype(kk)::value;
                     u[q] = shared_u ? __ldg(a.U + (int64_t)(n0 + tt) * NU + q) : in_cur[tt * NU + q];
                 });
-                code = tpi_step_hot<C>(m, Cn, S, u, y, sc, cache, a.initz + inst, a.ld);
+                code = tpi_step_hot<C>(m, Cn, S, u, y, sc, cache, inst, a.ld);
                 if (code < 0) break;
                 if (NN > 0) {
                     if (code <= 8) hist_s[(code - 1) * 32] += 1u;

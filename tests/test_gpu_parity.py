@@ -383,6 +383,30 @@ def test_dynamic_cache_learning_superover():
     assert abs(it_gpu - it_ref) < 0.25 * it_ref  # and behaves like the reference's
 
 
+def test_dynamic_cache_learning_birdie_tpi():
+    """the same learning CachingSolver in the thread-per-instance kernel (birdie, white noise)"""
+    B, N = 32, 8000
+    m = ex.birdie(vol=0.8)
+    rng = np.random.default_rng(5)
+    u = np.asfortranarray(np.clip(0.2 * rng.standard_normal((1, N, B)), -1, 1))
+    o = OracleModel(m, B, solver=HC)
+    yref = o.run(u, threads=0)
+    yexact = OracleModel(m, B, solver=H, tol=1e-13).run(u, threads=0)
+    yref2 = OracleModel(m, B, solver=H).run(u, threads=0)
+    r = BatchRunner(m, B, solver=HC)
+    assert r.kernel_name.startswith("tpi<")
+    assert_parity_within_reference_accuracy(r.run(u), yref, yexact, yref2)
+    it_gpu = r.stats()["newton_iters"] / r.stats()["solves"]
+    it_ref = o.stats()["newton_iters"] / o.stats()["solves"]
+    r.close()
+    r = BatchRunner(m, B, solver=H)
+    r.run(u)
+    it_nocache = r.stats()["newton_iters"] / r.stats()["solves"]
+    r.close()
+    assert it_gpu < 0.8 * it_nocache
+    assert abs(it_gpu - it_ref) < 0.25 * it_ref
+
+
 # ------------------------------------------------------------------ state, chunking, pointers
 @pytest.mark.parametrize("kernel", KERNELS)
 def test_state_persists_across_calls(kernel):
