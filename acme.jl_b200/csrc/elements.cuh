@@ -27,7 +27,7 @@ namespace acme {
 // trick, degree-11 minimax polynomial, exponent splice), restructured for the
 // latency-bound Newton loop: constants come from a table instead of immediate
 // moves, the polynomial is evaluated with Estrin's scheme and there is no branch.
-// Agrees with the library exp to <= 2 ulp (scratch/exp_test.py measures it).
+// Agrees with the library exp to <= 2 ulp (tools/exp_test.py measures it).
 #ifdef __CUDACC__
 __constant__ double ACME_EXPC[16] = {
     // log2(e), 2^52+2^51, -ln2_hi, -ln2_lo, then the degree-11 minimax coefficients c11..c2

@@ -67,9 +67,11 @@ extern "C" {
 #define ACMEB200_ELEM_TEST_QUAD 100
 
 /* solver selection; the reference default is HOMOTOPY_CACHING
- * (src/ACME.jl:150).  On the device the cache is a frozen, host-built k-d tree
- * (read-only lookup, src/solvers.jl:347-371); dynamic insertion
- * (src/solvers.jl:374-394) is not performed on the device. */
+ * (src/ACME.jl:150).  With HOMOTOPY_CACHING the device keeps a learning
+ * per-instance solution cache (insertion when a solve needed > 5 iterations,
+ * src/solvers.jl:374-386; nearest-start lookup, src/solvers.jl:347-371) with a
+ * fixed capacity; alternatively a frozen, host-built k-d tree can be supplied
+ * per sub-problem (acmeb200_cache), which is then used read-only instead. */
 #define ACMEB200_SOLVER_SIMPLE            0 /* SimpleSolver                          */
 #define ACMEB200_SOLVER_HOMOTOPY          1 /* HomotopySolver{SimpleSolver}          */
 #define ACMEB200_SOLVER_HOMOTOPY_CACHING  2 /* HomotopySolver{CachingSolver{Simple}} */
