@@ -521,3 +521,64 @@ def test_full_size_config3_linearity():
     assert torch.allclose(y2, 2 * y1, rtol=1e-12, atol=1e-15)
     assert torch.equal(y1[:64], y1[64:128])
     r.close()
+
+
+def test_full_size_config4_superover_batch():
+    """superover, pots as inputs, the full B = 8192 sweep (0.1 s of signal to keep the test short):
+    every instance converges, instances with identical inputs agree bit for bit wherever they sit,
+    spot instances match the oracle up to the reference's stopping-rule uncertainty."""
+    import torch
+    B, N = 8192, 4410
+    m = ex.superover()
+    dev = torch.device("cuda", 0)
+    U = torch.zeros((B, N, 4), dtype=torch.float64, device=dev)
+    U[:, :, 0] = torch.from_numpy(cases.sine(N)[0].copy()).to(dev)[None, :]
+    k = torch.arange(B, device=dev)
+    U[:, :, 1] = (((k % 128) + 0.5) / 128)[:, None]
+    U[:, :, 2] = (((k // 128) % 64 + 0.5) / 64)[:, None]
+    U[:, :, 3] = 1.0
+    U[B - 1] = U[5]
+    U[4000] = U[77]
+    r = BatchRunner(m, B, solver=HC)
+    assert r.kernel_name.startswith("coop<16") and "compile-time" in r.kernel_name
+    Y = r.run(U)
+    torch.cuda.synchronize()
+    assert torch.equal(Y[B - 1], Y[5]) and torch.equal(Y[4000], Y[77])
+    assert bool(torch.isfinite(Y).all())
+    st = r.stats()
+    assert st["samples"] == B * N and st["not_converged"] == 0 and (r.status()[0] == 0).all()
+    spots = [0, 127, 4095, 8000]
+    us = np.asfortranarray(U[spots].cpu().numpy().transpose(2, 1, 0))
+    yref = OracleModel(m, len(spots), solver=HC).run(us, threads=0)
+    yref2 = OracleModel(m, len(spots), solver=H).run(us, threads=0)
+    yexact = OracleModel(m, len(spots), solver=H, tol=1e-13).run(us, threads=0)
+    assert_parity_within_reference_accuracy(Y[spots].cpu().numpy().transpose(2, 1, 0), yref, yexact, yref2)
+    r.close()
+
+
+def test_full_size_config5_birdie_noise_chunked():
+    """birdie(vol=0.8), the full B = 32768, white noise generated on the device per time chunk
+    (the 10 s of config 5 do not fit in HBM at once): the histogram accounts for every solve,
+    all instances converge, and chunked == one-shot bit for bit (state persistence)."""
+    import torch
+    B, N = 32768, 2048
+    m = ex.birdie(vol=0.8)
+    dev = torch.device("cuda", 0)
+    g = torch.Generator(device=dev); g.manual_seed(0xACE5EED)
+    U = (0.2 * torch.randn((B, 2 * N, 1), generator=g, device=dev, dtype=torch.float64)).clamp_(-1, 1)
+    r = BatchRunner(m, B, solver=HC)
+    Y1 = r.run(U).clone()
+    st1 = r.stats()
+    assert sum(st1["iter_hist"]) == st1["solves"] == B * 2 * N and st1["not_converged"] == 0
+    assert bool(torch.isfinite(Y1).all()) and (r.status()[0] == 0).all()
+    r.reset()
+    Ya = r.run(U[:, :N].contiguous()).clone()
+    Yb = r.run(U[:, N:].contiguous())
+    assert torch.equal(torch.cat([Ya, Yb], dim=1), Y1)
+    spots = [0, 1, 32767]
+    us = np.asfortranarray(U[spots].cpu().numpy().transpose(2, 1, 0))
+    yref = OracleModel(m, 3, solver=HC).run(us, threads=0)
+    yref2 = OracleModel(m, 3, solver=H).run(us, threads=0)
+    yexact = OracleModel(m, 3, solver=H, tol=1e-13).run(us, threads=0)
+    assert_parity_within_reference_accuracy(Y1[spots].cpu().numpy().transpose(2, 1, 0), yref, yexact, yref2)
+    r.close()
