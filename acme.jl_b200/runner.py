@@ -50,6 +50,9 @@ class BatchRunner:
         self.batch_total = batch
         self.first = first
         self.batch = batch - first if count is None else count
+        self._params = desc_kw.get("params")
+        self._overrides = desc_kw.get("overrides")
+        self._has_overrides = bool(desc_kw.get("overrides"))
         self._holder = make_desc(model, batch, **desc_kw)
         h = C.c_void_p()
         check(lib().acmeb200_model_create(C.byref(self._holder.desc), first, self.batch, C.byref(h)))
@@ -200,6 +203,70 @@ class BatchRunner:
         """raw-pointer host run (used by bench.py for the end-to-end leg with pinned torch buffers)"""
         check(lib().acmeb200_run(self._h, C.c_void_p(u_ptr), ustride, C.c_void_p(y_ptr),
                                  self.model.ny * N, N, 0, None))
+
+    # ------------------------------------------------------------------ steady state (batched)
+    def steadystate(self, u=None) -> np.ndarray:
+        """Batched ``steadystate(model, u)`` (ACME.jl:474-497): the state every instance settles to
+        for a constant input ``u`` (``(nu,)`` shared or ``(nu, B)`` per instance).  The non-linear
+        part -- one Newton/homotopy solve per sub-problem with the state recursion folded into
+        ``fq``/``q0`` and tolerance 1e-15 -- runs on the device through the same C ABI: a derived
+        zero-state model whose single "sample" is that solve.  Returns x of shape (nx, B)."""
+        from .model import DiscreteModel, SubProblem
+        m = self.model
+        B = self.batch
+        if getattr(self, "_has_overrides", False) and m.subs:
+            raise NotImplementedError("steadystate with per-instance matrices of a non-linear model")
+        u = np.zeros((m.nu, B)) if u is None else np.broadcast_to(
+            np.asarray(u, dtype=np.float64).reshape(m.nu, -1), (m.nu, B)).copy()
+        ov = getattr(self, "_overrides", None) or {}
+        if not m.subs:  # linear: x = (I - a) \ (b u + x0), possibly per-instance matrices
+            a = np.asarray(ov.get("a", m.a)).reshape(m.nx, m.nx, -1)
+            b = np.asarray(ov.get("b", m.b)).reshape(m.nx, m.nu, -1)
+            x0 = np.asarray(ov.get("x0", m.x0)).reshape(m.nx, -1)
+            x = np.empty((m.nx, B))
+            for k in range(B):
+                kk = lambda arr: arr[..., k if arr.shape[-1] > 1 else 0]
+                x[:, k] = np.linalg.solve(np.eye(m.nx) - kk(a), kk(b) @ u[:, k] + kk(x0))
+            return x
+        IAinv = np.linalg.inv(np.eye(m.nx) - m.a) if m.nx else np.zeros((0, 0))
+        nnt = m.nn_total
+        steady_z = np.zeros((nnt, B))
+        zoff = 0
+        for i, s in enumerate(m.subs):
+            dqIA = s.dq @ IAinv if m.nx else s.dq
+            Eu = s.pexp @ (dqIA @ m.b + s.eq) if m.nx else s.pexp @ s.eq
+            Ez = s.pexp @ ((dqIA @ m.c if m.nx else 0.0) + s.fqprev)
+            const = s.q0 + (s.pexp @ dqIA @ m.x0 if m.nx else 0.0)
+            fq = (s.pexp @ dqIA @ m.c[:, zoff:zoff + s.nn] if m.nx else 0.0) + s.fq
+            nin = m.nu + nnt + 1
+            sub = SubProblem(nn=s.nn, nq=s.nq, np_=s.nq, dq=np.zeros((s.nq, 0)),
+                             eq=np.hstack([Eu, Ez, const.reshape(-1, 1)]), fqprev=np.zeros((s.nq, s.nn)),
+                             pexp=np.eye(s.nq), q0=np.zeros(s.nq), fq=fq, init_z=np.zeros(s.nn), elems=s.elems)
+            sm = DiscreteModel.from_matrices(a=np.zeros((0, 0)), b=np.zeros((0, nin)), c=np.zeros((0, s.nn)),
+                                             x0=np.zeros(0), dy=np.zeros((s.nn, 0)), ey=np.zeros((s.nn, nin)),
+                                             fy=np.eye(s.nn), y0=np.zeros(s.nn), subs=[sub],
+                                             solver="HomotopySolver{SimpleSolver}")
+            params = None
+            if getattr(self, "_params", None) is not None and self._params[i] is not None:
+                params = [self._params[i][:, self.first:self.first + B]]
+            r = BatchRunner(sm, B, params=params, tol=1e-15)
+            try:
+                uin = np.asfortranarray(np.vstack([u, steady_z, np.ones((1, B))]).reshape(nin, 1, B))
+                z = r.run(uin, check_status=False)[:, 0, :]
+                if (r.status()[0] != 0).any():
+                    raise RuntimeError("Failed to find steady state solution")  # ACME.jl:492
+            finally:
+                r.close()
+            steady_z[zoff:zoff + s.nn] = z
+            zoff += s.nn
+        rhs = m.b @ u + m.c @ steady_z + m.x0.reshape(-1, 1)
+        return IAinv @ rhs if m.nx else np.zeros((0, B))
+
+    def steadystate_(self, u=None) -> np.ndarray:
+        """``steadystate!``: also makes it the current state of every instance (ACME.jl:499-503)."""
+        x = self.steadystate(u)
+        self.x = x
+        return x
 
     def raise_for_status(self):
         """Re-raises the reference's failure semantics (ACME.jl:688-694)."""

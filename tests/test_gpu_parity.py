@@ -582,3 +582,28 @@ def test_full_size_config5_birdie_noise_chunked():
     yexact = OracleModel(m, 3, solver=H, tol=1e-13).run(us, threads=0)
     assert_parity_within_reference_accuracy(Y1[spots].cpu().numpy().transpose(2, 1, 0), yref, yexact, yref2)
     r.close()
+
+
+def test_batched_steadystate_on_device():
+    """steadystate / steadystate! (ACME.jl:474-503) for a batch: each instance's steady state for its
+    own DC input equals the host restatement's, and one more sample at that input keeps the state
+    (checksteady!, runtests.jl:664-671)."""
+    for m, nu in ((ex.birdie(vol=0.8), 1), (ex.superover(1.0, 1.0, 1.0), 1), (ex.diodeclipper(), 1), (ex.sallenkey(), 1)):
+        B = 5
+        udc = np.linspace(-0.2, 0.2, B).reshape(1, B)
+        r = BatchRunner(m, B, tol=1e-13)
+        xs = r.steadystate_(udc)
+        for b in range(B):
+            assert np.allclose(xs[:, b], m.steadystate(udc[:, b]), rtol=1e-9, atol=1e-12)
+        r.run(np.asfortranarray(np.repeat(udc[:, None, :], 1, axis=1)))
+        assert np.allclose(r.x, xs, rtol=1e-9, atol=1e-12)
+        r.close()
+    # parameter sweep: the swept instances get their own steady states
+    m = ex.diodeclipper()
+    P = clipper_sweep(4)
+    r = BatchRunner(m, 4, params=[P])
+    xs = r.steadystate(np.full((1, 4), 0.3))
+    for b in range(4):
+        mb = ex.diodeclipper(is1=P[0, b], η1=P[1, b], is2=P[2, b], η2=P[3, b])
+        assert np.allclose(xs[:, b], mb.steadystate([0.3]), rtol=1e-9, atol=1e-12)
+    r.close()
