@@ -255,3 +255,39 @@ def steadystate(model, u=None):
         steady_z[zoff:zoff + s.nn] = z
         zoff += s.nn
     return solveIA(model.b @ u + model.c @ steady_z + model.x0)
+
+
+def linearize(model, usteady=None):
+    """``linearize(model, usteady)`` (ACME.jl:505-550, solvers.jl:407-414): small-signal linear
+    ``DiscreteModel`` around the steady state for the constant input ``usteady``."""
+    from .model import DiscreteModel
+    usteady = np.zeros(model.nu) if usteady is None else np.array(usteady, dtype=float)
+    xsteady = steadystate(model, usteady)
+    zsteady = np.zeros(model.nn_total)
+    x0, a, b, c = model.x0.copy(), model.a.copy(), model.b.copy(), model.c.copy()
+    y0, dy, ey, fy = model.y0.copy(), model.dy.copy(), model.ey.copy(), model.fy.copy()
+    zranges, dzdps, dqlins, eqlins = [], [], [], []
+    zoff = 0
+    for idx, s in enumerate(model.subs):
+        psteady = s.dq @ xsteady + s.eq @ usteady + s.fqprev @ zsteady
+        base = _Simple(s.elems, s.fq, s.q0, s.pexp, s.nn, np.zeros(s.np_), s.init_z)
+        zsub = homotopy_solve(base, psteady)
+        base.set_origin(psteady, zsub)
+        if not base.converged():
+            raise ValueError(f"Cannot linearize because no solution found at p={psteady}")
+        dzdp = -np.linalg.solve(base.last_J, base.last_Jp)
+        zsteady[zoff:zoff + s.nn] = zsub
+        zr = slice(zoff, zoff + s.nn)
+        fqdzdps = [s.fqprev[:, zranges[n]] @ dzdps[n] for n in range(idx)]
+        dqlin = s.dq + sum((f @ d for f, d in zip(fqdzdps, dqlins)), np.zeros_like(s.dq))
+        eqlin = s.eq + sum((f @ e for f, e in zip(fqdzdps, eqlins)), np.zeros_like(s.eq))
+        zranges.append(zr); dzdps.append(dzdp); dqlins.append(dqlin); eqlins.append(eqlin)
+        x0 = x0 + c[:, zr] @ (zsub - dzdp @ psteady)
+        a = a + c[:, zr] @ dzdp @ dqlin
+        b = b + c[:, zr] @ dzdp @ eqlin
+        y0 = y0 + fy[:, zr] @ (zsub - dzdp @ psteady)
+        dy = dy + fy[:, zr] @ dzdp @ dqlin
+        ey = ey + fy[:, zr] @ dzdp @ eqlin
+        zoff += s.nn
+    return DiscreteModel.from_matrices(a=a, b=b, c=np.zeros((model.nx, 0)), x0=x0, dy=dy, ey=ey,
+                                       fy=np.zeros((model.ny, 0)), y0=y0, subs=[], solver=model.solver)

@@ -483,8 +483,6 @@ class DiscreteModel:
         """Build a model from already-derived Float64 matrices (what a Julia
         host would pass after running the reference's own derivation)."""
         m = cls(solver=solver)
-        f = lambda v, nd: np.asfortranarray(np.array(v, dtype=np.float64).reshape(
-            np.shape(v) if np.ndim(v) == nd else (-1,) * nd))
         m.a, m.b, m.c = (np.asfortranarray(np.array(v, dtype=np.float64)) for v in (a, b, c))
         m.dy, m.ey, m.fy = (np.asfortranarray(np.array(v, dtype=np.float64)) for v in (dy, ey, fy))
         m.x0 = np.array(x0, dtype=np.float64).reshape(-1)
@@ -510,6 +508,10 @@ class DiscreteModel:
     def steadystate(self, u=None):
         """ACME.jl:474-497"""
         return hostsolve.steadystate(self, u)
+
+    def linearize(self, usteady=None):
+        """ACME.jl:505-550"""
+        return hostsolve.linearize(self, usteady)
 
     def steadystate_(self, u=None):
         """``steadystate!`` (ACME.jl:499-503)"""

@@ -281,3 +281,25 @@ def test_batch_sweep_matches_single():
     for b in range(B):
         mb = ex.diodeclipper(is1=is_vals[b], is2=1.8 * is_vals[b], η1=eta_vals[b], η2=eta_vals[b])
         assert np.array_equal(run(mb, u)[0], yb[0, :, b])
+
+
+def linearization_error(model, amplitude, **kw):
+    """runtests.jl:673-682"""
+    lin = model.linearize()
+    N = 50000
+    u = (amplitude * np.sin(np.pi / 2 * np.arange(N + 1) ** 2 / N)).reshape(1, -1)
+    o = OracleModel(model, **kw); o.x = model.steadystate()
+    ol = OracleModel(lin); ol.x = lin.steadystate()
+    return np.max(np.abs(o.run(u) - ol.run(u)))
+
+
+def test_K11_linearization_bounds():
+    """runtests.jl:705, 730, 749.  The birdie/superover bounds of the reference sit at the level of
+    the Newton stopping noise (max|res| < 1e-10 times the circuit's transimpedance), so at the
+    default tolerance the restatement lands within a few 10 % of them (summation-order dependent);
+    with the tolerance tightened (set_resabstol!) the reference's bounds hold with margin."""
+    assert linearization_error(ex.diodeclipper(), 1e-3) < 1e-15
+    assert linearization_error(ex.birdie(vol=0.8), 1e-4) < 1.5e-7
+    assert linearization_error(ex.superover(1.0, 1.0, 1.0), 1e-4) < 1.5e-4
+    assert linearization_error(ex.birdie(vol=0.8), 1e-4, tol=1e-13) < 1e-7
+    assert linearization_error(ex.superover(1.0, 1.0, 1.0), 1e-4, tol=1e-13) < 1e-4
