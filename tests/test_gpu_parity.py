@@ -607,3 +607,38 @@ def test_batched_steadystate_on_device():
         mb = ex.diodeclipper(is1=P[0, b], η1=P[1, b], is2=P[2, b], η2=P[3, b])
         assert np.allclose(xs[:, b], mb.steadystate([0.3]), rtol=1e-9, atol=1e-12)
     r.close()
+
+
+@pytest.mark.parametrize("kernel", ["auto", "generic"])
+def test_odd_lengths_and_strides(kernel):
+    """odd sample counts / odd instance strides cannot use the 16-byte TMA row copies: the
+    synchronous staging path must give the same results (and a trailing partial tile, too)."""
+    m = ex.diodeclipper()
+    B = 37
+    P = clipper_sweep(B)
+    for N in (1, 7, 333, 1001):
+        u = np.asfortranarray(cases.sine(N)[:, :, None] * np.linspace(0.2, 1.2, B)[None, None, :])
+        yref = OracleModel(m, B, params=[P], solver=H).run(u, threads=0)
+        r = BatchRunner(m, B, params=[P], solver=H, kernel=kernel)
+        assert_parity(r.run(u), yref)
+        r.close()
+
+
+@pytest.mark.parametrize("kernel", ["auto", "generic"])
+def test_per_instance_matrices_nonlinear(kernel):
+    """swept R and C of the diode clipper change the linear stamps => every matrix differs per
+    instance (the PERINST variant of the thread-per-instance kernel / per-instance blobs)."""
+    B, N = 6, 2000
+    models = [ex.diodeclipper(r=1e3 * (1 + 0.3 * b), c=47e-9 * (1 + 0.2 * b)) for b in range(B)]
+    base = models[0]
+    ov = {}
+    for key in ("a", "b", "c", "x0", "dy", "ey", "fy", "y0"):
+        ov[key] = np.stack([getattr(mb, key) for mb in models], axis=-1)
+    for key in ("dq", "eq", "fqprev", "pexp", "q0", "fq"):
+        ov[key + "0"] = np.stack([getattr(mb.subs[0], key) for mb in models], axis=-1)
+    u = cases.sine(N)
+    r = BatchRunner(base, B, overrides=ov, solver=H, kernel=kernel)
+    y = r.run(u)
+    for b, mb in enumerate(models):
+        assert_parity(y[:, :, b], cpu_run(mb, u, solver=H))
+    r.close()
