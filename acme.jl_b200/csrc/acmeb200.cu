@@ -108,6 +108,42 @@ static void fill_tpi_mats(const DevModel& dm, const double* blob, TpiMats<C>& M)
     }
 }
 
+// cuTensorMapEncodeTiled, fetched through the runtime (the library does not link libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+
+// Tensor map of one f64 stream of a launch: dim0 = the `inner` contiguous values of an instance,
+// dim1 = `ninst` instances `stride` values apart, box {box_inner, 32} = one warp tile.
+// False when the stream does not meet TMA's 16-byte alignment rules (the kernel then uses its
+// synchronous path).
+static bool make_tile_map(CUtensorMap* tm, const double* base, int64_t stride, int64_t ninst, int64_t inner,
+                          int box_inner) {
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc || !base || inner <= 0 || ninst <= 0) return false;
+    if (ninst == 1 && stride < inner) stride = (inner + 1) & ~int64_t(1);  // a single row: the pitch is unused
+    if ((reinterpret_cast<uintptr_t>(base) & 15) || (stride & 1) || stride < inner || stride >= (int64_t(1) << 36)) return false;
+    if ((box_inner & 1) || box_inner > 256 || inner >= (int64_t(1) << 32) || ninst >= (int64_t(1) << 32)) return false;
+    const cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)ninst};
+    const cuuint64_t strides[1] = {(cuuint64_t)stride * 8};
+    const cuuint32_t box[2] = {(cuuint32_t)box_inner, 32};
+    const cuuint32_t estr[2] = {1, 1};
+    return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(base), dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 template <class C>
 static cudaError_t launch_tpi(const acmeb200_model* m, const RunArgs& a, cudaStream_t stream) {
     TpiMats<C> M;
@@ -116,12 +152,19 @@ static cudaError_t launch_tpi(const acmeb200_model* m, const RunArgs& a, cudaStr
     DevSub cache;
     memset(&cache, 0, sizeof cache);
     if (m->dm.nsub > 0) cache = m->dm.subs[0];
+    TpiMaps maps;
+    memset(&maps, 0, sizeof maps);
+    if (!a.init) {
+        maps.in_ok = C::NU > 0 && a.u_stride != 0 &&
+                     make_tile_map(&maps.u, a.U, a.u_stride, a.ninst, a.N * C::NU, TPI_T * C::NU);
+        maps.out_ok = C::NY > 0 && make_tile_map(&maps.y, a.Y, a.y_stride, a.ninst, a.N * C::NY, TPI_T * C::NY);
+    }
     const int64_t blocks = (a.ninst + TPI_TPB - 1) / TPI_TPB;
     const size_t smem = tpi_smem_bytes<C>();
     if (m->blob_stride)
-        k_tpi<C, true><<<(unsigned)blocks, TPI_TPB, smem, stream>>>(M, a, sc, cache);
+        k_tpi<C, true><<<(unsigned)blocks, TPI_TPB, smem, stream>>>(M, a, sc, cache, maps);
     else
-        k_tpi<C, false><<<(unsigned)blocks, TPI_TPB, smem, stream>>>(M, a, sc, cache);
+        k_tpi<C, false><<<(unsigned)blocks, TPI_TPB, smem, stream>>>(M, a, sc, cache, maps);
     return cudaGetLastError();
 }
 

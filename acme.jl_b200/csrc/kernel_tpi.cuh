@@ -20,6 +20,8 @@
 // converged solve; the start vector z0 = last_z - Mx*dp is the same up to
 // rounding.
 #pragma once
+#include <cuda.h>  // CUtensorMap (types only: the encoder is fetched through cudart)
+
 #include "devmodel.h"
 #include "elements.cuh"
 #include "kernel_generic.cuh"  // kd_nearest
@@ -473,33 +475,53 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
             : "memory");
     } while (!done);
 }
-// global -> shared bulk copy (TMA, UBLKCP in SASS), completion counted on an mbarrier
+// global -> shared bulk copy of a contiguous range (TMA, UBLKCP in SASS), completion on an mbarrier
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                  "l"(src), "r"(bytes), "r"(bar)
                  : "memory");
 }
-// shared -> global bulk copy, tracked by the thread's bulk async-group
-__device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src, uint32_t bytes) {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes)
+// One 2D tile of a (instances x samples) stream, global -> shared, through a tensor map
+// (TMA, UTMALDG in SASS); completion is counted on an mbarrier.  Out-of-range rows/columns of the
+// box are zero-filled, so partial tiles and partially filled warps need no special case.
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+        "l"(tm), "r"(c0), "r"(c1), "r"(bar)
+        : "memory");
+}
+// shared -> global tile store (UTMASTG), tracked by the issuing thread's bulk async-group;
+// the part of the box outside the tensor is not written
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, int c0, int c1, uint32_t src) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];" ::"l"(tm), "r"(c0),
+                 "r"(c1), "r"(src)
                  : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// per-warp shared memory: 2 input buffers (TMA double buffering), 1 output buffer, 2 mbarriers,
-// 8 histogram counters per lane.  Rows are padded by 16 B: TMA needs 16-byte aligned rows and the
-// pad spreads the lanes' own-row accesses over the banks.
+// Tensor maps of the launch's input and output streams (built by the host, launch_tpi):
+// rank 2, dim0 = samples*channels of one instance (contiguous), dim1 = instances, box = one
+// warp tile {TPI_T*channels, 32}.  *_ok = 0: stream not 16-byte aligned, synchronous path.
+struct alignas(64) TpiMaps {
+    CUtensorMap u, y;
+    int in_ok, out_ok;
+};
+
+// per-warp shared memory: 2 input tiles and 2 output tiles (TMA double buffering both ways;
+// dense box layout, row = instance), 8 histogram counters per lane, 2 mbarriers.
 template <class C>
 struct TpiSmem {
-    static constexpr int IROW = TPI_T * C::NU * 8 + 16;  // bytes per instance row, input
-    static constexpr int OROW = TPI_T * C::NY * 8 + 16;
-    static constexpr int IN_BYTES = 32 * IROW, OUT_BYTES = 32 * OROW;
-    static constexpr int HIST_OFF = 2 * IN_BYTES + OUT_BYTES;
+    static constexpr int IROW = TPI_T * C::NU * 8;  // bytes per instance row, input
+    static constexpr int OROW = TPI_T * C::NY * 8;
+    static constexpr int IN_BYTES = 32 * IROW, OUT_BYTES = 32 * OROW;  // multiples of 128 (TMA alignment)
+    static constexpr int OUT_OFF = 2 * IN_BYTES;
+    static constexpr int HIST_OFF = OUT_OFF + 2 * OUT_BYTES;
     static constexpr int BAR_OFF = HIST_OFF + 32 * 8 * 4;
-    static constexpr int PER_WARP = BAR_OFF + 16;
+    static constexpr int PER_WARP = (BAR_OFF + 16 + 127) / 128 * 128;
+    static_assert(IN_BYTES % 128 == 0 && OUT_BYTES % 128 == 0, "tile buffers must stay 128-byte aligned");
 };
 
 template <class C>
@@ -639,7 +661,8 @@ __device__ __noinline__ int tpi_step_cold(const M* mp, const double* Cn_, TpiSta
 
 template <class C, bool PERINST>
 __global__ void __launch_bounds__(TPI_TPB, ACME_TPI_MINB) k_tpi(const __grid_constant__ TpiMats<C> Msh, const RunArgs a,
-                                                 const __grid_constant__ SolverCfg sc, const __grid_constant__ DevSub cache) {
+                                                 const __grid_constant__ SolverCfg sc, const __grid_constant__ DevSub cache,
+                                                 const __grid_constant__ TpiMaps maps) {
     constexpr int NX = C::NX, NU = C::NU, NY = C::NY, NN = C::NN, NP = C::NP;
     constexpr int T = TPI_T;
     using SM = TpiSmem<C>;
@@ -707,57 +730,55 @@ __global__ void __launch_bounds__(TPI_TPB, ACME_TPI_MINB) k_tpi(const __grid_con
     bool dead = !active || (a.status[inst] & ACMEB200_STATUS_NONFINITE);
     int dead_at = dead ? 0 : -1;  // sample index (this call) at which the instance halted, -1 = alive
     const bool shared_u = (a.u_stride == 0) || NU == 0;
-    // TMA needs 16-byte aligned row segments: even strides, 16-byte aligned bases
-    const bool tma_in = !shared_u && ((reinterpret_cast<uintptr_t>(a.U) & 15) == 0) && ((a.u_stride & 1) == 0) &&
-                        ((T * NU) % 2 == 0);
-    const bool tma_out = NY > 0 && ((reinterpret_cast<uintptr_t>(a.Y) & 15) == 0) && ((a.y_stride & 1) == 0) &&
-                         ((T * NY) % 2 == 0);
+    const bool tma_in = !shared_u && maps.in_ok;   // the host checked alignment and built the maps
+    const bool tma_out = NY > 0 && maps.out_ok;
     const int t32 = (int)t;                 // launch-local instance (ninst < 2^31)
+    const int w0 = t32 - lane;              // first instance of this warp = tile row coordinate
+    const bool wact = w0 < (int)a.ninst;    // warp has at least one instance (lane 0 is active)
     const int n_samp = (int)a.N;            // N < 2^27 (checked by the host)
-    const int n_tiles = (n_samp + T - 1) / T, n_full = n_samp / T;
+    const int n_tiles = (n_samp + T - 1) / T;
     auto urow = [&](int n) { return a.U + (shared_u ? 0 : (int64_t)t32 * a.u_stride) + (int64_t)n * NU; };
     auto yrow = [&](int n) { return a.Y + (int64_t)t32 * a.y_stride + (int64_t)n * NY; };
-    unsigned char* const in_base = wsm + lane * SM::IROW;  // + buf*IN_BYTES
-    unsigned char* const out_row = wsm + 2 * SM::IN_BYTES + lane * SM::OROW;
     unsigned int* const hist_s = reinterpret_cast<unsigned int*>(wsm + SM::HIST_OFF) + lane;  // [bin*32]
     const uint32_t bar0 = smem_u32(wsm + SM::BAR_OFF);  // bar1 = bar0 + 8
 
 #pragma unroll
     for (int b = 0; b < 8; b++) hist_s[b * 32] = 0u;
     if (tma_in) {
-        if (lane == 0) { mbar_init(bar0, 32); mbar_init(bar0 + 8, 32); }
+        if (lane == 0) { mbar_init(bar0, 1); mbar_init(bar0 + 8, 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         __syncwarp();
         // prologue: tiles 0 and 1 in flight
-        for (int k = 0; k < 2 && k < n_full; k++) {
-            if (active) {
-                mbar_arrive_expect_tx(bar0 + 8 * k, T * NU * 8);
-                bulk_g2s(smem_u32(in_base + k * SM::IN_BYTES), urow(k * T), T * NU * 8, bar0 + 8 * k);
-            } else {
-                mbar_arrive(bar0 + 8 * k);
+        if (lane == 0 && wact)
+            for (int k = 0; k < 2 && k < n_tiles; k++) {
+                mbar_arrive_expect_tx(bar0 + 8 * k, SM::IN_BYTES);
+                tma_load_2d(smem_u32(wsm + k * SM::IN_BYTES), &maps.u, k * T * NU, w0, bar0 + 8 * k);
             }
-        }
     }
 
 #pragma unroll 1
     for (int k = 0; k < n_tiles; k++) {
         const int n0 = k * T;
         const int cnt = (n_samp - n0) < T ? (n_samp - n0) : T;
-        const bool full = cnt == T;
         const int buf = k & 1;
-        double* const in_cur = reinterpret_cast<double*>(in_base + buf * SM::IN_BYTES);
+        unsigned char* const in_tile = wsm + buf * SM::IN_BYTES;
+        unsigned char* const out_tile = wsm + SM::OUT_OFF + buf * SM::OUT_BYTES;
+        double* const in_cur = reinterpret_cast<double*>(in_tile + lane * SM::IROW);
+        double* const yrow_s = reinterpret_cast<double*>(out_tile + lane * SM::OROW);
         if (!shared_u) {
-            if (tma_in && full) {
-                mbar_wait(bar0 + 8 * buf, (uint32_t)((k >> 1) & 1));
+            if (tma_in) {
+                if (wact) mbar_wait(bar0 + 8 * buf, (uint32_t)((k >> 1) & 1));
             } else {
-                // synchronous fallback (unaligned streams, trailing partial tile): own-row loads
+                // synchronous path (unaligned streams): own-row loads
                 __syncwarp();
                 if (active)
                     for (int c = 0; c < cnt * NU; c++) in_cur[c] = __ldcs(urow(n0) + c);
             }
         }
-        if (tma_out) bulk_wait_read0();  // the previous tile's bulk store has drained this lane's row
-        double* const yrow_s = reinterpret_cast<double*>(out_row);
+        if (tma_out && k >= 2) {  // the store of tile k-2 has drained this output buffer
+            if (lane == 0) bulk_wait_read1();
+            __syncwarp();
+        }
         int code = 0;
         int tt = 0;
         while (tt < cnt && !dead) {
@@ -794,27 +815,28 @@ __global__ void __launch_bounds__(TPI_TPB, ACME_TPI_MINB) k_tpi(const __grid_con
         }
         for (; tt < cnt; tt++)  // halted instance: the reference throws (ACME.jl:692); mark the rest
             static_for<0, NY>([&](auto kk) { yrow_s[tt * NY + decltype(kk)::value] = NAN; });
-        // ---- output tile
-        if (NY > 0 && active) {
-            if (tma_out && full) {
-                fence_async_smem();
-                bulk_s2g(yrow(n0), smem_u32(out_row), T * NY * 8);
-                bulk_commit();
-            } else {
+        // ---- output tile: one TMA store per warp (rows of inactive lanes and the columns past N
+        //      lie outside the tensor and are clipped), or own-row stores
+        if (NY > 0) {
+            if (tma_out) fence_async_smem();  // generic-proxy writes -> visible to the async proxy
+            else if (active)
                 for (int c = 0; c < cnt * NY; c++) __stcs(yrow(n0) + c, yrow_s[c]);
-            }
         }
-        // ---- refill this input buffer with tile k+2
-        if (tma_in && k + 2 < n_full) {
-            if (active) {
-                mbar_arrive_expect_tx(bar0 + 8 * buf, T * NU * 8);
-                bulk_g2s(smem_u32(in_cur), urow((k + 2) * T), T * NU * 8, bar0 + 8 * buf);
-            } else {
-                mbar_arrive(bar0 + 8 * buf);
+        if (tma_in || tma_out) __syncwarp();  // all lanes are done with in_tile / have written out_tile
+        if (lane == 0 && wact) {
+            if (tma_out) {
+                tma_store_2d(&maps.y, n0 * NY, w0, smem_u32(out_tile));
+                bulk_commit();
+            }
+            // ---- refill this input buffer with tile k+2
+            if (tma_in && k + 2 < n_tiles) {
+                mbar_arrive_expect_tx(bar0 + 8 * buf, SM::IN_BYTES);
+                tma_load_2d(smem_u32(in_tile), &maps.u, (k + 2) * T * NU, w0, bar0 + 8 * buf);
             }
         }
     }
-    if (tma_out) bulk_wait_all();
+    if (tma_out && lane == 0) bulk_wait_all();
+    __syncwarp();
 
     if (active) store_state();
     // warp-reduce the counters, one set of atomics per warp
