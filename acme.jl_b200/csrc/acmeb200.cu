@@ -17,15 +17,11 @@
 #include "../../include/acmeb200.h"
 #include "devmodel.h"
 #include "elements.cuh"
+#define ACME_GENERIC_KERNEL_TU
 #include "kernel_generic.cuh"
-#include "kernel_tpi.cuh"
-#include "kernel_coop.cuh"
+#include "hostmodel.h"
 
 using namespace acme;
-
-// compile-time shapes of the cooperative kernel (BASELINE config 4: examples/superover.jl with the
-// three potentiometers as inputs: nx 11, nu 4, ny 1, nn 13, nq 29, np 11, 8 elements, 23 jv entries)
-using CoopSuperover = CoopStatic<11, 4, 1, 13, 29, 11, 8, 23>;
 
 
 // ------------------------------------------------------------------ errors
@@ -49,170 +45,6 @@ static int fail(int code, const char* fmt, ...) {
 
 extern "C" const char* acmeb200_last_error(void) { return g_err.c_str(); }
 extern "C" int acmeb200_abi_version(void) { return ACMEB200_ABI_VERSION; }
-
-// ------------------------------------------------------------------ model object
-struct TpiEntry;
-
-struct acmeb200_model {
-    DevModel dm;
-    int64_t B = 0;
-    int device = 0;
-    // device arrays
-    double* d_blob = nullptr;
-    int64_t blob_stride = 0;
-    double* d_consts = nullptr;
-    double* d_initz = nullptr;
-    double* d_ws = nullptr;      // state/workspace of the selected kernel
-    int64_t ws_rows = 0;
-    uint32_t* d_status = nullptr;
-    long long* d_first_fail = nullptr;
-    DevStats* d_stats = nullptr;
-    std::vector<void*> d_cache;  // device copies of the frozen caches
-    std::vector<void*> d_dyn;    // dynamic per-instance caches of the cooperative kernel
-    // host copies needed to (re)build kernel parameters
-    std::vector<double> h_blob;  // blob of instance 0 (or the shared blob)
-    const TpiEntry* tpi = nullptr;
-    int coop_lanes = 0;  // 0: not the cooperative kernel
-    int coop_static = 0; // 1: CoopSuperover compile-time shape
-    bool rows_ok = true;
-    bool has_cache = false;
-    int max_nn = 0, max_nelem = 0;
-    int kernel_mode = 0;
-    std::string kernel_name;
-    int64_t launches = 0;
-    int64_t n_done = 0;
-    // pinned staging for host-pointer runs
-    double* h_stage[2] = {nullptr, nullptr};
-    double* d_stage_u[2] = {nullptr, nullptr};
-    double* d_stage_y[2] = {nullptr, nullptr};
-    size_t stage_u_bytes = 0, stage_y_bytes = 0, hstage_bytes = 0;
-    cudaStream_t copy_streams[2] = {nullptr, nullptr};
-    cudaStream_t compute_stream = nullptr;
-    cudaEvent_t ev[2] = {nullptr, nullptr};
-    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_k[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
-};
-
-// ------------------------------------------------------------------ specialised kernels registry
-template <class C>
-static void fill_tpi_mats(const DevModel& dm, const double* blob, TpiMats<C>& M) {
-    memset(&M, 0, sizeof M);
-    auto cp = [&](double* dst, int off, int n) { for (int i = 0; i < n; i++) dst[i] = blob[off + i]; };
-    cp(M.a, dm.o_a, C::NX * C::NX); cp(M.b, dm.o_b, C::NX * C::NU); cp(M.c, dm.o_c, C::NX * C::NN);
-    cp(M.x0, dm.o_x0, C::NX);
-    cp(M.dy, dm.o_dy, C::NY * C::NX); cp(M.ey, dm.o_ey, C::NY * C::NU); cp(M.fy, dm.o_fy, C::NY * C::NN);
-    cp(M.y0, dm.o_y0, C::NY);
-    if (C::NN > 0) {
-        const DevSub& s = dm.subs[0];
-        cp(M.dq, s.o_dq, C::NP * C::NX); cp(M.eq, s.o_eq, C::NP * C::NU);
-        cp(M.pexp, s.o_pexp, C::NQ * C::NP); cp(M.q0, s.o_q0, C::NQ); cp(M.fq, s.o_fq, C::NQ * C::NN);
-    }
-}
-
-// cuTensorMapEncodeTiled, fetched through the runtime (the library does not link libcuda)
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static EncodeTiledFn encode_tiled_fn() {
-    static EncodeTiledFn fn = [] {
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
-            q != cudaDriverEntryPointSuccess)
-            p = nullptr;
-        return reinterpret_cast<EncodeTiledFn>(p);
-    }();
-    return fn;
-}
-
-// Tensor map of one f64 stream of a launch: dim0 = the `inner` contiguous values of an instance,
-// dim1 = `ninst` instances `stride` values apart, box {box_inner, 32} = one warp tile.
-// False when the stream does not meet TMA's 16-byte alignment rules (the kernel then uses its
-// synchronous path).
-static bool make_tile_map(CUtensorMap* tm, const double* base, int64_t stride, int64_t ninst, int64_t inner,
-                          int box_inner) {
-    EncodeTiledFn enc = encode_tiled_fn();
-    if (!enc || !base || inner <= 0 || ninst <= 0) return false;
-    if (ninst == 1 && stride < inner) stride = (inner + 1) & ~int64_t(1);  // a single row: the pitch is unused
-    if ((reinterpret_cast<uintptr_t>(base) & 15) || (stride & 1) || stride < inner || stride >= (int64_t(1) << 36)) return false;
-    if ((box_inner & 1) || box_inner > 256 || inner >= (int64_t(1) << 32) || ninst >= (int64_t(1) << 32)) return false;
-    const cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)ninst};
-    const cuuint64_t strides[1] = {(cuuint64_t)stride * 8};
-    const cuuint32_t box[2] = {(cuuint32_t)box_inner, 32};
-    const cuuint32_t estr[2] = {1, 1};
-    return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(base), dims, strides, box, estr,
-               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
-               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-}
-
-template <class C>
-static cudaError_t launch_tpi(const acmeb200_model* m, const RunArgs& a, cudaStream_t stream) {
-    TpiMats<C> M;
-    fill_tpi_mats<C>(m->dm, m->h_blob.data(), M);
-    SolverCfg sc{m->dm.tol, m->dm.maxiter, m->dm.solver, make_exp_table()};
-    DevSub cache;
-    memset(&cache, 0, sizeof cache);
-    if (m->dm.nsub > 0) cache = m->dm.subs[0];
-    TpiMaps maps;
-    memset(&maps, 0, sizeof maps);
-    if (!a.init) {
-        maps.in_ok = C::NU > 0 && a.u_stride != 0 &&
-                     make_tile_map(&maps.u, a.U, a.u_stride, a.ninst, a.N * C::NU, TPI_T * C::NU);
-        maps.out_ok = C::NY > 0 && make_tile_map(&maps.y, a.Y, a.y_stride, a.ninst, a.N * C::NY, TPI_T * C::NY);
-    }
-    const int64_t blocks = (a.ninst + TPI_TPB - 1) / TPI_TPB;
-    const size_t smem = tpi_smem_bytes<C>();
-    if (m->blob_stride)
-        k_tpi<C, true><<<(unsigned)blocks, TPI_TPB, smem, stream>>>(M, a, sc, cache, maps);
-    else
-        k_tpi<C, false><<<(unsigned)blocks, TPI_TPB, smem, stream>>>(M, a, sc, cache, maps);
-    return cudaGetLastError();
-}
-
-struct TpiEntry {
-    const char* name;
-    int nx, nu, ny, np, ne;
-    const int* kinds;
-    int state_rows;
-    cudaError_t (*launch)(const acmeb200_model*, const RunArgs&, cudaStream_t);
-};
-
-template <class C>
-static TpiEntry make_entry(const char* name) {
-    return TpiEntry{name, C::NX, C::NU, C::NY, C::NP, C::NE, C::kinds, C::S_ROWS, &launch_tpi<C>};
-}
-
-// shapes of the BASELINE circuits (SURVEY.md section 8 size table) + small test circuits
-using CfgDiodeClipper = TpiCfg<1, 1, 1, 1, Diode, Diode>;  // examples/diodeclipper.jl
-using CfgSallenKey = TpiCfg<2, 1, 1, 0>;                   // examples/sallenkey.jl (linear)
-using CfgBirdieFixed = TpiCfg<3, 1, 1, 2, Bjt>;            // examples/birdie.jl, vol baked in
-using CfgBirdieVol = TpiCfg<3, 2, 1, 3, Bjt, Pot>;         // examples/birdie.jl, vol as input
-
-static const std::vector<TpiEntry>& tpi_registry() {
-    static const std::vector<TpiEntry> reg = {
-        make_entry<CfgDiodeClipper>("tpi<diodeclipper nx1 nu1 ny1 np1 [diode,diode]>"),
-        make_entry<CfgSallenKey>("tpi<linear nx2 nu1 ny1>"),
-        make_entry<CfgBirdieFixed>("tpi<birdie nx3 nu1 ny1 np2 [bjt]>"),
-        make_entry<CfgBirdieVol>("tpi<birdie nx3 nu2 ny1 np3 [bjt,pot]>"),
-    };
-    return reg;
-}
-
-static const TpiEntry* find_tpi(const DevModel& dm) {
-    if (dm.nsub > 1) return nullptr;
-    for (const TpiEntry& e : tpi_registry()) {
-        if (e.nx != dm.nx || e.nu != dm.nu || e.ny != dm.ny) continue;
-        if (dm.nsub == 0) {
-            if (e.ne == 0) return &e;
-            continue;
-        }
-        const DevSub& s = dm.subs[0];
-        if (e.ne != s.nelem || e.np != s.np) continue;
-        bool same = true;
-        for (int k = 0; k < e.ne; k++) same = same && dm.elems[s.elem0 + k].kind == e.kinds[k];
-        if (same) return &e;
-    }
-    return nullptr;
-}
 
 // ------------------------------------------------------------------ creation
 static void prep_consts(int kind, const double* P, double* C) {
@@ -457,36 +289,29 @@ extern "C" int acmeb200_model_create(const acmeb200_model_desc* d, int64_t first
     return ACMEB200_OK;
 }
 
-// picks the kernel, (re)allocates its state and initialises it
-static int coop_lanes_for(const acmeb200_model* m) {
-    if (m->blob_stride != 0 || m->has_cache || m->dm.nsub == 0 || m->max_nn > MAX_ROWS || !m->rows_ok) return 0;
-    const int need = std::max(m->max_nn, m->max_nelem);
-    int lanes = need <= 8 ? 8 : (need <= 16 ? 16 : 32);
-    // small batches are latency-bound: one instance per warp avoids the two groups of a warp
-    // serialising when their Newton iteration counts differ, and doubles the warps in flight
-    if (m->B * lanes < (int64_t)148 * 32 * 24) lanes = std::min(32, lanes * 2);
-    size_t smem = lanes == 8 ? coop_smem_bytes<8>(m->dm) : lanes == 16 ? coop_smem_bytes<16>(m->dm) : coop_smem_bytes<32>(m->dm);
-    while (smem > 200 * 1024 && lanes < 32) {  // fewer groups per CTA
-        lanes *= 2;
-        smem = lanes == 16 ? coop_smem_bytes<16>(m->dm) : coop_smem_bytes<32>(m->dm);
-    }
-    return smem <= 200 * 1024 ? lanes : 0;
-}
-
 static int select_kernel(acmeb200_model* m) {
     m->tpi = nullptr;
     m->coop_lanes = 0;
+    m->rows = 0;
     if (m->kernel_mode == 0) m->tpi = find_tpi(m->dm);
-    if (!m->tpi && m->kernel_mode != 1) {
+    if (!m->tpi && (m->kernel_mode == 0 || m->kernel_mode == 3)) {
+        // one warp per instance, LU rows in registers: compile-time shapes only
+        if (m->blob_stride == 0 && !m->has_cache && m->rows_ok && rows_matches(m->dm)) m->rows = 1;
+        if (m->kernel_mode == 3 && !m->rows)
+            return fail(ACMEB200_EUNSUPPORTED, "the rows-in-registers kernel has no instantiation for this model shape");
+    }
+    if (!m->tpi && !m->rows && m->kernel_mode != 1) {
         const int lanes = coop_lanes_for(m);
         // automatic choice: large non-linear systems profit from lanes sharing one instance
         if (lanes && (m->kernel_mode == 2 || m->max_nn >= 4)) m->coop_lanes = lanes;
-        m->coop_static = (m->coop_lanes >= 16 && CoopSuperover::matches(m->dm)) ? 1 : 0;
+        m->coop_static = (m->coop_lanes >= 16 && coop_static_matches(m->dm)) ? 1 : 0;
         if (m->kernel_mode == 2 && !m->coop_lanes)
             return fail(ACMEB200_EUNSUPPORTED, "the cooperative kernel needs shared matrices, no frozen cache and nn <= %d", MAX_ROWS);
     }
     m->ws_rows = m->tpi ? m->tpi->state_rows : m->dm.w_rows;
     if (m->tpi) m->kernel_name = m->tpi->name;
+    else if (m->rows) m->kernel_name = std::string("rows<warp per instance, LU rows in registers, compile-time dims [superover]") +
+                                       (m->dm.solver == ACMEB200_SOLVER_HOMOTOPY_CACHING ? ", dynamic solution cache>" : ">");
     else if (m->coop_lanes) m->kernel_name = "coop<" + std::to_string(m->coop_lanes) + " lanes per instance, " +
                                             (m->coop_static ? "compile-time dims [superover]" : "runtime dims") + ", state in shared memory" +
                                             (m->dm.solver == ACMEB200_SOLVER_HOMOTOPY_CACHING ? ", dynamic solution cache>" : ">");
@@ -498,7 +323,7 @@ static int select_kernel(acmeb200_model* m) {
         DevSub& s = m->dm.subs[i];
         s.dyn_ps = nullptr; s.dyn_zs = nullptr; s.dyn_n = nullptr; s.dyn_cap = 0;
         // dynamic caches: the cooperative and the thread-per-instance kernels (each with its own layout)
-        if (!(m->coop_lanes || m->tpi) || m->dm.solver != ACMEB200_SOLVER_HOMOTOPY_CACHING || s.cache_n > 0) continue;
+        if (!(m->coop_lanes || m->rows || m->tpi) || m->dm.solver != ACMEB200_SOLVER_HOMOTOPY_CACHING || s.cache_n > 0) continue;
         size_t free_b = 0, total_b = 0;
         CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
         int cap = m->tpi ? 128 : 1024;
@@ -528,32 +353,11 @@ static RunArgs base_args(acmeb200_model* m) {
     return a;
 }
 
-template <int L, class P>
-static cudaError_t launch_coop(const acmeb200_model* m, const RunArgs& a, cudaStream_t stream) {
-    const size_t smem = coop_smem_bytes<L>(m->dm);
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(k_coop<L, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
-    constexpr int GPC = COOP_TPB / L;
-    k_coop<L, P><<<(unsigned)((a.ninst + GPC - 1) / GPC), COOP_TPB, smem, stream>>>(m->dm, a);
-    return cudaGetLastError();
-}
-
 static cudaError_t launch(acmeb200_model* m, const RunArgs& a, cudaStream_t stream) {
     m->launches++;
     if (m->tpi) return m->tpi->launch(m, a, stream);
-    if (m->coop_lanes && !a.init) {  // the generic kernel initialises the (shared) state layout
-        if (m->coop_static == 1) {
-            if (m->coop_lanes == 16) return launch_coop<16, CoopSuperover>(m, a, stream);
-            return launch_coop<32, CoopSuperover>(m, a, stream);
-        }
-        if (m->coop_lanes == 8) return launch_coop<8, CoopDyn>(m, a, stream);
-        if (m->coop_lanes == 16) return launch_coop<16, CoopDyn>(m, a, stream);
-        return launch_coop<32, CoopDyn>(m, a, stream);
-    }
+    if (m->rows && !a.init) return launch_rows_kernel(m, a, stream);  // the generic kernel initialises the (shared) state layout
+    if (m->coop_lanes && !a.init) return launch_coop_kernel(m, a, stream);
     const int tpb = 128;
     k_generic<<<(unsigned)((a.ninst + tpb - 1) / tpb), tpb, 0, stream>>>(m->dm, a);
     return cudaGetLastError();
@@ -577,7 +381,7 @@ extern "C" int acmeb200_reset(acmeb200_model* m) {
 
 extern "C" int acmeb200_set_kernel(acmeb200_model* m, int32_t mode) {
     if (!m) return fail(ACMEB200_EINVAL, "null model");
-    if (mode < 0 || mode > 2) return fail(ACMEB200_EINVAL, "kernel mode must be 0 (auto), 1 (generic) or 2 (cooperative)");
+    if (mode < 0 || mode > 3) return fail(ACMEB200_EINVAL, "kernel mode must be 0 (auto), 1 (generic), 2 (cooperative) or 3 (rows in registers)");
     CUDA_TRY(cudaSetDevice(m->device));
     m->kernel_mode = mode;
     return select_kernel(m);

@@ -29,7 +29,7 @@ namespace acme {
 // moves, the polynomial is evaluated with Estrin's scheme and there is no branch.
 // Agrees with the library exp to <= 2 ulp (tools/exp_test.py measures it).
 #ifdef __CUDACC__
-__constant__ double ACME_EXPC[16] = {
+static __constant__ double ACME_EXPC[16] = {
     // log2(e), 2^52+2^51, -ln2_hi, -ln2_lo, then the degree-11 minimax coefficients c11..c2
     0x1.71547652b82fep+0,
     0x1.8000000000000p+52,

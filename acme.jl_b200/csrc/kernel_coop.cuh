@@ -21,7 +21,7 @@
 #include "devmodel.h"
 #include "elements.cuh"
 #include "kernel_generic.cuh"
-#include "kernel_tpi.cuh"  // TMA / mbarrier helpers
+#include "tma.cuh"
 
 namespace acme {
 

@@ -336,6 +336,7 @@ struct LocalStats {
     unsigned long long samples = 0, solves = 0, iters = 0, homotopy = 0, notconv = 0;
 };
 
+#ifdef ACME_GENERIC_KERNEL_TU  // the kernel itself is compiled into one translation unit (acmeb200.cu)
 __global__ void __launch_bounds__(128) k_generic(const __grid_constant__ DevModel m, const RunArgs a) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= a.ninst) return;
@@ -441,5 +442,7 @@ __global__ void __launch_bounds__(128) k_generic(const __grid_constant__ DevMode
     for (int b = 0; b < 8; b++)
         if (hist_lo[b]) atomicAdd(&a.stats->iter_hist[b], (unsigned long long)hist_lo[b]);
 }
+
+#endif  // ACME_GENERIC_KERNEL_TU
 
 }  // namespace acme

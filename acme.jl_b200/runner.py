@@ -61,8 +61,10 @@ class BatchRunner:
             check(lib().acmeb200_set_kernel(self._h, 1))
         elif kernel == "coop":
             check(lib().acmeb200_set_kernel(self._h, 2))
+        elif kernel == "rows":
+            check(lib().acmeb200_set_kernel(self._h, 3))
         elif kernel != "auto":
-            raise ValueError("kernel must be 'auto', 'generic' or 'coop'")
+            raise ValueError("kernel must be 'auto', 'generic', 'coop' or 'rows'")
 
     def close(self):
         if getattr(self, "_h", None):

@@ -188,7 +188,8 @@ int acmeb200_get_status(acmeb200_model *m, uint32_t *status_host, int64_t *first
 int acmeb200_get_stats(acmeb200_model *m, acmeb200_stats *out);
 
 /* kernel selection: 0 = automatic, 1 = force the generic thread-per-instance
- * kernel, 2 = force the cooperative (lanes-per-instance) kernel; solver state is reset */
+ * kernel, 2 = force the cooperative (lanes-per-instance) kernel, 3 = force the
+ * warp-per-instance kernel with the LU rows in registers; solver state is reset */
 int acmeb200_set_kernel(acmeb200_model *m, int32_t mode);
 const char *acmeb200_kernel_name(const acmeb200_model *m);
 /* number of kernels launched by this model since creation */
