@@ -20,7 +20,7 @@ import cases
 
 pytestmark = pytest.mark.gpu
 
-KERNELS = ["auto", "generic", "coop"]
+KERNELS = ["auto", "generic", "coop", "rows"]
 H = "HomotopySolver{SimpleSolver}"
 HC = "HomotopySolver{CachingSolver{SimpleSolver}}"
 
@@ -60,9 +60,22 @@ def coop_ok(model, **kw):
     return len(model.subs) > 0 and not kw.get("overrides") and not kw.get("caches")
 
 
-def gpu_run(model, u, kernel="auto", **kw):
+def rows_ok(model, **kw):
+    """the rows-in-registers kernel is instantiated for compile-time shapes: superover with the
+    three potentiometers as inputs (BASELINE config 4)"""
+    return (coop_ok(model, **kw) and len(model.subs) == 1 and
+            (model.nx, model.nu, model.ny, model.subs[0].nn, model.subs[0].nq, model.subs[0].np_) == (11, 4, 1, 13, 29, 11))
+
+
+def skip_unless_applicable(kernel, model, **kw):
     if kernel == "coop" and not coop_ok(model, **kw):
         pytest.skip("cooperative kernel not applicable")
+    if kernel == "rows" and not rows_ok(model, **kw):
+        pytest.skip("rows-in-registers kernel has no instantiation for this shape")
+
+
+def gpu_run(model, u, kernel="auto", **kw):
+    skip_unless_applicable(kernel, model, **kw)
     r = BatchRunner(model, 1, kernel=kernel, **kw)
     try:
         return r.run(np.asarray(u, dtype=float))[:, :, 0]
@@ -116,8 +129,7 @@ EXAMPLES = {
 def test_examples_match_oracle(name, kernel):
     mk, mu = EXAMPLES[name]
     m = mk()
-    if kernel == "coop" and not coop_ok(m):
-        pytest.skip("cooperative kernel not applicable")
+    skip_unless_applicable(kernel, m)
     n = 4410 if "superover" not in name else 1000
     u = mu(n)
     yref = cpu_run(m, u, solver=H)
@@ -152,6 +164,7 @@ def test_K3_homotopy(kernel):
     rng = np.random.default_rng(3)
     for _ in range(5):
         m = cases.test_quad_model()
+        skip_unless_applicable(kernel, m)
         r = BatchRunner(m, 1, kernel=kernel)
         r.run(np.array([[-0.5 + rng.random()]]))
         assert r.status()[0][0] == 0
@@ -279,6 +292,7 @@ def test_config2_diodeclipper_sweep(kernel):
     m = ex.diodeclipper()
     P = clipper_sweep(B)
     u = cases.sine(N)
+    skip_unless_applicable(kernel, m)
     yref = OracleModel(m, B, params=[P], solver=H).run(u, threads=0)
     r = BatchRunner(m, B, params=[P], solver=H, kernel=kernel)
     y = r.run(u)                       # one shared input row
@@ -326,7 +340,7 @@ def test_config4_superover_pots_as_inputs(kernel):
     yref = OracleModel(m, B, solver=H).run(u, threads=0)
     r = BatchRunner(m, B, solver=H, kernel=kernel)
     if kernel == "auto":
-        assert r.kernel_name.startswith("coop<")
+        assert r.kernel_name.startswith("rows<")
     assert_parity(r.run(u), yref)
     r.close()
 
@@ -412,6 +426,7 @@ def test_dynamic_cache_learning_birdie_tpi():
 def test_state_persists_across_calls(kernel):
     """ACME.jl:561-562: model state survives run! calls -> chunked == one shot"""
     m = ex.birdie(vol=0.8)
+    skip_unless_applicable(kernel, m)
     u = cases.sine(3000)
     r = BatchRunner(m, 3, kernel=kernel, solver=H)
     y1 = r.run(u)
@@ -422,6 +437,55 @@ def test_state_persists_across_calls(kernel):
     r.x = x
     assert np.array_equal(r.x, x)
     r.close()
+
+
+def superover_inputs(B, N):
+    u = np.zeros((4, N, B), order="F")
+    u[0] = cases.sine(N)[0][:, None]
+    u[1] = ((np.arange(B) * 5 % 16 + 0.5) / 16)[None, :]
+    u[2] = ((np.arange(B) * 3 % 8 + 0.5) / 8)[None, :]
+    u[3] = 1.0
+    return u
+
+
+@pytest.mark.parametrize("solver", [H, HC])
+def test_rows_kernel_state_persists_and_matches_coop(solver):
+    """the rows-in-registers kernel keeps its extrapolation origin in the generic layout between
+    calls (rows at their pivoted positions + ipiv): chunked == one shot, bit for bit, and the
+    result equals the cooperative kernel's (same arithmetic, different data movement)"""
+    B, N = 5, 1800
+    m = ex.superover()
+    u = superover_inputs(B, N)
+    r = BatchRunner(m, B, kernel="rows", solver=solver)
+    assert r.kernel_name.startswith("rows<")
+    y1 = r.run(u)
+    st1 = r.stats()
+    r.reset()
+    y2 = np.concatenate([r.run(np.asfortranarray(u[:, :700])), r.run(np.asfortranarray(u[:, 700:701])),
+                         r.run(np.asfortranarray(u[:, 701:]))], axis=1)
+    assert np.array_equal(y1, y2)
+    r.close()
+    rc = BatchRunner(m, B, kernel="coop", solver=solver)
+    yc = rc.run(u)
+    stc = rc.stats()
+    rc.close()
+    assert np.array_equal(y1, yc)
+    assert st1["iter_hist"] == stc["iter_hist"] and st1["homotopy_solves"] == stc["homotopy_solves"]
+
+
+def test_rows_kernel_small_and_ragged_batches():
+    """1 instance, and a batch that does not fill the last CTA of the 4-warp variant"""
+    m = ex.superover()
+    for B in (1, 2371):
+        N = 400 if B > 1 else 1500
+        u = superover_inputs(B, N)
+        r = BatchRunner(m, B, kernel="rows", solver=H)
+        y = r.run(u)
+        idx = [0] if B == 1 else [0, 1, 1185, 2370]
+        yref = OracleModel(m, len(idx), solver=H).run(np.asfortranarray(u[:, :, idx]), threads=0)
+        assert_parity(y[:, :, idx], yref)
+        assert r.stats()["samples"] == B * N
+        r.close()
 
 
 def test_run_bang_updates_model_state():
@@ -540,7 +604,7 @@ def test_full_size_config4_superover_batch():
     U[B - 1] = U[5]
     U[4000] = U[77]
     r = BatchRunner(m, B, solver=HC)
-    assert r.kernel_name.startswith("coop<16") and "compile-time" in r.kernel_name
+    assert r.kernel_name.startswith("rows<") and "compile-time" in r.kernel_name
     Y = r.run(U)
     torch.cuda.synchronize()
     assert torch.equal(Y[B - 1], Y[5]) and torch.equal(Y[4000], Y[77])
