@@ -157,3 +157,17 @@ def test_quad_model(p0=0.0, z0=1.0):
     return DiscreteModel.from_matrices(a=np.zeros((0, 0)), b=np.zeros((0, 1)), c=np.zeros((0, 1)), x0=np.zeros(0),
                                        dy=np.zeros((1, 0)), ey=np.zeros((1, 1)), fy=np.ones((1, 1)), y0=np.zeros(1),
                                        subs=[sub], solver="HomotopySolver{SimpleSolver}")
+
+
+def golden():
+    """golden vectors the reference holds for the run! path (tests/golden/make_golden.py extracts them
+    from the reference's doctests and test suite; the JSON is committed because the GPU box has no
+    /root/reference)"""
+    import json
+    import os
+    return json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_vectors.json")))
+
+
+def assert_printed_equal(got, want, digits=6):
+    """compare like the doctest does: the value printed with `digits` significant digits"""
+    assert f"{got:.{digits}g}" == f"{want:.{digits}g}", (got, want)

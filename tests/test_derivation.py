@@ -137,3 +137,30 @@ def test_steadystate_ladder():
     """docs/src/ug.md:148-174"""
     m = A.DiscreteModel(cases.rc_ladder(), 1 / 44100)
     assert np.allclose(m.steadystate_(), np.zeros(20))
+
+
+def test_K10_pins_from_golden_fixture():
+    """every np/nn pin of test/runtests.jl, as extracted into tests/golden/reference_vectors.json
+    (line number -> value), against the host-side derivation"""
+    pins = {(p["line"], p["what"]): p["value"] for p in cases.golden()["K10_dimension_pins"]}
+    simp = A.DiscreteModel(ex.superover_circuit(1.0, 1.0, 1.0, vb_source=True), 1 / 44100)
+    simp_in = A.DiscreteModel(ex.superover_circuit(vb_source=True), 1 / 44100)
+    three = A.DiscreteModel(cases.three_diodes(), 1)
+    three_nd = A.DiscreteModel(cases.three_diodes(), 1, decompose_nonlinearity=False)
+    ours = {
+        (699, "np"): ex.diodeclipper().subs[0].np_, (724, "np"): ex.birdie(vol=0.8).subs[0].np_,
+        (734, "np"): ex.birdie().subs[0].np_, (744, "np"): ex.superover(1.0, 1.0, 1.0).subs[0].np_,
+        (757, "np"): simp.subs[0].np_, (758, "np"): simp.subs[1].np_, (759, "np"): simp.subs[2].np_,
+        (768, "np"): A.DiscreteModel(ex.superover_circuit(1.0, 1.0, 1.0, vb_source=True), 1 / 44100,
+                                     decompose_nonlinearity=False).subs[0].np_,
+        (777, "np"): ex.superover().subs[0].np_,
+        (788, "np"): simp_in.subs[0].np_, (789, "np"): simp_in.subs[1].np_, (790, "np"): simp_in.subs[2].np_,
+        (791, "np"): simp_in.subs[3].np_,
+        (283, "nn"): three_nd.subs[0].nn, (289, "nn"): three.subs[0].nn, (290, "nn"): three.subs[1].nn,
+    }
+    checked = 0
+    for key, val in ours.items():
+        assert key in pins, key
+        assert pins[key] == val, (key, pins[key], val)
+        checked += 1
+    assert checked == len(ours) >= 16
