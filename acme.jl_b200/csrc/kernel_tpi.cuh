@@ -441,7 +441,18 @@ __device__ __noinline__ bool tpi_cold_solve(const M* mp, TpiCold<C>* kp, const S
 #ifndef ACME_TPI_T
 #define ACME_TPI_T 8
 #endif
+#ifndef ACME_TPI_STAGES
+#define ACME_TPI_STAGES 2
+#endif
+#ifndef ACME_TPI_OSTAGES
+#define ACME_TPI_OSTAGES 2
+#endif
 constexpr int TPI_T = ACME_TPI_T;      // samples per staged tile
+constexpr int TPI_STAGES = ACME_TPI_STAGES;  // input tiles in flight per warp (power of two): the linear
+                                             // kernel needs ~50 KB of loads in flight per SM to cover HBM latency
+constexpr int TPI_OSTAGES = ACME_TPI_OSTAGES;  // output tiles per warp (1 or 2)
+static_assert((TPI_STAGES & (TPI_STAGES - 1)) == 0 && TPI_STAGES >= 2, "stages: power of two");
+static_assert(TPI_OSTAGES == 1 || TPI_OSTAGES == 2, "output stages");
 constexpr int TPI_TPB = ACME_TPI_TPB;  // threads per block (2 warps): small CTAs balance 148 SMs
 
 // Tensor maps of the launch's input and output streams (built by the host, launch_tpi):
@@ -454,16 +465,32 @@ struct alignas(64) TpiMaps {
 
 // per-warp shared memory: 2 input tiles and 2 output tiles (TMA double buffering both ways;
 // dense box layout, row = instance), 8 histogram counters per lane, 2 mbarriers.
+// TMA swizzle of a tile whose rows are `row_bytes` long: 16-byte chunks of a row are XOR-permuted
+// with the row index so that the lanes of a warp -- each reading ITS row at the same column --
+// spread over the shared-memory banks (dense 64-byte rows read column-wise are a 16-way bank
+// conflict).  mask m: byte address bits [4, 4+log2(m+1)) ^= bits [7, ...)  (CU_TENSOR_MAP_SWIZZLE_32B/64B/128B).
+__host__ __device__ constexpr int tpi_swizzle_mask(int row_bytes) {
+    return row_bytes == 128 ? 7 : (row_bytes == 64 ? 3 : (row_bytes == 32 ? 1 : 0));
+}
+
+// per-warp shared memory: TPI_STAGES input tiles and 2 output tiles (TMA multi-buffering;
+// box layout, row = instance, swizzled), 8 histogram counters per lane, one mbarrier per input stage.
 template <class C>
 struct TpiSmem {
     static constexpr int IROW = TPI_T * C::NU * 8;  // bytes per instance row, input
     static constexpr int OROW = TPI_T * C::NY * 8;
-    static constexpr int IN_BYTES = 32 * IROW, OUT_BYTES = 32 * OROW;  // multiples of 128 (TMA alignment)
-    static constexpr int OUT_OFF = 2 * IN_BYTES;
-    static constexpr int HIST_OFF = OUT_OFF + 2 * OUT_BYTES;
+    static constexpr int ISW = tpi_swizzle_mask(IROW), OSW = tpi_swizzle_mask(OROW);
+    static constexpr int IN_TX = 32 * IROW;  // bytes one TMA tile load delivers
+    static constexpr int IN_BYTES = (32 * IROW + 1023) / 1024 * 1024, OUT_BYTES = (32 * OROW + 1023) / 1024 * 1024;
+    static constexpr int OUT_OFF = TPI_STAGES * IN_BYTES;
+    static constexpr int HIST_OFF = OUT_OFF + TPI_OSTAGES * OUT_BYTES;
     static constexpr int BAR_OFF = HIST_OFF + 32 * 8 * 4;
-    static constexpr int PER_WARP = (BAR_OFF + 16 + 127) / 128 * 128;
-    static_assert(IN_BYTES % 128 == 0 && OUT_BYTES % 128 == 0, "tile buffers must stay 128-byte aligned");
+    static constexpr int PER_WARP = (BAR_OFF + 8 * TPI_STAGES + 1023) / 1024 * 1024;  // swizzled tiles want 1024-byte alignment
+    // Byte offset of (row, byte o within the row) inside a tile = row*ROW + (o ^ xor_term(row)):
+    // swizzled rows are at most 128 bytes long, so address bits >= 7 depend on the row alone and
+    // the XOR term is a per-lane constant (computed once, outside the sample loop).
+    __device__ static __forceinline__ int in_xor(int row) { return (((row * IROW) >> 7) & ISW) << 4; }
+    __device__ static __forceinline__ int out_xor(int row) { return (((row * OROW) >> 7) & OSW) << 4; }
 };
 
 template <class C>
@@ -608,7 +635,7 @@ __global__ void __launch_bounds__(TPI_TPB, ACME_TPI_MINB) k_tpi(const __grid_con
     constexpr int NX = C::NX, NU = C::NU, NY = C::NY, NN = C::NN, NP = C::NP;
     constexpr int T = TPI_T;
     using SM = TpiSmem<C>;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned char* wsm = smem_raw + (size_t)warp * SM::PER_WARP;
 
@@ -683,17 +710,19 @@ __global__ void __launch_bounds__(TPI_TPB, ACME_TPI_MINB) k_tpi(const __grid_con
     auto yrow = [&](int n) { return a.Y + (int64_t)t32 * a.y_stride + (int64_t)n * NY; };
     unsigned int* const hist_s = reinterpret_cast<unsigned int*>(wsm + SM::HIST_OFF) + lane;  // [bin*32]
     const uint32_t bar0 = smem_u32(wsm + SM::BAR_OFF);  // bar1 = bar0 + 8
+    const int ixr = SM::in_xor(lane), oxr = SM::out_xor(lane);  // swizzle terms of this lane's rows
 
 #pragma unroll
     for (int b = 0; b < 8; b++) hist_s[b * 32] = 0u;
     if (tma_in) {
-        if (lane == 0) { mbar_init(bar0, 1); mbar_init(bar0 + 8, 1); }
+        if (lane == 0)
+            for (int st_ = 0; st_ < TPI_STAGES; st_++) mbar_init(bar0 + 8 * st_, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         __syncwarp();
-        // prologue: tiles 0 and 1 in flight
+        // prologue: the first TPI_STAGES tiles in flight
         if (lane == 0 && wact)
-            for (int k = 0; k < 2 && k < n_tiles; k++) {
-                mbar_arrive_expect_tx(bar0 + 8 * k, SM::IN_BYTES);
+            for (int k = 0; k < TPI_STAGES && k < n_tiles; k++) {
+                mbar_arrive_expect_tx(bar0 + 8 * k, SM::IN_TX);
                 tma_load_2d(smem_u32(wsm + k * SM::IN_BYTES), &maps.u, k * T * NU, w0, bar0 + 8 * k);
             }
     }
@@ -702,67 +731,104 @@ __global__ void __launch_bounds__(TPI_TPB, ACME_TPI_MINB) k_tpi(const __grid_con
     for (int k = 0; k < n_tiles; k++) {
         const int n0 = k * T;
         const int cnt = (n_samp - n0) < T ? (n_samp - n0) : T;
-        const int buf = k & 1;
+        const int buf = k & (TPI_STAGES - 1);
         unsigned char* const in_tile = wsm + buf * SM::IN_BYTES;
-        unsigned char* const out_tile = wsm + SM::OUT_OFF + buf * SM::OUT_BYTES;
-        double* const in_cur = reinterpret_cast<double*>(in_tile + lane * SM::IROW);
-        double* const yrow_s = reinterpret_cast<double*>(out_tile + lane * SM::OROW);
+        unsigned char* const out_tile = wsm + SM::OUT_OFF + (k & (TPI_OSTAGES - 1)) * SM::OUT_BYTES;
+        unsigned char* const in_row = in_tile + lane * SM::IROW;
+        unsigned char* const out_row = out_tile + lane * SM::OROW;
+        auto in_at = [&](int c) -> double& { return *reinterpret_cast<double*>(in_row + ((c * 8) ^ ixr)); };
+        auto out_at = [&](int c) -> double& { return *reinterpret_cast<double*>(out_row + ((c * 8) ^ oxr)); };
         if (!shared_u) {
             if (tma_in) {
-                if (wact) mbar_wait(bar0 + 8 * buf, (uint32_t)((k >> 1) & 1));
+                if (wact) mbar_wait(bar0 + 8 * buf, (uint32_t)((k / TPI_STAGES) & 1));
             } else {
                 // synchronous path (unaligned streams): own-row loads
                 __syncwarp();
                 if (active)
-                    for (int c = 0; c < cnt * NU; c++) in_cur[c] = __ldcs(urow(n0) + c);
+                    for (int c = 0; c < cnt * NU; c++) in_at(c) = __ldcs(urow(n0) + c);
             }
         }
-        if (tma_out && k >= 2) {  // the store of tile k-2 has drained this output buffer
-            if (lane == 0) bulk_wait_read1();
+        if (tma_out && k >= TPI_OSTAGES) {  // the store of tile k-TPI_OSTAGES has drained this output buffer
+            if (lane == 0) { if (TPI_OSTAGES == 2) bulk_wait_read1(); else bulk_wait_read0(); }
             __syncwarp();
         }
-        int code = 0;
         int tt = 0;
-        while (tt < cnt && !dead) {
-            // hot loop: no calls, no cold-path state
-#pragma unroll 1
-            for (; tt < cnt; tt++) {
-                double u[dim1(NU)], y[dim1(NY)];
-                static_for<0, NU>([&](auto kk) {
-                    constexpr int q = decltype(kk)::value;
-                    u[q] = shared_u ? __ldg(a.U + (int64_t)(n0 + tt) * NU + q) : in_cur[tt * NU + q];
-                });
-                code = tpi_step_hot<C>(m, Cn, S, u, y, sc, cache, inst, a.ld);
-                if (code < 0) break;
-                if (NN > 0) {
-                    if (code <= 8) hist_s[(code - 1) * 32] += 1u;
-                    else atomicAdd(&a.stats->iter_hist[(code > ACMEB200_HIST_BINS ? ACMEB200_HIST_BINS : code) - 1], 1ull),
-                         atomicAdd(&a.stats->newton_iters, (unsigned long long)code);
+        if constexpr (NN == 0 && (SM::IROW % 16 == 0) && (SM::OROW % 16 == 0)) {
+            // ---- linear model: the whole tile row through registers.  128-bit loads/stores of the
+            //      swizzled rows are bank-conflict free; the per-sample work is a handful of DFMAs
+            //      (ACME.jl:699-714 with nn = 0), so this path is what makes the kernel HBM-bound.
+            if (!dead) {
+                double ub[dim1(T * NU)], yb[dim1(T * NY)];
+                if (shared_u) {
+                    static_for<0, T * NU>([&](auto cc) {
+                        constexpr int c = decltype(cc)::value;
+                        ub[c] = c < cnt * NU ? __ldg(a.U + (int64_t)n0 * NU + c) : 0.0;
+                    });
+                } else {
+                    static_for<0, SM::IROW / 16>([&](auto cc) {
+                        constexpr int c = decltype(cc)::value;
+                        const double2 v = *reinterpret_cast<const double2*>(in_row + ((c * 16) ^ ixr));
+                        ub[2 * c] = v.x;
+                        ub[2 * c + 1] = v.y;
+                    });
                 }
-                static_for<0, NY>([&](auto kk) { yrow_s[tt * NY + decltype(kk)::value] = y[decltype(kk)::value]; });
-            }
-            if (tt < cnt) {
-                // this lane's sample tt needs the cold path
-                double u[dim1(NU)], y[dim1(NY)];
-                static_for<0, NU>([&](auto kk) {
-                    constexpr int q = decltype(kk)::value;
-                    u[q] = shared_u ? __ldg(a.U + (int64_t)(n0 + tt) * NU + q) : in_cur[tt * NU + q];
+                static_for<0, T>([&](auto tc) {
+                    constexpr int ti = decltype(tc)::value;
+                    double u[dim1(NU)], y[dim1(NY)], znone[1] = {0.0};
+                    static_for<0, NU>([&](auto kk) { u[decltype(kk)::value] = ub[ti * NU + decltype(kk)::value]; });
+                    static_for<0, NY>([&](auto kk) { y[decltype(kk)::value] = 0.0; });
+                    if (ti < cnt) tpi_output_update<C>(m, S, u, znone, y);  // warp-uniform: only the last tile is short
+                    static_for<0, NY>([&](auto kk) { yb[ti * NY + decltype(kk)::value] = y[decltype(kk)::value]; });
                 });
-                const int it = tpi_step_cold<C>(&m, Cn, &S, u, y, &sc, &cache, &a, inst, n0 + tt, code);
-                if (it < 0) { dead = true; dead_at = n0 + tt; break; }
-                if (it >= 1 && it <= 8) hist_s[(it - 1) * 32] += 1u;
-                static_for<0, NY>([&](auto kk) { yrow_s[tt * NY + decltype(kk)::value] = y[decltype(kk)::value]; });
-                tt++;
+                static_for<0, SM::OROW / 16>([&](auto cc) {
+                    constexpr int c = decltype(cc)::value;
+                    *reinterpret_cast<double2*>(out_row + ((c * 16) ^ oxr)) = make_double2(yb[2 * c], yb[2 * c + 1]);
+                });
+                tt = cnt;
+            }
+        } else {
+            int code = 0;
+            while (tt < cnt && !dead) {
+                // hot loop: no calls, no cold-path state
+    #pragma unroll 1
+                for (; tt < cnt; tt++) {
+                    double u[dim1(NU)], y[dim1(NY)];
+                    static_for<0, NU>([&](auto kk) {
+                        constexpr int q = decltype(kk)::value;
+                        u[q] = shared_u ? __ldg(a.U + (int64_t)(n0 + tt) * NU + q) : in_at(tt * NU + q);
+                    });
+                    code = tpi_step_hot<C>(m, Cn, S, u, y, sc, cache, inst, a.ld);
+                    if (code < 0) break;
+                    if (NN > 0) {
+                        if (code <= 8) hist_s[(code - 1) * 32] += 1u;
+                        else atomicAdd(&a.stats->iter_hist[(code > ACMEB200_HIST_BINS ? ACMEB200_HIST_BINS : code) - 1], 1ull),
+                             atomicAdd(&a.stats->newton_iters, (unsigned long long)code);
+                    }
+                    static_for<0, NY>([&](auto kk) { out_at(tt * NY + decltype(kk)::value) = y[decltype(kk)::value]; });
+                }
+                if (tt < cnt) {
+                    // this lane's sample tt needs the cold path
+                    double u[dim1(NU)], y[dim1(NY)];
+                    static_for<0, NU>([&](auto kk) {
+                        constexpr int q = decltype(kk)::value;
+                        u[q] = shared_u ? __ldg(a.U + (int64_t)(n0 + tt) * NU + q) : in_at(tt * NU + q);
+                    });
+                    const int it = tpi_step_cold<C>(&m, Cn, &S, u, y, &sc, &cache, &a, inst, n0 + tt, code);
+                    if (it < 0) { dead = true; dead_at = n0 + tt; break; }
+                    if (it >= 1 && it <= 8) hist_s[(it - 1) * 32] += 1u;
+                    static_for<0, NY>([&](auto kk) { out_at(tt * NY + decltype(kk)::value) = y[decltype(kk)::value]; });
+                    tt++;
+                }
             }
         }
         for (; tt < cnt; tt++)  // halted instance: the reference throws (ACME.jl:692); mark the rest
-            static_for<0, NY>([&](auto kk) { yrow_s[tt * NY + decltype(kk)::value] = NAN; });
+            static_for<0, NY>([&](auto kk) { out_at(tt * NY + decltype(kk)::value) = NAN; });
         // ---- output tile: one TMA store per warp (rows of inactive lanes and the columns past N
         //      lie outside the tensor and are clipped), or own-row stores
         if (NY > 0) {
             if (tma_out) fence_async_smem();  // generic-proxy writes -> visible to the async proxy
             else if (active)
-                for (int c = 0; c < cnt * NY; c++) __stcs(yrow(n0) + c, yrow_s[c]);
+                for (int c = 0; c < cnt * NY; c++) __stcs(yrow(n0) + c, out_at(c));
         }
         if (tma_in || tma_out) __syncwarp();  // all lanes are done with in_tile / have written out_tile
         if (lane == 0 && wact) {
@@ -770,10 +836,10 @@ __global__ void __launch_bounds__(TPI_TPB, ACME_TPI_MINB) k_tpi(const __grid_con
                 tma_store_2d(&maps.y, n0 * NY, w0, smem_u32(out_tile));
                 bulk_commit();
             }
-            // ---- refill this input buffer with tile k+2
-            if (tma_in && k + 2 < n_tiles) {
-                mbar_arrive_expect_tx(bar0 + 8 * buf, SM::IN_BYTES);
-                tma_load_2d(smem_u32(in_tile), &maps.u, (k + 2) * T * NU, w0, bar0 + 8 * buf);
+            // ---- refill this input buffer with tile k+TPI_STAGES
+            if (tma_in && k + TPI_STAGES < n_tiles) {
+                mbar_arrive_expect_tx(bar0 + 8 * buf, SM::IN_TX);
+                tma_load_2d(smem_u32(in_tile), &maps.u, (k + TPI_STAGES) * T * NU, w0, bar0 + 8 * buf);
             }
         }
     }

@@ -58,8 +58,12 @@ static bool make_tile_map(CUtensorMap* tm, const double* base, int64_t stride, i
     const cuuint64_t strides[1] = {(cuuint64_t)stride * 8};
     const cuuint32_t box[2] = {(cuuint32_t)box_inner, 32};
     const cuuint32_t estr[2] = {1, 1};
+    // the swizzle the kernel's tile accessors assume (tpi_swizzle_mask): by the row length of the box
+    const int mask = tpi_swizzle_mask(box_inner * 8);
+    const CUtensorMapSwizzle sw = mask == 7 ? CU_TENSOR_MAP_SWIZZLE_128B : mask == 3 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                  : mask == 1 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE;
     return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(base), dims, strides, box, estr,
-               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
@@ -80,6 +84,15 @@ static cudaError_t launch_tpi(const acmeb200_model* m, const RunArgs& a, cudaStr
     }
     const int64_t blocks = (a.ninst + TPI_TPB - 1) / TPI_TPB;
     const size_t smem = tpi_smem_bytes<C>();
+    if (smem > 48 * 1024) {  // long tiles: opt in to the large dynamic shared memory carve-out
+        static bool attr_set = false;
+        if (!attr_set) {
+            cudaError_t e = cudaFuncSetAttribute(k_tpi<C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(k_tpi<C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            attr_set = true;
+        }
+    }
     if (m->blob_stride)
         k_tpi<C, true><<<(unsigned)blocks, TPI_TPB, smem, stream>>>(M, a, sc, cache, maps);
     else
