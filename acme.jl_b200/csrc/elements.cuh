@@ -22,60 +22,61 @@ namespace acme {
 
 #define ACME_DI __host__ __device__ __forceinline__
 
-// exp(double) for the element laws.  Same reduction and coefficients as the CUDA
-// math library's exp (Cody-Waite reduction by ln2 with the 2^52+2^51 rounding
-// trick, degree-11 minimax polynomial, exponent splice), restructured for the
-// latency-bound Newton loop: constants come from a table instead of immediate
-// moves, the polynomial is evaluated with Estrin's scheme and there is no branch.
-// Agrees with the library exp to <= 2 ulp (tools/exp_test.py measures it).
+// exp(double) for the element laws, built for the latency-bound Newton loops: the FP64 pipe issues
+// one warp instruction per 2 cycles and a dependent DFMA costs 8, so both the NUMBER of FP64
+// instructions and the depth of their chain matter.  Table-driven:
+//   x = (64 m + j) ln2/64 + r,  |r| <= ln2/128,   exp(x) = 2^m * 2^(j/64) * (1 + r + r^2/2 + ... + r^5/120)
+// Cody-Waite reduction (2^52+2^51 rounding trick, ln2/64 split in two for the FMA), a 64-entry table
+// of correctly rounded 2^(j/64) read through the read-only path (512 B, L1-resident), a degree-5
+// polynomial in Estrin form (3 dependent levels; truncation error r^6/720 < 0.17 ulp), exponent
+// splice in two steps (exact for normal results, one rounding for subnormal ones, overflow to +Inf
+// in the multiply), no branch.  12 FP64 instructions instead of the library's ~30, <= 1 ulp from
+// the correctly rounded result (tools/exp_test.py measures the distance to the library exp).
 #ifdef __CUDACC__
-static __constant__ double ACME_EXPC[16] = {
-    // log2(e), 2^52+2^51, -ln2_hi, -ln2_lo, then the degree-11 minimax coefficients c11..c2
-    0x1.71547652b82fep+0,
-    0x1.8000000000000p+52,
-    -0x1.62e42fefa39efp-1,
-    -0x1.abc9e3b39803fp-56,
-    0x1.ade1569ce2bdfp-26,
-    0x1.28af3fca213eap-22,
-    0x1.71dee62401315p-19,
-    0x1.a01997c89eb71p-16,
-    0x1.a01a014761f65p-13,
-    0x1.6c16c1852b7afp-10,
-    0x1.1111111122322p-7,
-    0x1.55555555502a1p-5,
-    0x1.5555555555511p-3,
-    0x1.000000000000bp-1,
-    1.0, 0.0};
+static __device__ const double ACME_EXP_T64[64] = {
+    0x1.0000000000000p+0, 0x1.02c9a3e778061p+0, 0x1.059b0d3158574p+0, 0x1.0874518759bc8p+0,
+    0x1.0b5586cf9890fp+0, 0x1.0e3ec32d3d1a2p+0, 0x1.11301d0125b51p+0, 0x1.1429aaea92de0p+0,
+    0x1.172b83c7d517bp+0, 0x1.1a35beb6fcb75p+0, 0x1.1d4873168b9aap+0, 0x1.2063b88628cd6p+0,
+    0x1.2387a6e756238p+0, 0x1.26b4565e27cddp+0, 0x1.29e9df51fdee1p+0, 0x1.2d285a6e4030bp+0,
+    0x1.306fe0a31b715p+0, 0x1.33c08b26416ffp+0, 0x1.371a7373aa9cbp+0, 0x1.3a7db34e59ff7p+0,
+    0x1.3dea64c123422p+0, 0x1.4160a21f72e2ap+0, 0x1.44e086061892dp+0, 0x1.486a2b5c13cd0p+0,
+    0x1.4bfdad5362a27p+0, 0x1.4f9b2769d2ca7p+0, 0x1.5342b569d4f82p+0, 0x1.56f4736b527dap+0,
+    0x1.5ab07dd485429p+0, 0x1.5e76f15ad2148p+0, 0x1.6247eb03a5585p+0, 0x1.6623882552225p+0,
+    0x1.6a09e667f3bcdp+0, 0x1.6dfb23c651a2fp+0, 0x1.71f75e8ec5f74p+0, 0x1.75feb564267c9p+0,
+    0x1.7a11473eb0187p+0, 0x1.7e2f336cf4e62p+0, 0x1.82589994cce13p+0, 0x1.868d99b4492edp+0,
+    0x1.8ace5422aa0dbp+0, 0x1.8f1ae99157736p+0, 0x1.93737b0cdc5e5p+0, 0x1.97d829fde4e50p+0,
+    0x1.9c49182a3f090p+0, 0x1.a0c667b5de565p+0, 0x1.a5503b23e255dp+0, 0x1.a9e6b5579fdbfp+0,
+    0x1.ae89f995ad3adp+0, 0x1.b33a2b84f15fbp+0, 0x1.b7f76f2fb5e47p+0, 0x1.bcc1e904bc1d2p+0,
+    0x1.c199bdd85529cp+0, 0x1.c67f12e57d14bp+0, 0x1.cb720dcef9069p+0, 0x1.d072d4a07897cp+0,
+    0x1.d5818dcfba487p+0, 0x1.da9e603db3285p+0, 0x1.dfc97337b9b5fp+0, 0x1.e502ee78b3ff6p+0,
+    0x1.ea4afa2a490dap+0, 0x1.efa1bee615a27p+0, 0x1.f50765b6e4540p+0, 0x1.fa7c1819e90d8p+0};
+// 64/ln2, 2^52+2^51, -ln2_hi/64, -ln2_lo/64, 1/2, 1/6, 1/24, 1/120
+#define ACME_EXP_CONSTANTS                                                                              \
+    0x1.71547652b82fep+6, 0x1.8000000000000p+52, -0x1.62e42fefa39efp-7, -0x1.abc9e3b39803fp-62, 0x1.0p-1, \
+        0x1.5555555555555p-3, 0x1.5555555555555p-5, 0x1.1111111111111p-7, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0
+static __constant__ double ACME_EXPC[16] = {ACME_EXP_CONSTANTS};
 
 __device__ __forceinline__ double acme_exp(double x, const double* __restrict__ K) {
     // Branch-free so that the exps of neighbouring elements interleave in one basic block
-    // (a dependent DFMA costs 8 cycles on B200; the FP64 pipe accepts one every 2 cycles).
     double t = fma(x, K[0], K[1]);
-    const int i = __double2loint(t);
+    const int i = __double2loint(t);  // 64 m + j
     t = t - K[1];
     double r = fma(t, K[2], x);
     r = fma(t, K[3], r);
-    // degree-11 polynomial, Estrin scheme: 4 dependent levels instead of Horner's 11
+    const double tj = __ldg(&ACME_EXP_T64[i & 63]);
     const double r2 = r * r;
-    const double p01 = fma(r, 1.0, 1.0);       // c0 + c1 r
-    const double p23 = fma(K[12], r, K[13]);   // c2 + c3 r
-    const double p45 = fma(K[10], r, K[11]);   // c4 + c5 r
-    const double p67 = fma(K[8], r, K[9]);     // c6 + c7 r
-    const double p89 = fma(K[6], r, K[7]);     // c8 + c9 r
-    const double pab = fma(K[4], r, K[5]);     // c10 + c11 r
-    const double r4 = r2 * r2;
-    const double q0 = fma(p23, r2, p01);
-    const double q1 = fma(p67, r2, p45);
-    const double q2 = fma(pab, r2, p89);
-    const double r8 = r4 * r4;
-    const double s0 = fma(q1, r4, q0);
-    const double p = fma(q2, r8, s0);
-    // scale by 2^i in two steps (i = k + (i - k)): exact for normal results, one rounding for
+    const double a = fma(r, K[5], K[4]);  // 1/2 + r/6
+    const double b = fma(r, K[7], K[6]);  // 1/24 + r/120
+    const double q = fma(b, r2, a);
+    const double p = fma(q, r2, r);       // exp(r) - 1
+    const double v = fma(tj, p, tj);      // 2^(j/64) exp(r), in [1, 2)
+    // scale by 2^m in two steps (m = k + (m - k)): exact for normal results, one rounding for
     // subnormal ones, overflow to +Inf happens naturally in the multiply
-    const int k = i >> 1;
-    const double a = __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
-    const double sc = __hiloint2double((0x3ff + (i - k)) << 20, 0);
-    double res = a * sc;
+    const int m = i >> 6;
+    const int k = m >> 1;
+    const double s1 = __hiloint2double(__double2hiint(v) + (k << 20), __double2loint(v));
+    const double sc = __hiloint2double((0x3ff + (m - k)) << 20, 0);
+    double res = s1 * sc;
     const int hx = __double2hiint(x) & 0x7fffffff;
     // |x| >= 745 (or NaN): i is meaningless; exp is +Inf / 0 / NaN there
     // +Inf for large x, NaN for NaN (NaN*Inf), 0 for very negative x -- no branch
@@ -94,10 +95,8 @@ __device__ __forceinline__ double acme_exp(double x, const double* __restrict__ 
 // (param-space constants are eligible for uniform-register operands)
 struct ExpTable { double k[16]; };
 inline ExpTable make_exp_table() {
-    return ExpTable{{0x1.71547652b82fep+0, 0x1.8000000000000p+52, -0x1.62e42fefa39efp-1, -0x1.abc9e3b39803fp-56,
-                     0x1.ade1569ce2bdfp-26, 0x1.28af3fca213eap-22, 0x1.71dee62401315p-19, 0x1.a01997c89eb71p-16,
-                     0x1.a01a014761f65p-13, 0x1.6c16c1852b7afp-10, 0x1.1111111122322p-7, 0x1.55555555502a1p-5,
-                     0x1.5555555555511p-3, 0x1.000000000000bp-1, 1.0, 0.0}};
+    return ExpTable{{0x1.71547652b82fep+6, 0x1.8000000000000p+52, -0x1.62e42fefa39efp-7, -0x1.abc9e3b39803fp-62, 0x1.0p-1,
+                     0x1.5555555555555p-3, 0x1.5555555555555p-5, 0x1.1111111111111p-7, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0}};
 }
 
 struct Diode {  // elements.jl:236-245
