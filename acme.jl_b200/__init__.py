@@ -14,11 +14,12 @@ from .circuit import Circuit, circuit, topomat
 from .model import DiscreteModel, SubProblem, gensolve, rank_factorize
 from . import examples
 from .runner import BatchRunner, ModelRunner, run_, DimensionMismatch
+from .sweep import derive_sweep
 
 __all__ = [
     "Element", "NLElem", "Circuit", "circuit", "topomat", "DiscreteModel", "SubProblem",
     "gensolve", "rank_factorize", "examples",
-    "BatchRunner", "ModelRunner", "run_", "DimensionMismatch",
+    "BatchRunner", "ModelRunner", "run_", "DimensionMismatch", "derive_sweep",
     "resistor", "potentiometer", "capacitor", "inductor", "transformer",
     "voltagesource", "currentsource", "voltageprobe", "currentprobe",
     "diode", "bjt", "mosfet", "opamp",

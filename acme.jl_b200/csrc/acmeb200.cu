@@ -296,7 +296,7 @@ static int select_kernel(acmeb200_model* m) {
     if (m->kernel_mode == 0) m->tpi = find_tpi(m->dm);
     if (!m->tpi && (m->kernel_mode == 0 || m->kernel_mode == 3)) {
         // one warp per instance, LU rows in registers: compile-time shapes only
-        if (m->blob_stride == 0 && !m->has_cache && m->rows_ok && rows_matches(m->dm)) m->rows = 1;
+        if (!m->has_cache && m->rows_ok) m->rows = rows_shape(m->dm);  // shared or per-instance matrices
         if (m->kernel_mode == 3 && !m->rows)
             return fail(ACMEB200_EUNSUPPORTED, "the rows-in-registers kernel has no instantiation for this model shape");
     }
@@ -310,7 +310,8 @@ static int select_kernel(acmeb200_model* m) {
     }
     m->ws_rows = m->tpi ? m->tpi->state_rows : m->dm.w_rows;
     if (m->tpi) m->kernel_name = m->tpi->name;
-    else if (m->rows) m->kernel_name = std::string("rows<warp per instance, LU rows in registers, compile-time dims [superover]") +
+    else if (m->rows) m->kernel_name = std::string("rows<warp per instance, LU rows in registers, compile-time dims ") +
+                                       (m->rows == 1 ? "[superover]" : "[superover, baked pots]") + (m->blob_stride ? ", per-instance matrices" : "") +
                                        (m->dm.solver == ACMEB200_SOLVER_HOMOTOPY_CACHING ? ", dynamic solution cache>" : ">");
     else if (m->coop_lanes) m->kernel_name = "coop<" + std::to_string(m->coop_lanes) + " lanes per instance, " +
                                             (m->coop_static ? "compile-time dims [superover]" : "runtime dims") + ", state in shared memory" +

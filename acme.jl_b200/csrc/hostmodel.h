@@ -42,7 +42,7 @@ struct acmeb200_model {
     const TpiEntry* tpi = nullptr;
     int coop_lanes = 0;  // 0: not the cooperative kernel
     int coop_static = 0; // 1: CoopSuperover compile-time shape
-    int rows = 0;        // 1: warp-per-instance kernel with LU rows in registers (CoopSuperover shape)
+    int rows = 0;        // > 0: warp-per-instance kernel with LU rows in registers, shape index (rows.cu)
     bool rows_ok = true;
     bool has_cache = false;
     int max_nn = 0, max_nelem = 0;
@@ -69,5 +69,5 @@ int coop_lanes_for(const acmeb200_model* m);
 bool coop_static_matches(const acme::DevModel& dm);
 cudaError_t launch_coop_kernel(const acmeb200_model* m, const acme::RunArgs& a, cudaStream_t stream);
 // rows.cu: warp-per-instance kernel, LU rows in registers
-bool rows_matches(const acme::DevModel& dm);
+int rows_shape(const acme::DevModel& dm);  // 0: no instantiation, else the shape index stored in acmeb200_model::rows
 cudaError_t launch_rows_kernel(const acmeb200_model* m, const acme::RunArgs& a, cudaStream_t stream);

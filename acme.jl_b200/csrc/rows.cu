@@ -8,25 +8,35 @@ using namespace acme;
 
 // BASELINE config 4: examples/superover.jl with the three potentiometers as inputs
 using RowsSuperover = CoopStatic<11, 4, 1, 13, 29, 11, 8, 23>;
+// the alternative reading of config 4: potentiometers baked into the stamps (runtests.jl:744: np 5), one set of
+// matrices per instance (q1, d1, d2, d3, q2: 5 elements, 11 variable Jacobian entries)
+using RowsSuperoverBaked = CoopStatic<11, 1, 1, 7, 14, 5, 5, 11>;
 
-bool rows_matches(const DevModel& dm) { return RowsSuperover::matches(dm); }
+int rows_shape(const DevModel& dm) { return RowsSuperover::matches(dm) ? 1 : (RowsSuperoverBaked::matches(dm) ? 2 : 0); }
 
-template <class S, int WARPS>
+template <class S, int WARPS, bool PERINST>
 static cudaError_t launch_rows(const acmeb200_model* m, const RunArgs& a, cudaStream_t stream) {
-    const size_t smem = rows_smem_bytes<S>(WARPS, m->dm.nconst);
+    const size_t smem = rows_smem_bytes<S>(WARPS, m->dm.nconst, PERINST);
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(k_rows<S, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(k_rows<S, WARPS, PERINST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    k_rows<S, WARPS><<<(unsigned)((a.ninst + WARPS - 1) / WARPS), WARPS * 32, smem, stream>>>(m->dm, a);
+    k_rows<S, WARPS, PERINST><<<(unsigned)((a.ninst + WARPS - 1) / WARPS), WARPS * 32, smem, stream>>>(m->dm, a);
     return cudaGetLastError();
 }
 
-cudaError_t launch_rows_kernel(const acmeb200_model* m, const RunArgs& a, cudaStream_t stream) {
+template <class S>
+static cudaError_t launch_rows_shape(const acmeb200_model* m, const RunArgs& a, cudaStream_t stream) {
     // small batches: one warp per CTA spreads the instances evenly over the SMs and may use 255
     // registers (8 resident warps per SM); larger batches need the 16 warps per SM of the 128-register build
-    if (a.ninst <= 148 * 8) return launch_rows<RowsSuperover, 1>(m, a, stream);
-    return launch_rows<RowsSuperover, 4>(m, a, stream);
+    const bool small = a.ninst <= 148 * 8;
+    if (m->blob_stride) return small ? launch_rows<S, 1, true>(m, a, stream) : launch_rows<S, 4, true>(m, a, stream);
+    return small ? launch_rows<S, 1, false>(m, a, stream) : launch_rows<S, 4, false>(m, a, stream);
+}
+
+cudaError_t launch_rows_kernel(const acmeb200_model* m, const RunArgs& a, cudaStream_t stream) {
+    if (m->rows == 2) return launch_rows_shape<RowsSuperoverBaked>(m, a, stream);
+    return launch_rows_shape<RowsSuperover>(m, a, stream);
 }

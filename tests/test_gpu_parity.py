@@ -61,10 +61,13 @@ def coop_ok(model, **kw):
 
 
 def rows_ok(model, **kw):
-    """the rows-in-registers kernel is instantiated for compile-time shapes: superover with the
-    three potentiometers as inputs (BASELINE config 4)"""
-    return (coop_ok(model, **kw) and len(model.subs) == 1 and
-            (model.nx, model.nu, model.ny, model.subs[0].nn, model.subs[0].nq, model.subs[0].np_) == (11, 4, 1, 13, 29, 11))
+    """the rows-in-registers kernel is instantiated for compile-time shapes: superover with the three
+    potentiometers as inputs (BASELINE config 4) and with baked potentiometers (its alternative
+    reading); shared or per-instance matrices, no frozen cache"""
+    if len(model.subs) != 1 or kw.get("caches"):
+        return False
+    s = model.subs[0]
+    return (model.nx, model.nu, model.ny, s.nn, s.nq, s.np_) in {(11, 4, 1, 13, 29, 11), (11, 1, 1, 7, 14, 5)}
 
 
 def skip_unless_applicable(kernel, model, **kw):

@@ -1,0 +1,92 @@
+"""Sweep-scale model derivation (acme.jl_b200/sweep.py): the parallel
+derivation must equal a plain loop of DiscreteModel(...) calls, and a sweep of baked-in element values
+(BASELINE config 3; the alternative reading of config 4) must run through the same ABI."""
+import numpy as np
+import pytest
+
+import acme_jl_b200 as A
+from acme_jl_b200 import examples as ex
+
+import cases
+
+
+def build_sk(R, kap):
+    return ex.sallenkey(fs=96000, r1=R, r2=R, c1=10e-9 * kap, c2=10e-9 / kap)
+
+
+def build_so(drive, tone):
+    return ex.superover(drive, tone, 1.0)
+
+
+def test_derive_sweep_equals_loop():
+    pts = [(10 ** (3 + 2 * k / 7), 10 ** (1.3 * (k % 3) / 2)) for k in range(8)]
+    base, kw, B = A.derive_sweep(build_sk, pts, workers=2, chunk=3)
+    assert B == 8 and set(kw) == {"overrides"}          # a linear model: nothing but matrices
+    ov = kw["overrides"]
+    assert set(ov) == {"a", "b", "dy", "ey"}             # x0, y0 do not depend on R, C here
+    for b, p in enumerate(pts):
+        m = build_sk(*p)
+        for key in ("a", "b", "dy", "ey"):
+            assert np.array_equal(ov[key][..., b], getattr(m, key))
+    serial, kw1, _ = A.derive_sweep(build_sk, pts, workers=1)
+    assert all(np.array_equal(kw1["overrides"][k], ov[k]) for k in ov)
+
+
+def test_derive_sweep_rejects_structure_change():
+    # r -> 0 Ohm decouples the two diodes of the clipper: the non-linear problem decomposes into two
+    # sub-problems (ACME.jl:277-315); a different model structure in one batch is an error
+    def build(r):
+        return A.DiscreteModel(ex.diodeclipper_circuit(r=r), 1 / 44100)
+    with pytest.raises(ValueError, match="different model structure"):
+        A.derive_sweep(build, [1e3, 0.0], workers=1)
+
+
+def test_derive_sweep_empty():
+    with pytest.raises(ValueError, match="empty sweep"):
+        A.derive_sweep(build_sk, [])
+
+
+@pytest.mark.gpu
+def test_config3_sweep_through_derive_sweep():
+    from acme_jl_b200 import BatchRunner
+    from oracle.oracle import OracleModel
+    pts = [(10 ** (3 + 2 * (k % 4) / 3), 10 ** (1.3 * (k // 4) / 3)) for k in range(16)]
+    base, kw, B = A.derive_sweep(build_sk, pts, workers=2)
+    u = cases.sine(3000) if hasattr(cases, "sine") else None
+    r = BatchRunner(base, B, **kw)
+    y = r.run(u)
+    yref = OracleModel(base, B, **kw).run(u, threads=0)
+    peak = np.abs(yref).max()
+    assert np.max(np.abs(y - yref) / np.maximum(np.abs(yref), 1e-3 * peak)) < 1e-6
+    assert r.kernel_name.startswith("tpi<linear")
+    r.close()
+
+
+@pytest.mark.gpu
+def test_config4_alternative_reading_baked_pots():
+    """superover(drive, tone, level) with the potentiometers baked into the stamps (np 5, nn 7,
+    runtests.jl:744): per-instance matrices AND per-instance initial solutions, derived at sweep
+    scale, against the oracle fed with the same per-instance arrays"""
+    from acme_jl_b200 import BatchRunner
+    from oracle.oracle import OracleModel
+    pts = [(0.15 + 0.2 * (k % 3), 0.3 + 0.4 * (k // 3)) for k in range(6)]
+    base, kw, B = A.derive_sweep(build_so, pts, workers=2, chunk=1)
+    assert base.subs[0].np_ == 5 and "init_z" in kw and "fq0" in kw["overrides"]
+    u = cases.sine(1200)
+    H = "HomotopySolver{SimpleSolver}"
+    r = BatchRunner(base, B, solver=H, **kw)
+    assert r.kernel_name.startswith("rows<") and "per-instance matrices" in r.kernel_name
+    y = r.run(u)
+    yref = OracleModel(base, B, solver=H, **kw).run(u, threads=0)
+    rg = BatchRunner(base, B, solver=H, kernel="generic", **kw)
+    yg = rg.run(u)                               # the generic kernel sums J = Jq*fq in another order
+    assert np.max(np.abs(yg - y)) <= 1e-9 * np.abs(yref).max()
+    rg.close()
+    peak = np.abs(yref).max()
+    err = np.abs(y - yref) / np.maximum(np.abs(yref), 1e-3 * peak)
+    assert err.max() < 1e-6, err.max()
+    # and every instance equals its own single-instance model
+    for b in (0, 5):
+        y1 = BatchRunner(build_so(*pts[b]), 1, solver=H).run(u)
+        assert np.max(np.abs(y1[:, :, 0] - y[:, :, b])) <= 1e-9 * peak
+    r.close()
