@@ -37,6 +37,7 @@ def lib():
         L.acmeb200_reset.argtypes = [vp]
         L.acmeb200_get_status.argtypes = [vp, vp, vp]
         L.acmeb200_get_stats.argtypes = [vp, C.POINTER(Stats)]
+        L.acmeb200_get_cache_sizes.argtypes = [vp, C.c_int32, vp, C.POINTER(C.c_int32)]
         L.acmeb200_set_kernel.argtypes = [vp, C.c_int32]
         L.acmeb200_kernel_name.argtypes = [vp]
         L.acmeb200_kernel_name.restype = C.c_char_p
@@ -55,7 +56,7 @@ def check(rc):
 
 
 EXPORTS = ["acmeb200_model_create", "acmeb200_model_destroy", "acmeb200_run", "acmeb200_get_state",
-           "acmeb200_set_state", "acmeb200_reset", "acmeb200_get_status", "acmeb200_get_stats",
+           "acmeb200_set_state", "acmeb200_reset", "acmeb200_get_status", "acmeb200_get_stats", "acmeb200_get_cache_sizes",
            "acmeb200_set_kernel", "acmeb200_kernel_name", "acmeb200_launch_count", "acmeb200_measure_fp64_peak",
            "acmeb200_last_error", "acmeb200_abi_version"]
 

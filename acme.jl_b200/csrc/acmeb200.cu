@@ -327,7 +327,10 @@ static int select_kernel(acmeb200_model* m) {
         if (!(m->coop_lanes || m->rows || m->tpi) || m->dm.solver != ACMEB200_SOLVER_HOMOTOPY_CACHING || s.cache_n > 0) continue;
         size_t free_b = 0, total_b = 0;
         CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
-        int cap = m->tpi ? 128 : 1024;
+        // ring-buffer capacity: the start points that matter are the recently stored ones (superover: the
+        // iteration statistics are identical for 64, 256 and 1024), and every stored point is scanned per sample
+        int cap = m->tpi ? 128 : 256;
+        if (const char* e = getenv("ACMEB200_CACHE_CAP")) { const long v = atol(e); if (v >= 2 && v <= (1 << 20)) cap = (int)v; }  // tuning knob
         while (cap > 32 && (size_t)m->B * (s.np + s.nn) * cap * 8 > free_b / 8) cap /= 2;
         void *ps = nullptr, *zs = nullptr, *nn_ = nullptr;
         CUDA_TRY(cudaMalloc(&ps, std::max<size_t>(8, (size_t)m->B * s.np * cap * 8)));
@@ -555,6 +558,20 @@ extern "C" int acmeb200_get_stats(acmeb200_model* m, acmeb200_stats* out) {
     out->samples = s.samples; out->solves = s.solves; out->newton_iters = s.newton_iters;
     out->homotopy_solves = s.homotopy_solves; out->not_converged = s.not_converged;
     for (int i = 0; i < ACMEB200_HIST_BINS; i++) out->iter_hist[i] = s.iter_hist[i];
+    return ACMEB200_OK;
+}
+
+extern "C" int acmeb200_get_cache_sizes(acmeb200_model* m, int32_t sub, int32_t* sizes_host, int32_t* capacity_out) {
+    if (!m || !sizes_host) return fail(ACMEB200_EINVAL, "null argument");
+    if (sub < 0 || sub >= m->dm.nsub) return fail(ACMEB200_EINVAL, "sub-problem %d out of range", sub);
+    CUDA_TRY(cudaSetDevice(m->device));
+    CUDA_TRY(cudaDeviceSynchronize());
+    const DevSub& s = m->dm.subs[sub];
+    if (capacity_out) *capacity_out = s.dyn_cap;
+    if (s.dyn_cap > 0 && s.dyn_n)
+        CUDA_TRY(cudaMemcpy(sizes_host, s.dyn_n, sizeof(int32_t) * (size_t)m->B, cudaMemcpyDeviceToHost));
+    else
+        memset(sizes_host, 0, sizeof(int32_t) * (size_t)m->B);
     return ACMEB200_OK;
 }
 

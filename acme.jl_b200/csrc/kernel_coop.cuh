@@ -322,7 +322,8 @@ __device__ inline GSolveResult c_base_solve(const CCtx<L>& g, const DevSub& s, i
     if (caching) {
         cps = s.dyn_ps + inst * (int64_t)SD(NP, s.np) * s.dyn_cap;
         czs = s.dyn_zs + inst * (int64_t)SD(NN, s.nn) * s.dyn_cap;
-        n = s.dyn_n[inst];
+        n = s.dyn_n[inst];  // solutions stored so far; the ring buffer holds the newest dyn_cap of them
+        const int nvalid = n < s.dyn_cap ? n : s.dyn_cap;
         double best = 0.0;
         for (int i = 0; i < SD(NP, s.np); i++) {
             const double d = g.W(prow + i) - g.W(SD(W_LASTP, s.w_lastp) + i);
@@ -330,7 +331,7 @@ __device__ inline GSolveResult c_base_solve(const CCtx<L>& g, const DevSub& s, i
         }
         double lbest = best;
         int lidx = -1;
-        for (int idx = g.lane; idx < n; idx += L) {
+        for (int idx = g.lane; idx < nvalid; idx += L) {
             double d2 = 0.0;
             for (int d = 0; d < SD(NP, s.np); d++) {
                 const double df = cps[(int64_t)d * s.dyn_cap + idx] - g.W(prow + d);
@@ -355,9 +356,10 @@ __device__ inline GSolveResult c_base_solve(const CCtx<L>& g, const DevSub& s, i
         }
     }
     const GSolveResult r = c_simple_solve<L, P>(g, s, si, prow);
-    if (caching && r.iters > 5 && r.converged && n < s.dyn_cap) {
-        for (int i = g.lane; i < SD(NP, s.np); i += L) cps[(int64_t)i * s.dyn_cap + n] = g.W(prow + i);
-        for (int i = g.lane; i < SD(NN, s.nn); i += L) czs[(int64_t)i * s.dyn_cap + n] = g.W(SD(W_Z, m.w_z) + i);
+    if (caching && r.iters > 5 && r.converged) {
+        const int slot = n % s.dyn_cap;  // ring buffer: the oldest entry is overwritten
+        for (int i = g.lane; i < SD(NP, s.np); i += L) cps[(int64_t)i * s.dyn_cap + slot] = g.W(prow + i);
+        for (int i = g.lane; i < SD(NN, s.nn); i += L) czs[(int64_t)i * s.dyn_cap + slot] = g.W(SD(W_Z, m.w_z) + i);
         g.sync();
         if (g.lane == 0) s.dyn_n[inst] = n + 1;
         __threadfence_block();

@@ -313,8 +313,9 @@ template <class C>
 __device__ __forceinline__ int tpi_cache_nearest(const DevSub& c, int64_t inst, int64_t ld,
                                                  const double (&p)[dim1(C::NP)], const double (&lp)[dim1(C::NP)],
                                                  int& n_out) {
-    const int n = c.dyn_n[inst];
+    const int n = c.dyn_n[inst];  // solutions stored so far; the ring buffer holds the newest dyn_cap of them
     n_out = n;
+    const int nvalid = n < c.dyn_cap ? n : c.dyn_cap;
     double best = 0.0;
     static_for<0, C::NP>([&](auto ii) {
         constexpr int i = decltype(ii)::value;
@@ -322,24 +323,35 @@ __device__ __forceinline__ int tpi_cache_nearest(const DevSub& c, int64_t inst, 
         best = fma(d, d, best);
     });
     int cidx = -1;
+    // four entries per pass: their loads are independent and in flight together (a one-entry loop
+    // pays the L2 latency once per entry); the minimum is still taken in index order
+    constexpr int UNR = 4;
 #pragma unroll 1
-    for (int idx = 0; idx < n; idx++) {
-        double d2 = 0.0;
-        static_for<0, C::NP>([&](auto ii) {
-            constexpr int i = decltype(ii)::value;
-            const double d = c.dyn_ps[((int64_t)idx * C::NP + i) * ld + inst] - p[i];
-            d2 = fma(d, d, d2);
-        });
-        if (d2 < best) { best = d2; cidx = idx; }
+    for (int i0 = 0; i0 < nvalid; i0 += UNR) {
+        double d2[UNR];
+#pragma unroll
+        for (int k = 0; k < UNR; k++) {
+            const int idx = i0 + k < nvalid ? i0 + k : nvalid - 1;
+            double acc = 0.0;
+            static_for<0, C::NP>([&](auto ii) {
+                constexpr int i = decltype(ii)::value;
+                const double d = c.dyn_ps[((int64_t)idx * C::NP + i) * ld + inst] - p[i];
+                acc = fma(d, d, acc);
+            });
+            d2[k] = acc;
+        }
+#pragma unroll
+        for (int k = 0; k < UNR; k++)
+            if (i0 + k < nvalid && d2[k] < best) { best = d2[k]; cidx = i0 + k; }
     }
     return cidx;
 }
 template <class C>
 __device__ __forceinline__ void tpi_cache_append(const DevSub& c, int64_t inst, int64_t ld, int n,
                                                  const double (&p)[dim1(C::NP)], const double (&z)[dim1(C::NN)]) {
-    if (n >= c.dyn_cap) return;
-    static_for<0, C::NP>([&](auto i) { c.dyn_ps[((int64_t)n * C::NP + decltype(i)::value) * ld + inst] = p[decltype(i)::value]; });
-    static_for<0, C::NN>([&](auto i) { c.dyn_zs[((int64_t)n * C::NN + decltype(i)::value) * ld + inst] = z[decltype(i)::value]; });
+    const int slot = n % c.dyn_cap;  // ring buffer: the oldest entry is overwritten
+    static_for<0, C::NP>([&](auto i) { c.dyn_ps[((int64_t)slot * C::NP + decltype(i)::value) * ld + inst] = p[decltype(i)::value]; });
+    static_for<0, C::NN>([&](auto i) { c.dyn_zs[((int64_t)slot * C::NN + decltype(i)::value) * ld + inst] = z[decltype(i)::value]; });
     c.dyn_n[inst] = n + 1;
 }
 

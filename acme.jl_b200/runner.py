@@ -91,6 +91,13 @@ class BatchRunner:
         check(lib().acmeb200_get_stats(self._h, C.byref(s)))
         return s.as_dict()
 
+    def cache_sizes(self, sub: int = 0):
+        """(sizes, capacity): solutions held by the learning CachingSolver per instance (solvers.jl:321-323)"""
+        n = np.zeros(self.batch, dtype=np.int32)
+        cap = C.c_int32(0)
+        check(lib().acmeb200_get_cache_sizes(self._h, sub, n.ctypes.data_as(C.c_void_p), C.byref(cap)))
+        return n, int(cap.value)
+
     def status(self):
         st = np.zeros(self.batch, dtype=np.uint32)
         ff = np.zeros(self.batch, dtype=np.int64)

@@ -186,6 +186,10 @@ int acmeb200_reset(acmeb200_model *m);
  * (int64 per instance, -1 if none); either pointer may be NULL */
 int acmeb200_get_status(acmeb200_model *m, uint32_t *status_host, int64_t *first_fail_host);
 int acmeb200_get_stats(acmeb200_model *m, acmeb200_stats *out);
+/* number of solutions the learning CachingSolver of sub-problem `sub` holds per instance
+ * (num_ps of /root/reference/src/solvers.jl:321-323; 0 when the model has no dynamic cache);
+ * *capacity_out (may be NULL) receives the fixed per-instance capacity */
+int acmeb200_get_cache_sizes(acmeb200_model *m, int32_t sub, int32_t *sizes_host, int32_t *capacity_out);
 
 /* kernel selection: 0 = automatic, 1 = force the generic thread-per-instance
  * kernel, 2 = force the cooperative (lanes-per-instance) kernel, 3 = force the
