@@ -403,6 +403,40 @@ def test_dynamic_cache_learning_superover():
     assert abs(it_gpu - it_ref) < 0.25 * it_ref  # and behaves like the reference's
 
 
+def test_dynamic_cache_ring_buffer_long_run(monkeypatch):
+    """The device store of the learning CachingSolver is a ring buffer.  With a capacity small enough
+    to wrap many times inside the test, a long run must keep learning like the reference does
+    (iterations per sample fall from second to second, solvers.jl:347-396) instead of degrading once
+    the store is full, and stay within the reference's own stopping-rule accuracy."""
+    monkeypatch.setenv("ACMEB200_CACHE_CAP", "32")
+    B, N = 6, 22050
+    m = ex.superover()
+    u = np.zeros((4, 2 * N, B), order="F")
+    u[0] = cases.sine(2 * N)[0][:, None]
+    u[1] = ((np.arange(B) * 21 + 10.5) / 128)[None, :]
+    u[2] = 0.5
+    u[3] = 1.0
+    o = OracleModel(m, B, solver=HC)
+    r = BatchRunner(m, B, solver=HC)
+    assert r.kernel_name.startswith("rows<")
+    it_gpu, it_ref, ys, yrefs = [], [], [], []
+    pg = po = (0, 0)
+    for half in range(2):
+        uh = np.asfortranarray(u[:, half * N:(half + 1) * N])
+        yrefs.append(o.run(uh, threads=0)); ys.append(r.run(uh))
+        sg, so = r.stats(), o.stats()
+        it_gpu.append((sg["newton_iters"] - pg[0]) / (sg["solves"] - pg[1])); pg = (sg["newton_iters"], sg["solves"])
+        it_ref.append((so["newton_iters"] - po[0]) / (so["solves"] - po[1])); po = (so["newton_iters"], so["solves"])
+    stored, cap = r.cache_sizes()
+    assert cap == 32 and stored.max() > 2 * cap            # the ring wrapped
+    assert it_gpu[1] < it_gpu[0] and it_ref[1] < it_ref[0]  # both keep learning
+    assert abs(it_gpu[1] - it_ref[1]) < 0.25 * it_ref[1]
+    y, yref = np.concatenate(ys, axis=1), np.concatenate(yrefs, axis=1)
+    yexact = OracleModel(m, B, solver=H, tol=1e-13).run(u, threads=0)
+    assert_parity_within_reference_accuracy(y, yref, yexact)
+    r.close()
+
+
 def test_dynamic_cache_learning_birdie_tpi():
     """the same learning CachingSolver in the thread-per-instance kernel (birdie, white noise)"""
     B, N = 32, 8000
