@@ -142,4 +142,18 @@ end
 
 ACME.run!(r::BatchRunner, U::Array{Float64,3}) = ACME.run!(r, Array{Float64,3}(undef, ny(r.model), size(U, 2), r.batch), U)
 
+"""
+    cache_sizes(runner; sub=1) -> (stored::Vector{Int32}, capacity::Int)
+
+Solutions the learning `CachingSolver` of sub-problem `sub` has stored so far, per instance
+(`num_ps`, src/solvers.jl:321-323).  The device keeps the newest `capacity` of them (ring buffer).
+"""
+function cache_sizes(r::BatchRunner; sub::Integer=1)
+    n = Vector{Int32}(undef, r.batch)
+    cap = Ref{Int32}(0)
+    check(ccall((:acmeb200_get_cache_sizes, libacmeb200), Cint, (Ptr{Cvoid}, Int32, Ptr{Int32}, Ptr{Int32}),
+                r.handle, sub - 1, n, cap))
+    return n, Int(cap[])
+end
+
 end # module
