@@ -2,6 +2,7 @@
 // maps of the launch's streams, launchers.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstring>
 #include <vector>
 
@@ -91,6 +92,27 @@ static cudaError_t launch_tpi(const acmeb200_model* m, const RunArgs& a, cudaStr
             if (e == cudaSuccess) e = cudaFuncSetAttribute(k_tpi<C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
             attr_set = true;
+        }
+    }
+    {
+        // Shared-memory carve-out: only what the CTAs resident for THIS batch need, the rest of the
+        // unified array stays L1.  The learning cache's stored points are scanned from global memory
+        // every sample (config 5: 124 KB per SM); with the default maximum carve-out (200 KB) only 39 % of
+        // those loads hit L1 and the kernel waits on L2 latency (profiles/k_tpi_r1.md).
+        static int last_pct = -1, sms = 0, max_smem = 0;
+        if (!sms) {
+            int dev = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
+        }
+        const int64_t resident = std::min<int64_t>(ACME_TPI_MINB, (blocks + sms - 1) / std::max(sms, 1));
+        const int64_t need = resident * (int64_t)(smem + 1024);
+        const int pct = (int)std::min<int64_t>(100, (need * 100 + max_smem - 1) / std::max(max_smem, 1));
+        if (pct != last_pct) {
+            cudaFuncSetAttribute(k_tpi<C, true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+            cudaFuncSetAttribute(k_tpi<C, false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+            last_pct = pct;
         }
     }
     if (m->blob_stride)
