@@ -1,0 +1,29 @@
+"""bench.py's synthetic workloads (BASELINE.json configs[1] and configs[3]) -- the parts that need no GPU"""
+import numpy as np
+
+import bench
+
+
+def test_config2_sweep_grid():
+    P = bench.sweep_params(65536, 0, 65536)
+    assert P.shape == (4, 65536)
+    Is, eta = P[0].reshape(256, 256), P[1].reshape(256, 256)           # index = 256 j + k
+    assert np.allclose(Is[0], 10.0 ** (-16 + 4 * np.arange(256) / 255)) and np.all(Is == Is[:1])
+    assert np.allclose(eta[:, 0], 1 + np.arange(256) / 255) and np.all(eta == eta[:, :1])
+    assert np.allclose(P[2], 1.8 * P[0]) and np.array_equal(P[3], P[1])  # diodeclipper.jl:11-12 asymmetry
+    # shards see their slice of the same grid
+    assert np.array_equal(bench.sweep_params(131072, 65536, 10), bench.sweep_params(65536, 0, 10))
+
+
+def test_config4_inputs():
+    u = bench.c4_inputs_np(0, 8192, 5)
+    assert u.shape == (8192, 5, 4)
+    assert np.allclose(u[:, :, 0], np.sin(2 * np.pi * 1000 / 44100 * np.arange(5))[None, :])
+    drive, tone = u[:, 0, 1], u[:, 0, 2]
+    assert np.allclose(np.unique(drive), (np.arange(128) + 0.5) / 128) and np.allclose(np.unique(tone), (np.arange(64) + 0.5) / 64)
+    assert len({(d, t) for d, t in zip(drive, tone)}) == 8192 and np.all(u[:, :, 3] == 1.0)
+    assert np.array_equal(bench.c4_inputs_np(1024, 16, 5), u[1024:1040])  # a rank's shard
+
+
+def test_host_cores_positive():
+    assert bench.host_cores() >= 1
