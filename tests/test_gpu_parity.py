@@ -528,6 +528,59 @@ def test_rows_kernel_small_and_ragged_batches():
         r.close()
 
 
+def test_rows_kernel_failure_paths_match_other_kernels():
+    """Error behaviour of step! (ACME.jl:688-694) in the rows-in-registers kernel: an absurd drive
+    (kilovolts into the superover) makes Newton fail, the homotopy take over and -- with
+    SimpleSolver alone -- the solve fail for good.  Status words, first failing sample, iteration
+    statistics and every output sample must equal the cooperative and the generic kernel's
+    (same arithmetic, different data movement), and the oracle's statuses."""
+    B, N = 4, 60
+    m = ex.superover()
+    u = np.zeros((4, N, B), order="F")
+    u[0] = (cases.sine(N)[0] * 1.0)[:, None] * np.array([1.0, 3e2, 3e3, 3e4])[None, :]
+    u[1], u[2], u[3] = 0.9, 0.5, 1.0
+    for solver in (H, "SimpleSolver"):
+        res = {}
+        for kernel in ("rows", "coop", "generic"):
+            r = BatchRunner(m, B, solver=solver, kernel=kernel)
+            y = r.run(u, check_status=False)   # statuses are compared below instead of raised
+            st, ff = r.status()
+            res[kernel] = (y.copy(), st.copy(), ff.copy(), r.stats())
+            r.close()
+        o = OracleModel(m, B, solver=solver)
+        o.run(u, threads=0)
+        yr, sr, fr, str_ = res["rows"]
+        for other in ("coop", "generic"):
+            yo, so_, fo, sto = res[other]
+            assert np.array_equal(sr, so_) and np.array_equal(fr, fo), (solver, other)
+            assert str_["iter_hist"] == sto["iter_hist"] and str_["homotopy_solves"] == sto["homotopy_solves"]
+            assert str_["not_converged"] == sto["not_converged"]
+            assert np.array_equal(np.isnan(yr), np.isnan(yo))
+            if other == "coop":
+                assert np.array_equal(np.nan_to_num(yr), np.nan_to_num(yo))
+        if solver == "SimpleSolver":
+            assert sr.any()                    # the solver alone does fail on this drive
+        assert np.array_equal(sr, np.asarray(o.status()[0]))
+
+
+def test_rows_kernel_shared_input_and_empty_run():
+    """one (nu, N) input shared by all instances (u_stride = 0) equals B copies of it; N = 0 is a no-op"""
+    B, N = 3, 500
+    m = ex.superover(0.4, 0.6, 1.0)                       # baked pots: nu = 1, the 7x7 instantiation
+    u = cases.sine(N)
+    r = BatchRunner(m, B, solver=HC)
+    assert r.kernel_name.startswith("rows<")
+    y_shared = r.run(u)
+    r.reset()
+    y_copies = r.run(np.asfortranarray(np.repeat(u[:, :, None], B, axis=2)))
+    assert np.array_equal(y_shared, y_copies)
+    assert np.array_equal(y_shared[:, :, 0], y_shared[:, :, 2])
+    x = r.x.copy()
+    y0 = r.run(np.zeros((1, 0)))
+    assert y0.shape == (1, 0, B) and np.array_equal(r.x, x)
+    r.close()
+
+
 def test_run_bang_updates_model_state():
     m = ex.sallenkey()
     y1 = run_(m, cases.sine(100))
