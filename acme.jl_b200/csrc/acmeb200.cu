@@ -323,8 +323,8 @@ static int select_kernel(acmeb200_model* m) {
     for (int i = 0; i < m->dm.nsub; i++) {
         DevSub& s = m->dm.subs[i];
         s.dyn_ps = nullptr; s.dyn_zs = nullptr; s.dyn_n = nullptr; s.dyn_cap = 0;
-        // dynamic caches: the cooperative and the thread-per-instance kernels (each with its own layout)
-        if (!(m->coop_lanes || m->rows || m->tpi) || m->dm.solver != ACMEB200_SOLVER_HOMOTOPY_CACHING || s.cache_n > 0) continue;
+        // learning caches for every kernel (the thread-per-instance kernels use their own SoA layout)
+        if (m->dm.solver != ACMEB200_SOLVER_HOMOTOPY_CACHING || s.cache_n > 0) continue;
         size_t free_b = 0, total_b = 0;
         CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
         // ring-buffer capacity: the start points that matter are the recently stored ones (superover: the

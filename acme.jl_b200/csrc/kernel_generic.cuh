@@ -19,6 +19,7 @@ struct GCtx {
     const double* initz;   // already offset by the instance
     double* ws;            // already offset by the instance
     int64_t ld;
+    int64_t inst;          // instance index (per-instance solution cache)
     __device__ __forceinline__ double iz(int k) const { return initz[(int64_t)k * ld]; }
     __device__ __forceinline__ double& w(int row) const { return ws[(int64_t)row * ld]; }
     __device__ __forceinline__ double c(int k) const { return consts[(int64_t)k * ld]; }
@@ -270,7 +271,7 @@ __device__ inline int kd_nearest(const DevSub& s, PF p, double best) {
     return best_idx;
 }
 
-// solve(::CachingSolver, p) restricted to a frozen cache (solvers.jl:347-373)
+// solve(::CachingSolver, p) (solvers.jl:347-396): frozen k-d tree supplied by the host, or the learning per-instance store
 __device__ inline GSolveResult g_base_solve(const GCtx& g, const DevSub& s, int prow) {
     const DevModel& m = g.m;
     if (m.solver == ACMEB200_SOLVER_HOMOTOPY_CACHING) {
@@ -286,8 +287,37 @@ __device__ inline GSolveResult g_base_solve(const GCtx& g, const DevSub& s, int 
                 for (int i = 0; i < s.nn; i++) g.w(m.w_z + i) = s.zs[(int64_t)(idx - 1) * s.nn + i];
                 g_set_origin(g, s, m.w_cp, m.w_z);
             }
+        } else if (s.dyn_cap > 0) {
+            // learning cache (solvers.jl:347-396), ring buffer of the newest dyn_cap solutions, layout
+            // [instance][dim][slot] shared with the cooperative / rows kernels: nearest stored point by scanning
+            double* const cps = s.dyn_ps + g.inst * (int64_t)s.np * s.dyn_cap;
+            double* const czs = s.dyn_zs + g.inst * (int64_t)s.nn * s.dyn_cap;
+            const int n = s.dyn_n[g.inst];
+            const int nvalid = n < s.dyn_cap ? n : s.dyn_cap;
+            int idx = -1;
+            for (int k = 0; k < nvalid; k++) {
+                double d2 = 0.0;
+                for (int i = 0; i < s.np; i++) {
+                    const double df = cps[(int64_t)i * s.dyn_cap + k] - g.w(prow + i);
+                    d2 = fma(df, df, d2);
+                }
+                if (d2 < best) { best = d2; idx = k; }
+            }
+            if (idx >= 0) {
+                for (int i = 0; i < s.np; i++) g.w(m.w_cp + i) = cps[(int64_t)i * s.dyn_cap + idx];
+                for (int i = 0; i < s.nn; i++) g.w(m.w_z + i) = czs[(int64_t)i * s.dyn_cap + idx];
+                g_set_origin(g, s, m.w_cp, m.w_z);
+            }
+            const GSolveResult r = g_simple_solve(g, s, prow);
+            if (r.iters > 5 && r.converged) {  // solvers.jl:374-386
+                const int slot = n % s.dyn_cap;
+                for (int i = 0; i < s.np; i++) cps[(int64_t)i * s.dyn_cap + slot] = g.w(prow + i);
+                for (int i = 0; i < s.nn; i++) czs[(int64_t)i * s.dyn_cap + slot] = g.w(m.w_z + i);
+                s.dyn_n[g.inst] = n + 1;
+            }
+            return r;
         } else {
-            // fresh CachingSolver: the cache holds only (p = 0, z = init_z)  (solvers.jl:327-333)
+            // fresh CachingSolver without a store: the cache holds only (p = 0, z = init_z)  (solvers.jl:327-333)
             double d0 = 0.0;
             for (int i = 0; i < s.np; i++) d0 = fma(g.w(prow + i), g.w(prow + i), d0);
             if (d0 < best) {
@@ -341,7 +371,7 @@ __global__ void __launch_bounds__(128) k_generic(const __grid_constant__ DevMode
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= a.ninst) return;
     const int64_t inst = a.inst0 + t;
-    GCtx g{m, a.blob + inst * a.blob_stride, a.consts + inst, a.initz + inst, a.ws + inst, a.ld};
+    GCtx g{m, a.blob + inst * a.blob_stride, a.consts + inst, a.initz + inst, a.ws + inst, a.ld, inst};
 
     if (a.init) {
         // DiscreteModel ctor: x = 0 (ACME.jl:145); solver ctor: origin at (0, init_z) (solvers.jl:176)

@@ -401,6 +401,14 @@ def test_dynamic_cache_learning_superover():
     r.close()
     assert it_gpu < 0.8 * it_nocache          # the cache pays off
     assert abs(it_gpu - it_ref) < 0.25 * it_ref  # and behaves like the reference's
+    # the generic (fallback) kernel learns too: same store, same nearest-neighbour rule
+    r = BatchRunner(m, B, solver=HC, kernel="generic")
+    yg = r.run(u)
+    it_generic = r.stats()["newton_iters"] / r.stats()["solves"]
+    stored, cap = r.cache_sizes()
+    r.close()
+    assert_parity_within_reference_accuracy(yg, yref, yexact, yref2)
+    assert abs(it_generic - it_gpu) < 0.05 * it_gpu and stored.min() > 1 and cap >= 32
 
 
 def test_dynamic_cache_ring_buffer_long_run(monkeypatch):
