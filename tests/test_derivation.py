@@ -164,3 +164,27 @@ def test_K10_pins_from_golden_fixture():
         assert pins[key] == val, (key, pins[key], val)
         checked += 1
     assert checked == len(ours) >= 16
+
+
+def test_compiled_kernel_shapes_match_derived_models():
+    """The compile-time shapes the device library instantiates (csrc/tpi.cu, csrc/rows.cu) are the
+    shapes the derivation produces for the BASELINE circuits (SURVEY.md section 8 size table):
+    (nx, nu, ny, nn, nq, np, element kinds in CircuitNLFunc order)."""
+    D, B, P = 1, 2, 3   # ACMEB200_ELEM_DIODE / BJT / POT (include/acmeb200.h)
+    nj = {D: 1, B: 4, P: 4}  # variable Jacobian entries per element (csrc/elements.cuh)
+
+    def shape(m):
+        s = m.subs[0]
+        kinds = [e.kind for e, _ in s.elems]
+        return (m.nx, m.nu, m.ny, s.nn, s.nq, s.np_, kinds, sum(nj[k] for k in kinds))
+
+    assert shape(ex.diodeclipper()) == (1, 1, 1, 2, 4, 1, [D, D], 2)                      # tpi<diodeclipper>
+    assert shape(ex.birdie(vol=0.8)) == (3, 1, 1, 2, 4, 2, [B], 4)                          # tpi<birdie ... [bjt]>
+    assert shape(ex.birdie()) == (3, 2, 1, 4, 9, 3, [B, P], 8)                              # tpi<birdie ... [bjt,pot]>
+    m = ex.sallenkey(fs=96000)
+    assert (m.nx, m.nu, m.ny, len(m.subs)) == (2, 1, 1, 0)                                  # tpi<linear>
+    so = shape(ex.superover())
+    assert so[:6] == (11, 4, 1, 13, 29, 11) and len(so[6]) == 8 and so[7] == 23             # rows: RowsSuperover
+    assert sorted(so[6]) == sorted([B, D, D, D, P, P, P, B])
+    sb = shape(ex.superover(0.3, 0.7, 1.0))
+    assert sb[:6] == (11, 1, 1, 7, 14, 5) and sb[6] == [B, D, D, D, B] and sb[7] == 11       # rows: RowsSuperoverBaked
