@@ -61,6 +61,15 @@ def usable_cores() -> int:
     return n
 
 
+def _cuda_initialised() -> bool:
+    import sys
+    torch = sys.modules.get("torch")
+    try:
+        return bool(torch is not None and torch.cuda.is_initialized())
+    except Exception:
+        return False
+
+
 def derive_sweep(builder: Callable, points: Iterable, workers: Optional[int] = None, chunk: int = 16):
     """Derive ``builder(point)`` (a :class:`DiscreteModel`) for every sweep point.
 
@@ -73,7 +82,10 @@ def derive_sweep(builder: Callable, points: Iterable, workers: Optional[int] = N
     pts = list(points)
     if not pts:
         raise ValueError("empty sweep")
-    workers = workers or usable_cores()
+    if workers is None:
+        # the pool forks: a process that already holds a CUDA context (driver threads, locks) should
+        # not be forked behind the caller's back -- derive first, then create runners, or pass workers
+        workers = 1 if _cuda_initialised() else usable_cores()
     chunks = [pts[i:i + chunk] for i in range(0, len(pts), chunk)]
     _builder = builder
     try:

@@ -1,5 +1,5 @@
 import os, sys, json
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from acme_jl_b200 import BatchRunner, examples as ex
 import bench

@@ -1,5 +1,5 @@
 import os, sys, time, json
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from acme_jl_b200 import BatchRunner, examples as ex
 B = int(os.environ.get("KB_B", 8192)); N = int(os.environ.get("KB_N", 2000)); kernel = os.environ.get("KB_KERNEL", "auto")

@@ -1,6 +1,6 @@
 """static SASS statistics of one kernel of the library: registers/spills from the loop body's point of view"""
-import collections, re, subprocess, sys
-lib = sys.argv[1] if len(sys.argv) > 1 else '/root/repo/acme.jl_b200/libacmeb200.so'
+import collections, os, re, subprocess, sys
+lib = sys.argv[1] if len(sys.argv) > 1 else os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'acme.jl_b200', 'libacmeb200.so')
 pat = sys.argv[2] if len(sys.argv) > 2 else 'Li1ELi1ELi1ELi1EJNS_5DiodeES2_EEELb0'
 out = subprocess.check_output(['cuobjdump', '-sass', lib], text=True)
 blocks = out.split('Function : ')
