@@ -35,6 +35,9 @@ BATCH_PER_GPU = 65536
 SOLVER = "HomotopySolver{CachingSolver{SimpleSolver}}"  # the reference's default (ACME.jl:150)
 METRIC = "Msamples/sec (batched circuit-samples)"
 ALG_BYTES_PER_SAMPLE = 16  # one f64 input read + one f64 probe sample written
+# FP64 work the diode-clipper kernel executes per circuit-sample at 2.24 Newton iterations, from the ncu
+# instruction mix of profiles/k_tpi_r1.md (per thread: 124.6 DFMA, 37.6 DMUL, 34.0 DADD; DSETP/MUFU not counted)
+FP64_FLOPS_PER_SAMPLE = 2 * 124.6 + 37.6 + 34.0
 
 
 def sweep_params(batch_total: int, first: int, count: int) -> np.ndarray:
@@ -516,6 +519,12 @@ def main():
             "fp64_pipe": {"measured_dfma_peak_tflops": fp64_peak,
                           "note": "DFMA microbenchmark in this run (acmeb200_measure_fp64_peak); per-sample "
                                   "flop counts are in DESIGN.md"},
+            # the roofline that actually binds this kernel (FP64 CUDA-core pipe; dependent-issue latency keeps it
+            # from the peak): executed FP64 flops per sample x samples/s against the DFMA peak measured in this run
+            "roofline_fp64": {"bound": "fp64", "achieved": FP64_FLOPS_PER_SAMPLE * per_gpu_rate / 1e12, "peak": fp64_peak,
+                              "unit": "TFLOP/s", "frac": FP64_FLOPS_PER_SAMPLE * per_gpu_rate / 1e12 / fp64_peak if fp64_peak else None,
+                              "flops_per_sample": FP64_FLOPS_PER_SAMPLE,
+                              "source": "ncu instruction mix (profiles/k_tpi_r1.md), 2.24 Newton iterations per sample"},
             "newton": {"mean_iters": st["newton_iters"] / max(st["solves"], 1), "hist_1_to_8": st["iter_hist"][:8],
                        "homotopy_solves": st["homotopy_solves"], "not_converged": st["not_converged"],
                        "instances_with_status": status_bad},
