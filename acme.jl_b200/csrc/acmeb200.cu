@@ -363,7 +363,7 @@ static cudaError_t launch(acmeb200_model* m, const RunArgs& a, cudaStream_t stre
     if (m->rows && !a.init) return launch_rows_kernel(m, a, stream);  // the generic kernel initialises the (shared) state layout
     if (m->coop_lanes && !a.init) return launch_coop_kernel(m, a, stream);
     const int tpb = 128;
-    k_generic<<<(unsigned)((a.ninst + tpb - 1) / tpb), tpb, 0, stream>>>(m->dm, a);
+    ACME_LAUNCH(k_generic, (unsigned)((a.ninst + tpb - 1) / tpb), tpb, 0, stream, m->dm, a);
     return cudaGetLastError();
 }
 
@@ -602,7 +602,7 @@ extern "C" int acmeb200_measure_fp64_peak(double* tflops_out) {
     float best = 1e30f;
     for (int rep = 0; rep < 5; rep++) {
         CUDA_TRY(cudaEventRecord(e0));
-        k_dfma_peak<<<blocks, tpb>>>(d, iters, 0.999999, 1e-9);
+        ACME_LAUNCH(k_dfma_peak, blocks, tpb, 0, (cudaStream_t) nullptr, d, iters, 0.999999, 1e-9);
         CUDA_TRY(cudaEventRecord(e1));
         CUDA_TRY(cudaEventSynchronize(e1));
         float ms = 0;

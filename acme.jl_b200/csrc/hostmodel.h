@@ -12,6 +12,13 @@
 
 struct acmeb200_model;
 
+// kernel launch: CUDA's <<<>>> in the product; the host emulation of tests/emu runs the CTAs as fibers
+#ifdef ACME_HOST_EMU
+#define ACME_LAUNCH(kernel, grid, block, smem, stream, ...) acme_emu::launch(kernel, (unsigned)(grid), (unsigned)(block), (size_t)(smem), __VA_ARGS__)
+#else
+#define ACME_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#endif
+
 struct TpiEntry {
     const char* name;
     int nx, nu, ny, np, ne;

@@ -431,7 +431,7 @@ __global__ void __launch_bounds__(COOP_TPB) k_coop(const __grid_constant__ DevMo
     // ---- stage the shared model matrices with one TMA bulk copy
     if (threadIdx.x == 0) {
         mbar_init(bar, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_init_fence();
     }
     __syncthreads();
     if (threadIdx.x == 0) {

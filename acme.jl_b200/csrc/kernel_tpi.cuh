@@ -729,7 +729,7 @@ __global__ void __launch_bounds__(TPI_TPB, ACME_TPI_MINB) k_tpi(const __grid_con
     if (tma_in) {
         if (lane == 0)
             for (int st_ = 0; st_ < TPI_STAGES; st_++) mbar_init(bar0 + 8 * st_, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_init_fence();
         __syncwarp();
         // prologue: the first TPI_STAGES tiles in flight
         if (lane == 0 && wact)

@@ -23,7 +23,7 @@ static cudaError_t launch_rows(const acmeb200_model* m, const RunArgs& a, cudaSt
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    k_rows<S, WARPS, PERINST><<<(unsigned)((a.ninst + WARPS - 1) / WARPS), WARPS * 32, smem, stream>>>(m->dm, a);
+    ACME_LAUNCH((k_rows<S, WARPS, PERINST>), (unsigned)((a.ninst + WARPS - 1) / WARPS), WARPS * 32, smem, stream, m->dm, a);
     return cudaGetLastError();
 }
 

@@ -17,11 +17,30 @@ __device__ __forceinline__ void static_for(F&& f) {
 }
 
 
+#ifdef ACME_HOST_EMU
+// ---- host emulation (tests/emu): a "shared address" is the offset into the emulated shared memory, an
+// mbarrier is a completion flag, a bulk copy is a memcpy.  Tensor-map tiles are not emulated.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t) { *reinterpret_cast<uint64_t*>(acme_emu::g_smem + bar) = 0; }
+__device__ __forceinline__ void mbar_init_fence() {}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t, uint32_t) {}
+__device__ __forceinline__ void mbar_arrive(uint32_t) {}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t) {
+    while (*reinterpret_cast<volatile uint64_t*>(acme_emu::g_smem + bar) == 0) acme_emu::yield();
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    memcpy(acme_emu::g_smem + dst, src, bytes);
+    *reinterpret_cast<uint64_t*>(acme_emu::g_smem + bar) = 1;
+    acme_emu::g_cta.progress++;
+}
+#else
 // ---- TMA (bulk async copy) + mbarrier primitives, PTX ISA 8.x --------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
+// makes the mbarrier initialisation visible to the async proxy / the cluster
+__device__ __forceinline__ void mbar_init_fence() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
@@ -66,5 +85,7 @@ __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+
+#endif  // ACME_HOST_EMU
 
 }  // namespace acme

@@ -1,0 +1,100 @@
+// Fiber scheduler of the host emulation (see cuda_runtime.h in this directory) -- test infrastructure.
+#include "cuda_runtime.h"
+
+emu_uint3 threadIdx, blockIdx, blockDim, gridDim;
+
+namespace acme {
+alignas(1024) unsigned char smem_raw[256 * 1024];  // the kernels' `extern __shared__ smem_raw[]`
+}
+
+namespace acme_emu {
+Cta g_cta;
+unsigned char* g_smem = acme::smem_raw;
+
+namespace {
+struct Fiber {
+    ucontext_t ctx;
+    std::vector<char> stack;
+    bool done = false;
+};
+std::vector<Fiber> fibers;
+ucontext_t sched_ctx;
+int cur = -1;
+const std::function<void()>* g_body = nullptr;
+
+void trampoline() {
+    (*g_body)();
+    fibers[cur].done = true;
+    g_cta.live--;
+    g_cta.warp_live[cur >> 5]--;
+    g_cta.progress++;
+    // a finished lane no longer takes part in its warp's barriers: release a barrier it was the last one missing from
+    const int w = cur >> 5;
+    if (g_cta.warp_live[w] && g_cta.warp_cnt[w] >= g_cta.warp_live[w]) { g_cta.warp_cnt[w] = 0; g_cta.warp_gen[w]++; }
+    if (g_cta.live && g_cta.cta_cnt >= (unsigned)g_cta.live) { g_cta.cta_cnt = 0; g_cta.cta_gen++; }
+    swapcontext(&fibers[cur].ctx, &sched_ctx);
+}
+}  // namespace
+
+void yield() { swapcontext(&fibers[cur].ctx, &sched_ctx); }
+
+void warp_barrier() {
+    const int w = cur >> 5;
+    const unsigned gen = g_cta.warp_gen[w];
+    if (++g_cta.warp_cnt[w] >= g_cta.warp_live[w]) {
+        g_cta.warp_cnt[w] = 0;
+        g_cta.warp_gen[w]++;
+        g_cta.progress++;
+        return;
+    }
+    while (g_cta.warp_gen[w] == gen) yield();
+}
+
+void cta_barrier() {
+    const unsigned gen = g_cta.cta_gen;
+    if (++g_cta.cta_cnt >= (unsigned)g_cta.live) {
+        g_cta.cta_cnt = 0;
+        g_cta.cta_gen++;
+        g_cta.progress++;
+        return;
+    }
+    while (g_cta.cta_gen == gen) yield();
+}
+
+void run_cta(const std::function<void()>& body, unsigned block, unsigned bx, unsigned grid) {
+    if (block > MAX_THREADS) { fprintf(stderr, "emu: block of %u threads\n", block); abort(); }
+    g_body = &body;
+    g_cta = Cta();
+    g_cta.nthreads = g_cta.live = (int)block;
+    for (unsigned w = 0; w < MAX_THREADS / 32; w++) {
+        g_cta.warp_gen[w] = g_cta.warp_cnt[w] = 0;
+        const int lo = (int)w * 32;
+        g_cta.warp_live[w] = lo >= (int)block ? 0u : (unsigned)std::min(32, (int)block - lo);
+    }
+    blockIdx = {bx, 0, 0}; blockDim = {block, 1, 1}; gridDim = {grid, 1, 1};
+    fibers.assign(block, Fiber());
+    for (unsigned t = 0; t < block; t++) {
+        Fiber& f = fibers[t];
+        f.stack.resize(512 * 1024);
+        getcontext(&f.ctx);
+        f.ctx.uc_stack.ss_sp = f.stack.data();
+        f.ctx.uc_stack.ss_size = f.stack.size();
+        f.ctx.uc_link = nullptr;
+        makecontext(&f.ctx, trampoline, 0);
+    }
+    while (g_cta.live > 0) {
+        const unsigned long before = g_cta.progress;
+        for (unsigned t = 0; t < block; t++) {
+            if (fibers[t].done) continue;
+            cur = (int)t;
+            threadIdx = {t, 0, 0};
+            swapcontext(&sched_ctx, &fibers[t].ctx);
+        }
+        if (g_cta.progress == before && g_cta.live > 0) {
+            fprintf(stderr, "emu: deadlock -- a collective was not reached by every live thread of its warp/CTA\n");
+            abort();
+        }
+    }
+    cur = -1;
+}
+}  // namespace acme_emu

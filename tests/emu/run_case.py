@@ -1,0 +1,57 @@
+"""Runs in a subprocess with ACMEB200_LIB = the emulated library (tests/test_emu.py): the device
+library's own kernel sources on the CPU against the oracle.  Prints one JSON line."""
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+import numpy as np
+
+import acme_jl_b200 as A
+from acme_jl_b200 import BatchRunner, examples as ex
+from oracle.oracle import OracleModel
+
+assert os.environ.get("ACMEB200_LIB", "").endswith("libacmeb200_emu.so")
+H, HC = "HomotopySolver{SimpleSolver}", "HomotopySolver{CachingSolver{SimpleSolver}}"
+case = sys.argv[1]
+sine = lambda n: np.sin(2 * np.pi * 1000 / 44100 * np.arange(n)).reshape(1, -1)
+out = {"case": case}
+if case == "superover_rows":
+    m = ex.superover()
+    B, N = 2, 70
+    u = np.zeros((4, N, B), order="F"); u[0] = sine(N)[0][:, None]; u[1] = np.array([0.3, 0.8])[None, :]; u[2] = 0.5; u[3] = 1.0
+    for solver in (H, HC):
+        o = OracleModel(m, B, solver=solver); yref = o.run(u, threads=0)
+        r = BatchRunner(m, B, solver=solver); y = r.run(u)
+        out[solver] = dict(kernel=r.kernel_name, err=float(np.abs(y - yref).max() / np.abs(yref).max()),
+                           hist=r.stats()["iter_hist"], hist_ref=o.stats()["iter_hist"],
+                           hom=r.stats()["homotopy_solves"], hom_ref=o.stats()["homotopy_solves"])
+        # chunked == one shot (state conversion rows-in-lanes <-> generic layout), and the generic kernel agrees
+        r.reset()
+        y2 = np.concatenate([r.run(np.asfortranarray(u[:, :31])), r.run(np.asfortranarray(u[:, 31:]))], axis=1)
+        out[solver]["chunked_equal"] = bool(np.array_equal(y, y2))
+        rg = BatchRunner(m, B, solver=solver, kernel="generic"); yg = rg.run(u)
+        out[solver]["generic_diff"] = float(np.abs(yg - y).max() / np.abs(yref).max())
+        r.close(); rg.close()
+elif case == "baked_perinst":
+    base, kw, B = A.derive_sweep(lambda d, t: ex.superover(d, t, 1.0), [(0.2, 0.5), (0.7, 0.4), (0.45, 0.9)], workers=1)
+    u = sine(60)
+    o = OracleModel(base, B, solver=H, **kw); yref = o.run(u, threads=0)
+    r = BatchRunner(base, B, solver=H, **kw); y = r.run(u)
+    out.update(kernel=r.kernel_name, err=float(np.abs(y - yref).max() / np.abs(yref).max()), hist=r.stats()["iter_hist"],
+               hist_ref=o.stats()["iter_hist"])
+    r.close()
+elif case == "failure":
+    m = ex.superover()
+    B, N = 2, 25
+    u = np.zeros((4, N, B), order="F"); u[0] = sine(N)[0][:, None] * np.array([3e2, 3e4])[None, :]; u[1] = 0.9; u[2] = 0.5; u[3] = 1.0
+    for solver in (H, "SimpleSolver"):
+        o = OracleModel(m, B, solver=solver); o.run(u, threads=0)
+        r = BatchRunner(m, B, solver=solver); y = r.run(u, check_status=False)
+        st, ff = r.status()
+        out[solver] = dict(kernel=r.kernel_name, status=[int(v) for v in st], status_ref=[int(v) for v in o.status()[0]],
+                           first=[int(v) for v in ff], first_ref=[int(v) for v in o.status()[1]],
+                           hist=r.stats()["iter_hist"], hist_ref=o.stats()["iter_hist"], nan=int(np.isnan(y).sum()))
+        r.close()
+print(json.dumps(out))
