@@ -18,21 +18,53 @@ __device__ __forceinline__ void static_for(F&& f) {
 
 
 #ifdef ACME_HOST_EMU
-// ---- host emulation (tests/emu): a "shared address" is the offset into the emulated shared memory, an
-// mbarrier is a completion flag, a bulk copy is a memcpy.  Tensor-map tiles are not emulated.
+// ---- host emulation (tests/emu): a "shared address" is the offset into the emulated shared memory; an
+// mbarrier is its count of completed phases (every use here is one arrival + the bytes of one copy);
+// bulk and tensor copies happen synchronously, so the bulk async-groups have nothing to wait for.
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t) { *reinterpret_cast<uint64_t*>(acme_emu::g_smem + bar) = 0; }
 __device__ __forceinline__ void mbar_init_fence() {}
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t, uint32_t) {}
 __device__ __forceinline__ void mbar_arrive(uint32_t) {}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t) {
-    while (*reinterpret_cast<volatile uint64_t*>(acme_emu::g_smem + bar) == 0) acme_emu::yield();
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {  // phase with this parity completed?
+    while ((*reinterpret_cast<volatile uint64_t*>(acme_emu::g_smem + bar) & 1u) == (uint64_t)parity) acme_emu::yield();
+}
+__device__ __forceinline__ void emu_complete_phase(uint32_t bar) {
+    *reinterpret_cast<uint64_t*>(acme_emu::g_smem + bar) += 1;
+    acme_emu::g_cta.progress++;
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
     memcpy(acme_emu::g_smem + dst, src, bytes);
-    *reinterpret_cast<uint64_t*>(acme_emu::g_smem + bar) = 1;
-    acme_emu::g_cta.progress++;
+    emu_complete_phase(bar);
 }
+// tile <-> shared memory with the descriptor's swizzle (16-byte chunks XOR-permuted by address bits 7..9),
+// zero fill on loads and clipping on stores outside the tensor -- what the TMA unit does
+__device__ __forceinline__ uint32_t emu_swizzle(const CUtensorMap* tm, uint32_t off) { return off ^ (((off >> 7) & tm->swizzle_mask) << 4); }
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, uint32_t bar) {
+    for (unsigned r = 0; r < tm->box1; r++)
+        for (unsigned c = 0; c < tm->box0; c++) {
+            const long long i0 = (long long)c0 + c, i1 = (long long)c1 + r;
+            double v = 0.0;
+            if (i0 >= 0 && i1 >= 0 && (unsigned long long)i0 < tm->dim0 && (unsigned long long)i1 < tm->dim1)
+                memcpy(&v, tm->base + (unsigned long long)i1 * tm->stride1_bytes + (unsigned long long)i0 * 8, 8);
+            memcpy(acme_emu::g_smem + dst + emu_swizzle(tm, (r * tm->box0 + c) * 8), &v, 8);
+        }
+    emu_complete_phase(bar);
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, int c0, int c1, uint32_t src) {
+    for (unsigned r = 0; r < tm->box1; r++)
+        for (unsigned c = 0; c < tm->box0; c++) {
+            const long long i0 = (long long)c0 + c, i1 = (long long)c1 + r;
+            if (i0 >= 0 && i1 >= 0 && (unsigned long long)i0 < tm->dim0 && (unsigned long long)i1 < tm->dim1)
+                memcpy(tm->base + (unsigned long long)i1 * tm->stride1_bytes + (unsigned long long)i0 * 8,
+                       acme_emu::g_smem + src + emu_swizzle(tm, (r * tm->box0 + c) * 8), 8);
+        }
+}
+__device__ __forceinline__ void bulk_commit() {}
+__device__ __forceinline__ void bulk_wait_read1() {}
+__device__ __forceinline__ void bulk_wait_read0() {}
+__device__ __forceinline__ void bulk_wait_all() {}
+__device__ __forceinline__ void fence_async_smem() {}
 #else
 // ---- TMA (bulk async copy) + mbarrier primitives, PTX ISA 8.x --------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }

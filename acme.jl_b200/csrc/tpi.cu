@@ -116,9 +116,9 @@ static cudaError_t launch_tpi(const acmeb200_model* m, const RunArgs& a, cudaStr
         }
     }
     if (m->blob_stride)
-        k_tpi<C, true><<<(unsigned)blocks, TPI_TPB, smem, stream>>>(M, a, sc, cache, maps);
+        ACME_LAUNCH((k_tpi<C, true>), (unsigned)blocks, TPI_TPB, smem, stream, M, a, sc, cache, maps);
     else
-        k_tpi<C, false><<<(unsigned)blocks, TPI_TPB, smem, stream>>>(M, a, sc, cache, maps);
+        ACME_LAUNCH((k_tpi<C, false>), (unsigned)blocks, TPI_TPB, smem, stream, M, a, sc, cache, maps);
     return cudaGetLastError();
 }
 

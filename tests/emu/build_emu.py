@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "acme.jl_b200", "csrc")
 OUT = os.path.join(HERE, "_build", "libacmeb200_emu.so")
-SOURCES = [os.path.join(CSRC, "acmeb200.cu"), os.path.join(CSRC, "rows.cu"),
+SOURCES = [os.path.join(CSRC, "acmeb200.cu"), os.path.join(CSRC, "rows.cu"), os.path.join(CSRC, "tpi.cu"),
            os.path.join(HERE, "emu_runtime.cpp"), os.path.join(HERE, "emu_stubs.cpp")]
 
 

@@ -1,6 +1,6 @@
 // Host emulation of the slice of CUDA the device library uses -- TEST INFRASTRUCTURE ONLY.
 //
-// tests/emu/build_emu.py compiles acme.jl_b200/csrc/{acmeb200,rows}.cu with g++ against THIS header
+// tests/emu/build_emu.py compiles acme.jl_b200/csrc/{acmeb200,tpi,rows}.cu with g++ against THIS header
 // (found as <cuda_runtime.h>) into tests/emu/_build/libacmeb200_emu.so, so that the kernels' logic --
 // the very source the GPU runs -- can be executed and checked against the oracle on a machine without
 // a GPU (tests/test_emu.py).  The product never loads it: acme.jl_b200/_lib.py loads
@@ -8,7 +8,8 @@
 //
 // Model: one CTA at a time; every CUDA thread is a fiber (ucontext) in one OS thread, switched only at
 // collectives, so warp-synchronous code sees exactly the lock-step semantics it relies on.  Full-mask
-// warp collectives only (what kernel_rows.cuh uses); no tensor maps (kernel_tpi.cuh is not built).
+// warp collectives only (the cooperative kernel with its sub-warp masks is not built); tensor-map tiles,
+// bulk copies and mbarrier phases are emulated synchronously (csrc/tma.cuh, cuda.h here).
 #pragma once
 #define ACME_HOST_EMU 1
 #define __CUDACC__ 1
@@ -182,4 +183,7 @@ inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
 inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent_t) { *ms = 1.0f; return cudaSuccess; }
 inline cudaError_t cudaPointerGetAttributes(cudaPointerAttributes* a, const void*) { a->type = cudaMemoryTypeUnregistered; return cudaSuccess; }
 template <class F> inline cudaError_t cudaFuncSetAttribute(F, int, int) { return cudaSuccess; }
+enum cudaDriverEntryPointQueryResult { cudaDriverEntryPointSuccess = 0, cudaDriverEntryPointSymbolNotFound = 1 };
+enum { cudaEnableDefault = 0 };
+cudaError_t cudaGetDriverEntryPoint(const char* name, void** fn, unsigned long long flags, cudaDriverEntryPointQueryResult* q);  // emu_runtime.cpp
 inline cudaError_t cudaDeviceGetAttribute(int* v, int attr, int) { *v = attr == cudaDevAttrMultiProcessorCount ? 148 : 233472; return cudaSuccess; }

@@ -1,7 +1,15 @@
 // Fiber scheduler of the host emulation (see cuda_runtime.h in this directory) -- test infrastructure.
 #include "cuda_runtime.h"
+#include "cuda.h"
 
 emu_uint3 threadIdx, blockIdx, blockDim, gridDim;
+
+cudaError_t cudaGetDriverEntryPoint(const char* name, void** fn, unsigned long long, cudaDriverEntryPointQueryResult* q) {
+    const bool ok = strcmp(name, "cuTensorMapEncodeTiled") == 0;
+    *fn = ok ? (void*)&emu_cuTensorMapEncodeTiled : nullptr;
+    *q = ok ? cudaDriverEntryPointSuccess : cudaDriverEntryPointSymbolNotFound;
+    return cudaSuccess;
+}
 
 namespace acme {
 alignas(1024) unsigned char smem_raw[256 * 1024];  // the kernels' `extern __shared__ smem_raw[]`

@@ -54,4 +54,38 @@ elif case == "failure":
                            first=[int(v) for v in ff], first_ref=[int(v) for v in o.status()[1]],
                            hist=r.stats()["iter_hist"], hist_ref=o.stats()["iter_hist"], nan=int(np.isnan(y).sum()))
         r.close()
+elif case == "tpi":
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import cases
+    # G1: the reference's doctest vector through the thread-per-instance kernel (TMA tiles, swizzle, mbarriers emulated)
+    r = BatchRunner(ex.diodeclipper(), 1, solver=HC); y = r.run(cases.sine())[:, :, 0]
+    out["g1"] = dict(kernel=r.kernel_name, n=int(y.shape[1]), first=[float(v) for v in y[0, :4]], last=[float(v) for v in y[0, -3:]],
+                     hist=r.stats()["iter_hist"][:6])
+    r.close()
+    # a batch that fills neither its last warp nor its last tile, per-instance element parameters
+    B, N = 70, 203
+    Is = 10.0 ** (-16 + 4 * np.arange(B) / 69); eta = 1 + np.arange(B) / 69
+    P = np.vstack([Is, eta, 1.8 * Is, eta])
+    u = np.asfortranarray(np.repeat(sine(N)[:, :, None], B, axis=2))
+    o = OracleModel(ex.diodeclipper(), B, params=[P], solver=H); yref = o.run(u, threads=0)
+    r = BatchRunner(ex.diodeclipper(), B, params=[P], solver=H); y = r.run(u)
+    out["clipper"] = dict(err=float(np.abs(y - yref).max() / np.abs(yref).max()), hist=r.stats()["iter_hist"][:8], hist_ref=o.stats()["iter_hist"][:8])
+    r.close()
+    # linear model, per-instance matrices: the whole-tile register path
+    base, kw, B = A.derive_sweep(lambda R: ex.sallenkey(fs=96000, r1=R, r2=R), [1e3 * (1 + k) for k in range(37)], workers=1)
+    u = np.asfortranarray(np.repeat(sine(101)[:, :, None], B, axis=2))
+    yref = OracleModel(base, B, **kw).run(u, threads=0)
+    r = BatchRunner(base, B, **kw); y = r.run(u)
+    out["linear"] = dict(kernel=r.kernel_name, err=float(np.abs(y - yref).max() / np.abs(yref).max()))
+    r.close()
+    # birdie with white noise: homotopy, learning cache; tolerance tightened on both sides for the strict criterion
+    rng = np.random.default_rng(1)
+    u = np.asfortranarray(np.clip(0.2 * rng.standard_normal((1, 400, 5)), -1, 1))
+    m = ex.birdie(vol=0.8)
+    yref = OracleModel(m, 5, solver=H, tol=1e-13).run(u, threads=0)
+    r = BatchRunner(m, 5, solver=HC, tol=1e-13); y = r.run(u)
+    peak = np.abs(yref).max()
+    out["birdie"] = dict(kernel=r.kernel_name, err=float(np.max(np.abs(y - yref) / np.maximum(np.abs(yref), 1e-3 * peak))),
+                         stored=[int(v) for v in r.cache_sizes()[0]], bad=int((r.status()[0] != 0).sum()))
+    r.close()
 print(json.dumps(out))

@@ -2,8 +2,8 @@
 
 tests/emu/ holds a host emulation of the slice of CUDA the kernels use (every CUDA thread a fiber,
 full-mask warp collectives, host memory for device memory).  tests/emu/build_emu.py compiles
-csrc/acmeb200.cu (ABI + generic kernel) and csrc/rows.cu (the warp-per-instance kernel with the LU rows
-in registers) against it with g++; these tests drive that library through the normal Python host layer
+csrc/acmeb200.cu (ABI + generic kernel), csrc/tpi.cu (thread-per-instance kernels, TMA tiles) and
+csrc/rows.cu (the warp-per-instance kernel with the LU rows in registers) against it with g++; these tests drive that library through the normal Python host layer
 (ACMEB200_LIB) in a subprocess and compare with the oracle -- so the warp-level algorithm of the CUDA
 kernel (row relabelling instead of swapping, bit-pattern pivot search, augmented right-hand side, the
 solver state machine, the rows <-> generic state conversion, per-instance matrices, failure paths) is
@@ -58,3 +58,21 @@ def test_emulated_rows_kernel_failure_semantics(emu_lib):
         o = out[solver]
         assert o["status"] == o["status_ref"] and o["first"] == o["first_ref"] and o["hist"] == o["hist_ref"]
     assert any(out["SimpleSolver"]["status"])                 # the plain solver does fail on this drive
+
+
+def test_emulated_tpi_kernel_golden_vector_and_batches(emu_lib):
+    """k_tpi -- the headline kernel -- under emulation: 2D tensor-map tiles with their swizzle, mbarrier phases,
+    hot/cold step split, learning cache.  G1 is the reference's own doctest output."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import cases
+    out = run_case(emu_lib, "tpi")
+    g = cases.golden()["G1_diodeclipper_doctest"]
+    assert out["g1"]["kernel"].startswith("tpi<diodeclipper") and out["g1"]["n"] == g["n"]
+    for got, want in zip(out["g1"]["first"], g["first"]):
+        cases.assert_printed_equal(got, want, g["printed_digits"])
+    for got, want in zip(out["g1"]["last"], g["last"]):
+        cases.assert_printed_equal(got, want, g["printed_digits"])
+    assert out["clipper"]["err"] < 1e-12 and out["clipper"]["hist"] == out["clipper"]["hist_ref"]
+    assert out["linear"]["kernel"].startswith("tpi<linear") and out["linear"]["err"] < 1e-13
+    assert out["birdie"]["kernel"].startswith("tpi<birdie") and out["birdie"]["err"] < 1e-6
+    assert out["birdie"]["bad"] == 0 and max(out["birdie"]["stored"]) > 1
