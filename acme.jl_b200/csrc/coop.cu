@@ -39,7 +39,7 @@ static cudaError_t launch_coop(const acmeb200_model* m, const RunArgs& a, cudaSt
         attr_set = true;
     }
     constexpr int GPC = COOP_TPB / L;
-    k_coop<L, P><<<(unsigned)((a.ninst + GPC - 1) / GPC), COOP_TPB, smem, stream>>>(m->dm, a);
+    ACME_LAUNCH((k_coop<L, P>), (unsigned)((a.ninst + GPC - 1) / GPC), COOP_TPB, smem, stream, m->dm, a);
     return cudaGetLastError();
 }
 

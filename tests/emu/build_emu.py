@@ -1,5 +1,5 @@
 """Builds tests/emu/_build/libacmeb200_emu.so: the device library's OWN sources (csrc/acmeb200.cu with the
-generic kernel, csrc/rows.cu with the rows-in-registers kernel) compiled with g++ against the host emulation
+generic kernel, csrc/tpi.cu, csrc/coop.cu, csrc/rows.cu) compiled with g++ against the host emulation
 of CUDA in this directory.  Test infrastructure (tests/test_emu.py); the product never loads it."""
 import os
 import subprocess
@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "acme.jl_b200", "csrc")
 OUT = os.path.join(HERE, "_build", "libacmeb200_emu.so")
-SOURCES = [os.path.join(CSRC, "acmeb200.cu"), os.path.join(CSRC, "rows.cu"), os.path.join(CSRC, "tpi.cu"),
+SOURCES = [os.path.join(CSRC, "acmeb200.cu"), os.path.join(CSRC, "rows.cu"), os.path.join(CSRC, "tpi.cu"), os.path.join(CSRC, "coop.cu"),
            os.path.join(HERE, "emu_runtime.cpp"), os.path.join(HERE, "emu_stubs.cpp")]
 
 

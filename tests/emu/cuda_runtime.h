@@ -7,8 +7,8 @@
 // libacmeb200.so and fails loudly without a CUDA device.
 //
 // Model: one CTA at a time; every CUDA thread is a fiber (ucontext) in one OS thread, switched only at
-// collectives, so warp-synchronous code sees exactly the lock-step semantics it relies on.  Full-mask
-// warp collectives only (the cooperative kernel with its sub-warp masks is not built); tensor-map tiles,
+// collectives, so warp-synchronous code sees exactly the lock-step semantics it relies on.  Warp collectives
+// synchronise the lanes of their mask (full warps, or the cooperative kernel's sub-warp groups); tensor-map tiles,
 // bulk copies and mbarrier phases are emulated synchronously (csrc/tma.cuh, cuda.h here).
 #pragma once
 #define ACME_HOST_EMU 1
@@ -47,13 +47,16 @@ constexpr int MAX_THREADS = 1024;
 struct Cta {
     int nthreads = 0, live = 0;
     unsigned warp_gen[MAX_THREADS / 32], warp_cnt[MAX_THREADS / 32], warp_live[MAX_THREADS / 32];
+    // sub-warp groups (the cooperative kernel's lanes-per-instance masks): one barrier per (warp, mask)
+    struct GroupBar { unsigned mask, gen, cnt; } group[MAX_THREADS / 32][4];
+    unsigned live_mask[MAX_THREADS / 32];
     unsigned cta_gen = 0, cta_cnt = 0;
     uint64_t slot[MAX_THREADS];
     unsigned long progress = 0;
 };
 extern Cta g_cta;
 void yield();
-void warp_barrier();
+void warp_barrier(unsigned mask = 0xffffffffu);
 void cta_barrier();
 void run_cta(const std::function<void()>& body, unsigned block, unsigned bx, unsigned grid);
 extern unsigned char* g_smem;  // dynamic shared memory of the running CTA
@@ -66,58 +69,64 @@ inline void launch(K kernel, unsigned grid, unsigned block, size_t /*smem*/, A..
 
 // ------------------------------------------------------------------ warp / CTA collectives (full mask)
 inline void __syncthreads() { acme_emu::cta_barrier(); }
-inline void __syncwarp(unsigned = 0xffffffffu) { acme_emu::warp_barrier(); }
+inline void __syncwarp(unsigned mask = 0xffffffffu) { acme_emu::warp_barrier(mask); }
 template <class T>
-inline T emu_exchange(T v, int src_lane_in_warp) {
+inline T emu_exchange(T v, int src_lane_in_warp, unsigned mask = 0xffffffffu) {
     uint64_t bits = 0;
     static_assert(sizeof(T) <= 8, "shuffle of at most 64 bits");
     memcpy(&bits, &v, sizeof(T));
     const unsigned tid = threadIdx.x;
     acme_emu::g_cta.slot[tid] = bits;
-    acme_emu::warp_barrier();
+    acme_emu::warp_barrier(mask);
     const uint64_t r = acme_emu::g_cta.slot[(tid & ~31u) | (unsigned)(src_lane_in_warp & 31)];
-    acme_emu::warp_barrier();
+    acme_emu::warp_barrier(mask);
     T out;
     memcpy(&out, &r, sizeof(T));
     return out;
 }
 template <class T>
-inline T __shfl_sync(unsigned, T v, int src, int width = 32) {
+inline T __shfl_sync(unsigned mask, T v, int src, int width = 32) {
     const int lane = threadIdx.x & 31;
-    return emu_exchange(v, (lane & ~(width - 1)) | (src & (width - 1)));
+    return emu_exchange(v, (lane & ~(width - 1)) | (src & (width - 1)), mask);
 }
 template <class T>
-inline T __shfl_xor_sync(unsigned, T v, int mask, int width = 32) {
+inline T __shfl_xor_sync(unsigned mask, T v, int xr, int width = 32) {
     const int lane = threadIdx.x & 31;
-    return emu_exchange(v, (lane & ~(width - 1)) | ((lane ^ mask) & (width - 1)));
+    return emu_exchange(v, (lane & ~(width - 1)) | ((lane ^ xr) & (width - 1)), mask);
 }
 template <class F>
-inline unsigned emu_reduce(unsigned v, F f) {
-    const unsigned tid = threadIdx.x;
+inline unsigned emu_reduce(unsigned mask, unsigned v, F f) {  // over the live lanes of `mask`
+    const unsigned tid = threadIdx.x, base = tid & ~31u;
     acme_emu::g_cta.slot[tid] = v;
-    acme_emu::warp_barrier();
-    const unsigned base = tid & ~31u;
-    const unsigned n = acme_emu::g_cta.warp_live[tid >> 5];
-    unsigned r = (unsigned)acme_emu::g_cta.slot[base];
-    for (unsigned l = 1; l < n; l++) r = f(r, (unsigned)acme_emu::g_cta.slot[base + l]);
-    acme_emu::warp_barrier();
-    return r;
-}
-inline unsigned __reduce_max_sync(unsigned, unsigned v) { return emu_reduce(v, [](unsigned a, unsigned b) { return a > b ? a : b; }); }
-inline unsigned __reduce_min_sync(unsigned, unsigned v) { return emu_reduce(v, [](unsigned a, unsigned b) { return a < b ? a : b; }); }
-inline unsigned __reduce_add_sync(unsigned, unsigned v) { return emu_reduce(v, [](unsigned a, unsigned b) { return a + b; }); }
-inline unsigned __ballot_sync(unsigned, int pred) {
-    const unsigned tid = threadIdx.x;
-    acme_emu::g_cta.slot[tid] = pred ? 1u : 0u;
-    acme_emu::warp_barrier();
+    acme_emu::warp_barrier(mask);
+    const unsigned m = mask & acme_emu::g_cta.live_mask[tid >> 5];
     unsigned r = 0;
-    for (unsigned l = 0; l < 32 && (tid & ~31u) + l < (unsigned)acme_emu::g_cta.nthreads; l++)
-        r |= (unsigned)acme_emu::g_cta.slot[(tid & ~31u) + l] << l;
-    acme_emu::warp_barrier();
+    bool first = true;
+    for (unsigned l = 0; l < 32; l++)
+        if (m >> l & 1u) {
+            const unsigned x = (unsigned)acme_emu::g_cta.slot[base + l];
+            r = first ? x : f(r, x);
+            first = false;
+        }
+    acme_emu::warp_barrier(mask);
     return r;
 }
-inline int __all_sync(unsigned m, int pred) { return emu_reduce(pred ? 1u : 0u, [](unsigned a, unsigned b) { return a & b; }) != 0; }
-inline int __any_sync(unsigned m, int pred) { return emu_reduce(pred ? 1u : 0u, [](unsigned a, unsigned b) { return a | b; }) != 0; }
+inline unsigned __reduce_max_sync(unsigned m, unsigned v) { return emu_reduce(m, v, [](unsigned a, unsigned b) { return a > b ? a : b; }); }
+inline unsigned __reduce_min_sync(unsigned m, unsigned v) { return emu_reduce(m, v, [](unsigned a, unsigned b) { return a < b ? a : b; }); }
+inline unsigned __reduce_add_sync(unsigned m, unsigned v) { return emu_reduce(m, v, [](unsigned a, unsigned b) { return a + b; }); }
+inline unsigned __ballot_sync(unsigned mask, int pred) {
+    const unsigned tid = threadIdx.x, base = tid & ~31u;
+    acme_emu::g_cta.slot[tid] = pred ? 1u : 0u;
+    acme_emu::warp_barrier(mask);
+    const unsigned m = mask & acme_emu::g_cta.live_mask[tid >> 5];
+    unsigned r = 0;
+    for (unsigned l = 0; l < 32; l++)
+        if (m >> l & 1u) r |= (unsigned)acme_emu::g_cta.slot[base + l] << l;
+    acme_emu::warp_barrier(mask);
+    return r;
+}
+inline int __all_sync(unsigned m, int pred) { return emu_reduce(m, pred ? 1u : 0u, [](unsigned a, unsigned b) { return a & b; }) != 0; }
+inline int __any_sync(unsigned m, int pred) { return emu_reduce(m, pred ? 1u : 0u, [](unsigned a, unsigned b) { return a | b; }) != 0; }
 
 // ------------------------------------------------------------------ device intrinsics
 inline int __double2hiint(double v) { int64_t b; memcpy(&b, &v, 8); return (int)(b >> 32); }

@@ -54,6 +54,27 @@ elif case == "failure":
                            first=[int(v) for v in ff], first_ref=[int(v) for v in o.status()[1]],
                            hist=r.stats()["iter_hist"], hist_ref=o.stats()["iter_hist"], nan=int(np.isnan(y).sum()))
         r.close()
+elif case == "coop":
+    # the cooperative kernel: one warp per instance (compile-time superover shape) against the oracle and, bit for bit,
+    # against the rows-in-registers kernel; sub-warp groups of 16 lanes with runtime dimensions on a model with three
+    # non-linear sub-problems (the "simplified superover" of runtests.jl:751-756)
+    m = ex.superover()
+    B, N = 2, 40
+    u = np.zeros((4, N, B), order="F"); u[0] = sine(N)[0][:, None]; u[1] = np.array([0.3, 0.8])[None, :]; u[2] = 0.5; u[3] = 1.0
+    o = OracleModel(m, B, solver=HC); yref = o.run(u, threads=0)
+    rr = BatchRunner(m, B, solver=HC, kernel="rows"); yr = rr.run(u)
+    r = BatchRunner(m, B, solver=HC, kernel="coop"); y = r.run(u)
+    out["static"] = dict(kernel=r.kernel_name, err=float(np.abs(y - yref).max() / np.abs(yref).max()), equals_rows=bool(np.array_equal(y, yr)),
+                         hist_equals_rows=r.stats()["iter_hist"] == rr.stats()["iter_hist"])
+    r.close(); rr.close()
+    ms = A.DiscreteModel(ex.superover_circuit(1.0, 1.0, 1.0, vb_source=True), 1 / 44100)
+    u1 = sine(60)
+    o = OracleModel(ms, 1, solver=H); yref = o.run(u1, threads=0)
+    r = BatchRunner(ms, 40, solver=H, kernel="coop"); y = r.run(u1)
+    out["multisub"] = dict(kernel=r.kernel_name, nsub=len(ms.subs), err=float(np.abs(y[:, :, 0] - yref[:, :, 0]).max() / np.abs(yref).max()),
+                           all_instances_equal=bool(np.all(y == y[:, :, :1])), hist=r.stats()["iter_hist"][:8],
+                           hist_ref=[40 * v for v in o.stats()["iter_hist"][:8]])
+    r.close()
 elif case == "tpi":
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import cases

@@ -2,8 +2,9 @@
 
 tests/emu/ holds a host emulation of the slice of CUDA the kernels use (every CUDA thread a fiber,
 full-mask warp collectives, host memory for device memory).  tests/emu/build_emu.py compiles
-csrc/acmeb200.cu (ABI + generic kernel), csrc/tpi.cu (thread-per-instance kernels, TMA tiles) and
-csrc/rows.cu (the warp-per-instance kernel with the LU rows in registers) against it with g++; these tests drive that library through the normal Python host layer
+csrc/acmeb200.cu (ABI + generic kernel), csrc/tpi.cu (thread-per-instance kernels, TMA tiles), csrc/coop.cu
+(lanes-per-instance kernel) and csrc/rows.cu (the warp-per-instance kernel with the LU rows in registers)
+against it with g++; these tests drive that library through the normal Python host layer
 (ACMEB200_LIB) in a subprocess and compare with the oracle -- so the warp-level algorithm of the CUDA
 kernel (row relabelling instead of swapping, bit-pattern pivot search, augmented right-hand side, the
 solver state machine, the rows <-> generic state conversion, per-instance matrices, failure paths) is
@@ -76,3 +77,13 @@ def test_emulated_tpi_kernel_golden_vector_and_batches(emu_lib):
     assert out["linear"]["kernel"].startswith("tpi<linear") and out["linear"]["err"] < 1e-13
     assert out["birdie"]["kernel"].startswith("tpi<birdie") and out["birdie"]["err"] < 1e-6
     assert out["birdie"]["bad"] == 0 and max(out["birdie"]["stored"]) > 1
+
+
+def test_emulated_cooperative_kernel(emu_lib):
+    """k_coop under emulation, including its sub-warp masks (two 16-lane groups per warp with independent control flow)"""
+    out = run_case(emu_lib, "coop")
+    st = out["static"]
+    assert st["kernel"].startswith("coop<32") and st["err"] < 1e-6 and st["equals_rows"] and st["hist_equals_rows"]
+    ms = out["multisub"]
+    assert ms["kernel"].startswith("coop<16") and "runtime dims" in ms["kernel"] and ms["nsub"] == 3
+    assert ms["err"] < 1e-12 and ms["all_instances_equal"] and ms["hist"] == ms["hist_ref"]
