@@ -25,7 +25,7 @@
  * the waveforms of sallenkey/birdie/superover are NOT pinned by the reference's
  * own tests (they say "TODO: further validate y").
  *
- * Build: gcc -O2 -ffp-contract=off -pthread -shared -fPIC (see oracle/Makefile).
+ * Build: gcc -O3 -ffp-contract=off -pthread -shared -fPIC (see oracle/Makefile).
  */
 #include <math.h>
 #include <stdint.h>
