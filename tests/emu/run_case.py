@@ -92,6 +92,14 @@ elif case == "tpi":
     r = BatchRunner(ex.diodeclipper(), B, params=[P], solver=H); y = r.run(u)
     out["clipper"] = dict(err=float(np.abs(y - yref).max() / np.abs(yref).max()), hist=r.stats()["iter_hist"][:8], hist_ref=o.stats()["iter_hist"][:8])
     r.close()
+    # the host-buffer pipeline (time chunks, state carried from chunk to chunk): 1 MiB staging chunks = 3 chunks here
+    N2 = 5003
+    u2 = np.asfortranarray(np.repeat(sine(N2)[:, :, None], B, axis=2))
+    r = BatchRunner(ex.diodeclipper(), B, params=[P], solver=HC); y_one = r.run(u2); r.close()
+    os.environ["ACMEB200_CHUNK_MB"] = "1"
+    r = BatchRunner(ex.diodeclipper(), B, params=[P], solver=HC); y_chunked = r.run(u2); launches = r.launch_count; r.close()
+    del os.environ["ACMEB200_CHUNK_MB"]
+    out["chunks"] = dict(equal=bool(np.array_equal(y_one, y_chunked)), launches=int(launches))
     # linear model, per-instance matrices: the whole-tile register path
     base, kw, B = A.derive_sweep(lambda R: ex.sallenkey(fs=96000, r1=R, r2=R), [1e3 * (1 + k) for k in range(37)], workers=1)
     u = np.asfortranarray(np.repeat(sine(101)[:, :, None], B, axis=2))

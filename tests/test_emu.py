@@ -74,6 +74,7 @@ def test_emulated_tpi_kernel_golden_vector_and_batches(emu_lib):
     for got, want in zip(out["g1"]["last"], g["last"]):
         cases.assert_printed_equal(got, want, g["printed_digits"])
     assert out["clipper"]["err"] < 1e-12 and out["clipper"]["hist"] == out["clipper"]["hist_ref"]
+    assert out["chunks"]["equal"] and out["chunks"]["launches"] >= 4   # init + 3 time chunks, bit-identical to one chunk
     assert out["linear"]["kernel"].startswith("tpi<linear") and out["linear"]["err"] < 1e-13
     assert out["birdie"]["kernel"].startswith("tpi<birdie") and out["birdie"]["err"] < 1e-6
     assert out["birdie"]["bad"] == 0 and max(out["birdie"]["stored"]) > 1
