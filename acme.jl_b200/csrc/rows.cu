@@ -1,6 +1,8 @@
 // Warp-per-instance kernel with the LU rows in registers (kernel_rows.cuh): launchers.
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+
 #include "hostmodel.h"
 #include "kernel_rows.cuh"
 
@@ -31,7 +33,9 @@ template <class S>
 static cudaError_t launch_rows_shape(const acmeb200_model* m, const RunArgs& a, cudaStream_t stream) {
     // small batches: one warp per CTA spreads the instances evenly over the SMs and may use 255
     // registers (8 resident warps per SM); larger batches need the 16 warps per SM of the 128-register build
-    const bool small = a.ninst <= 148 * 8;
+    int64_t small_max = 148 * 8;
+    if (const char* e = getenv("ACMEB200_ROWS_SMALL_MAX")) small_max = atoll(e);  // tuning / test knob: 0 forces the 4-warp build
+    const bool small = a.ninst <= small_max;
     if (m->blob_stride) return small ? launch_rows<S, 1, true>(m, a, stream) : launch_rows<S, 4, true>(m, a, stream);
     return small ? launch_rows<S, 1, false>(m, a, stream) : launch_rows<S, 4, false>(m, a, stream);
 }

@@ -42,6 +42,23 @@ elif case == "baked_perinst":
     out.update(kernel=r.kernel_name, err=float(np.abs(y - yref).max() / np.abs(yref).max()), hist=r.stats()["iter_hist"],
                hist_ref=o.stats()["iter_hist"])
     r.close()
+elif case == "rows_4warp":
+    # the 4-warp build of the rows kernel (normally chosen from 1185 instances per GPU), forced at a small batch:
+    # a ragged last CTA, shared and per-instance matrices
+    os.environ["ACMEB200_ROWS_SMALL_MAX"] = "0"
+    base, kw, B = A.derive_sweep(lambda d, t: ex.superover(d, t, 1.0), [(0.15 + 0.12 * k, 0.3 + 0.1 * k) for k in range(6)], workers=1)
+    u = sine(40)
+    yref = OracleModel(base, B, solver=HC, **kw).run(u, threads=0)
+    r = BatchRunner(base, B, solver=HC, **kw); y = r.run(u)
+    out["perinst"] = dict(kernel=r.kernel_name, err=float(np.abs(y - yref).max() / np.abs(yref).max()), samples=int(r.stats()["samples"]))
+    r.close()
+    m = ex.superover()
+    B, N = 5, 30
+    us = np.zeros((4, N, B), order="F"); us[0] = sine(N)[0][:, None]; us[1] = ((np.arange(B) + 0.5) / B)[None, :]; us[2] = 0.5; us[3] = 1.0
+    yref = OracleModel(m, B, solver=H).run(us, threads=0)
+    r = BatchRunner(m, B, solver=H); y = r.run(us)
+    out["shared"] = dict(kernel=r.kernel_name, err=float(np.abs(y - yref).max() / np.abs(yref).max()), samples=int(r.stats()["samples"]))
+    r.close()
 elif case == "failure":
     m = ex.superover()
     B, N = 2, 25

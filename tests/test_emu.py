@@ -53,6 +53,12 @@ def test_emulated_rows_kernel_per_instance_matrices(emu_lib):
     assert "per-instance matrices" in out["kernel"] and out["err"] < 1e-12 and out["hist"] == out["hist_ref"]
 
 
+def test_emulated_rows_kernel_four_warp_build(emu_lib):
+    out = run_case(emu_lib, "rows_4warp")
+    assert "per-instance matrices" in out["perinst"]["kernel"] and out["perinst"]["err"] < 1e-6 and out["perinst"]["samples"] == 6 * 40
+    assert out["shared"]["kernel"].startswith("rows<") and out["shared"]["err"] < 1e-12 and out["shared"]["samples"] == 5 * 30
+
+
 def test_emulated_rows_kernel_failure_semantics(emu_lib):
     out = run_case(emu_lib, "failure")
     for solver in (H, "SimpleSolver"):
