@@ -94,3 +94,18 @@ def test_emulated_cooperative_kernel(emu_lib):
     ms = out["multisub"]
     assert ms["kernel"].startswith("coop<16") and "runtime dims" in ms["kernel"] and ms["nsub"] == 3
     assert ms["err"] < 1e-12 and ms["all_instances_equal"] and ms["hist"] == ms["hist_ref"]
+
+
+def test_gpu_parity_suite_subset_under_emulation(emu_lib):
+    """The `-m gpu` parity tests themselves, driven against the emulated library: the known-answer tests of
+    runtests.jl (K3-K9), frozen k-d tree caches, batched steady state, unaligned/odd streams (the synchronous
+    tile path), per-instance matrices of a non-linear model, size checks.  (The long-running ones -- full
+    waveforms on the lane-parallel kernels -- stay GPU-only.)"""
+    sel = ("K4 or K5 or K6 or K7 or K8 or K9 or empty_circuits or io_size or frozen_cache or steadystate_on_device or "
+           "run_bang or odd_lengths or per_instance_matrices_nonlinear or (K3 and not coop)")
+    env = dict(os.environ, ACMEB200_LIB=emu_lib)
+    res = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_parity.py"), "-m", "gpu", "-q", "-x",
+                          "-p", "no:cacheprovider", "-k", sel], env=env, capture_output=True, text=True, timeout=900, cwd=ROOT)
+    tail = res.stdout.strip().splitlines()[-1] if res.stdout.strip() else res.stderr[-500:]
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-1000:]
+    assert " passed" in tail and int(tail.split(" passed")[0].split()[-1]) >= 20, tail
