@@ -3,7 +3,7 @@ oracle on a bounded sample beside each.  Writes a markdown table (stdout) -- the
 DESIGN.md section 7 / profiles/configs_r1.md.  Not the driver's bench (that is bench.py = config 2).
 CONFIGS=3,5 restricts the run; NO_CPU=1 skips the oracle columns."""
 import json, os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 from acme_jl_b200 import BatchRunner, examples as ex
 from oracle.oracle import OracleModel

@@ -1,7 +1,7 @@
 """quick GPU check of the rows-in-registers kernel: parity against the oracle and the cooperative
 kernel on superover, iteration statistics, timing at B=1024 and B=8192"""
 import json, os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 from acme_jl_b200 import BatchRunner, examples as ex
 from oracle.oracle import OracleModel

@@ -1,5 +1,5 @@
 """device acme_exp vs the CUDA library exp: exercised through the diode law: run the TPI kernel
-(acme_exp) against the oracle; plus a direct sweep through a tiny nvcc-built test kernel."""
+(acme_exp); here: a direct sweep through a tiny nvcc-built test kernel."""
 import subprocess, os, sys
 src = r'''
 #include <cstdio>
