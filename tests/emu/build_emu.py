@@ -9,7 +9,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "acme.jl_b200", "csrc")
 OUT = os.path.join(HERE, "_build", "libacmeb200_emu.so")
 SOURCES = [os.path.join(CSRC, "acmeb200.cu"), os.path.join(CSRC, "rows.cu"), os.path.join(CSRC, "tpi.cu"), os.path.join(CSRC, "coop.cu"),
-           os.path.join(HERE, "emu_runtime.cpp"), os.path.join(HERE, "emu_stubs.cpp")]
+           os.path.join(HERE, "emu_runtime.cpp")]
 
 
 def stale() -> bool:
