@@ -223,34 +223,46 @@ class BatchRunner:
         from .model import DiscreteModel, SubProblem
         m = self.model
         B = self.batch
-        if getattr(self, "_has_overrides", False) and m.subs:
-            raise NotImplementedError("steadystate with per-instance matrices of a non-linear model")
         u = np.zeros((m.nu, B)) if u is None else np.broadcast_to(
             np.asarray(u, dtype=np.float64).reshape(m.nu, -1), (m.nu, B)).copy()
         ov = getattr(self, "_overrides", None) or {}
+
+        def stk(name, default):
+            """matrix `name` as a stack (Bk, rows, cols) with Bk = B for a per-instance override (this
+            runner's slice of it), else 1"""
+            arr = np.asarray(ov[name], dtype=np.float64) if name in ov else np.asarray(default, dtype=np.float64)
+            base = np.asarray(default)
+            if arr.ndim == base.ndim + 1:
+                arr = arr[..., self.first:self.first + B] if arr.shape[-1] != B else arr
+                arr = np.moveaxis(arr, -1, 0)
+            else:
+                arr = arr[None]
+            return arr.reshape(arr.shape[0], *(base.shape if base.ndim == 2 else (base.shape[0], 1)))
+
+        A_, B_, C_, X0 = stk("a", m.a), stk("b", m.b), stk("c", m.c), stk("x0", m.x0)
+        IAinv = np.linalg.inv(np.eye(m.nx)[None] - A_) if m.nx else np.zeros((1, 0, 0))
+        uB = u.T[:, :, None]                                        # (B, nu, 1)
         if not m.subs:  # linear: x = (I - a) \ (b u + x0), possibly per-instance matrices
-            a = np.asarray(ov.get("a", m.a)).reshape(m.nx, m.nx, -1)
-            b = np.asarray(ov.get("b", m.b)).reshape(m.nx, m.nu, -1)
-            x0 = np.asarray(ov.get("x0", m.x0)).reshape(m.nx, -1)
-            x = np.empty((m.nx, B))
-            for k in range(B):
-                kk = lambda arr: arr[..., k if arr.shape[-1] > 1 else 0]
-                x[:, k] = np.linalg.solve(np.eye(m.nx) - kk(a), kk(b) @ u[:, k] + kk(x0))
-            return x
-        IAinv = np.linalg.inv(np.eye(m.nx) - m.a) if m.nx else np.zeros((0, 0))
+            return (IAinv @ (B_ @ uB + X0))[:, :, 0].T if m.nx else np.zeros((0, B))
         nnt = m.nn_total
         steady_z = np.zeros((nnt, B))
         zoff = 0
         for i, s in enumerate(m.subs):
-            dqIA = s.dq @ IAinv if m.nx else s.dq
-            Eu = s.pexp @ (dqIA @ m.b + s.eq) if m.nx else s.pexp @ s.eq
-            Ez = s.pexp @ ((dqIA @ m.c if m.nx else 0.0) + s.fqprev)
-            const = s.q0 + (s.pexp @ dqIA @ m.x0 if m.nx else 0.0)
-            fq = (s.pexp @ dqIA @ m.c[:, zoff:zoff + s.nn] if m.nx else 0.0) + s.fq
+            dq, eq, fqprev = stk(f"dq{i}", s.dq), stk(f"eq{i}", s.eq), stk(f"fqprev{i}", s.fqprev)
+            pexp, q0, fqm = stk(f"pexp{i}", s.pexp), stk(f"q0{i}", s.q0), stk(f"fq{i}", s.fq)
+            dqIA = dq @ IAinv if m.nx else dq
+            Eu = pexp @ (dqIA @ B_ + eq) if m.nx else pexp @ eq
+            Ez = pexp @ ((dqIA @ C_ if m.nx else 0.0) + fqprev)
+            const = q0 + (pexp @ dqIA @ X0 if m.nx else 0.0)
+            fq = (pexp @ dqIA @ C_[:, :, zoff:zoff + s.nn] if m.nx else 0.0) + fqm
             nin = m.nu + nnt + 1
+            bk = max(Eu.shape[0], Ez.shape[0], const.shape[0], fq.shape[0])   # 1: every matrix shared
+            eq_d = np.concatenate([np.broadcast_to(Eu, (bk,) + Eu.shape[1:]), np.broadcast_to(Ez, (bk,) + Ez.shape[1:]),
+                                   np.broadcast_to(const, (bk,) + const.shape[1:])], axis=2)   # (bk, nq, nin)
+            fq_d = np.broadcast_to(fq, (bk,) + fq.shape[1:])
             sub = SubProblem(nn=s.nn, nq=s.nq, np_=s.nq, dq=np.zeros((s.nq, 0)),
-                             eq=np.hstack([Eu, Ez, const.reshape(-1, 1)]), fqprev=np.zeros((s.nq, s.nn)),
-                             pexp=np.eye(s.nq), q0=np.zeros(s.nq), fq=fq, init_z=np.zeros(s.nn), elems=s.elems)
+                             eq=eq_d[0], fqprev=np.zeros((s.nq, s.nn)),
+                             pexp=np.eye(s.nq), q0=np.zeros(s.nq), fq=fq_d[0], init_z=np.zeros(s.nn), elems=s.elems)
             sm = DiscreteModel.from_matrices(a=np.zeros((0, 0)), b=np.zeros((0, nin)), c=np.zeros((0, s.nn)),
                                              x0=np.zeros(0), dy=np.zeros((s.nn, 0)), ey=np.zeros((s.nn, nin)),
                                              fy=np.eye(s.nn), y0=np.zeros(s.nn), subs=[sub],
@@ -258,7 +270,10 @@ class BatchRunner:
             params = None
             if getattr(self, "_params", None) is not None and self._params[i] is not None:
                 params = [self._params[i][:, self.first:self.first + B]]
-            r = BatchRunner(sm, B, params=params, tol=1e-15)
+            sov = None
+            if bk > 1:  # per-instance matrices: the derived model has per-instance eq / fq
+                sov = {"eq0": np.asfortranarray(np.moveaxis(eq_d, 0, -1)), "fq0": np.asfortranarray(np.moveaxis(fq_d, 0, -1))}
+            r = BatchRunner(sm, B, params=params, overrides=sov, tol=1e-15)
             try:
                 uin = np.asfortranarray(np.vstack([u, steady_z, np.ones((1, B))]).reshape(nin, 1, B))
                 z = r.run(uin, check_status=False)[:, 0, :]
@@ -268,8 +283,10 @@ class BatchRunner:
                 r.close()
             steady_z[zoff:zoff + s.nn] = z
             zoff += s.nn
-        rhs = m.b @ u + m.c @ steady_z + m.x0.reshape(-1, 1)
-        return IAinv @ rhs if m.nx else np.zeros((0, B))
+        if not m.nx:
+            return np.zeros((0, B))
+        rhs = B_ @ uB + C_ @ steady_z.T[:, :, None] + X0
+        return (IAinv @ rhs)[:, :, 0].T
 
     def steadystate_(self, u=None) -> np.ndarray:
         """``steadystate!``: also makes it the current state of every instance (ACME.jl:499-503)."""

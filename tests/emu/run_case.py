@@ -59,6 +59,25 @@ elif case == "rows_4warp":
     r = BatchRunner(m, B, solver=H); y = r.run(us)
     out["shared"] = dict(kernel=r.kernel_name, err=float(np.abs(y - yref).max() / np.abs(yref).max()), samples=int(r.stats()["samples"]))
     r.close()
+elif case == "steady":
+    # batched steadystate (ACME.jl:474-497) through the ABI: shared matrices, per-instance matrices of a non-linear
+    # model (derived zero-state model with per-instance eq/fq), per-instance matrices of a linear model
+    m = ex.birdie(vol=0.8)
+    r = BatchRunner(m, 3); xs = r.steadystate(np.array([[0.0, 0.1, 0.3]])); r.close()
+    out["shared"] = max(float(np.abs(xs[:, b] - m.steadystate([uv])).max()) for b, uv in enumerate([0.0, 0.1, 0.3]))
+    pts = [(0.2, 0.5), (0.7, 0.4), (0.45, 0.9)]
+    base, kw, B = A.derive_sweep(lambda d, t: ex.superover(d, t, 1.0), pts, workers=1)
+    r = BatchRunner(base, B, **kw); xs = r.steadystate_(np.array([[0.0, 0.05, -0.02]]))
+    out["perinst"] = max(float(np.abs(xs[:, b] - ex.superover(*p, 1.0).steadystate([uv])).max())
+                         for b, (p, uv) in enumerate(zip(pts, [0.0, 0.05, -0.02])))
+    # started from its steady state with that constant input, every instance stays there (checksteady!, runtests.jl:664-682)
+    y = r.run(np.asfortranarray(np.repeat(np.array([0.0, 0.05, -0.02])[None, None, :], 50, axis=1)))
+    out["drift"] = float(np.abs(r.x - xs).max()); out["y_span"] = float(np.abs(y - y[:, :1, :]).max())
+    r.close()
+    Rs = [1e3, 5e3, 2e4]
+    base, kw, B = A.derive_sweep(lambda R: ex.sallenkey(fs=96000, r1=R, r2=R), Rs, workers=1)
+    r = BatchRunner(base, B, **kw); xs = r.steadystate(np.array([[0.3, 0.3, 0.3]])); r.close()
+    out["linear"] = max(float(np.abs(xs[:, b] - ex.sallenkey(fs=96000, r1=R, r2=R).steadystate([0.3])).max()) for b, R in enumerate(Rs))
 elif case == "failure":
     m = ex.superover()
     B, N = 2, 25

@@ -59,6 +59,15 @@ def test_emulated_rows_kernel_four_warp_build(emu_lib):
     assert out["shared"]["kernel"].startswith("rows<") and out["shared"]["err"] < 1e-12 and out["shared"]["samples"] == 5 * 30
 
 
+def test_batched_steadystate_with_per_instance_matrices(emu_lib):
+    """steadystate / steadystate! for a sweep of baked-in element values (host logic + the ABI, here against the
+    emulated library): equals each instance's own host-side steadystate, and the instances stay there"""
+    out = run_case(emu_lib, "steady")
+    assert out["shared"] < 1e-10 and out["perinst"] < 1e-10 and out["linear"] < 1e-10
+    assert out["drift"] < 1e-9          # checksteady! (runtests.jl:664-682) compares the state
+    assert out["y_span"] < 1e-4          # the output only up to the Newton stopping rule (res < 1e-10 A at high-impedance nodes)
+
+
 def test_emulated_rows_kernel_failure_semantics(emu_lib):
     out = run_case(emu_lib, "failure")
     for solver in (H, "SimpleSolver"):

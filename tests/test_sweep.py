@@ -90,3 +90,19 @@ def test_config4_alternative_reading_baked_pots():
         y1 = BatchRunner(build_so(*pts[b]), 1, solver=H).run(u)
         assert np.max(np.abs(y1[:, :, 0] - y[:, :, b])) <= 1e-9 * peak
     r.close()
+
+
+@pytest.mark.gpu
+def test_steadystate_of_a_baked_sweep():
+    """batched steadystate! with per-instance matrices of a non-linear model, on the device"""
+    from acme_jl_b200 import BatchRunner
+    pts = [(0.2, 0.5), (0.7, 0.4), (0.45, 0.9)]
+    base, kw, B = A.derive_sweep(build_so, pts, workers=1)
+    r = BatchRunner(base, B, **kw)
+    udc = np.array([[0.0, 0.05, -0.02]])
+    xs = r.steadystate_(udc)
+    for b, p in enumerate(pts):
+        assert np.allclose(xs[:, b], build_so(*p).steadystate([udc[0, b]]), rtol=1e-8, atol=1e-11)
+    r.run(np.asfortranarray(np.repeat(udc[:, None, :], 64, axis=1)))
+    assert np.abs(r.x - xs).max() < 1e-9
+    r.close()
