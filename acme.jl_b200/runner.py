@@ -215,35 +215,41 @@ class BatchRunner:
 
     # ------------------------------------------------------------------ steady state (batched)
     def steadystate(self, u=None) -> np.ndarray:
+        """Batched ``steadystate(model, u)`` (ACME.jl:474-497); see ``_steady``.  Returns x of shape (nx, B)."""
+        return self._steady(u)[0]
+
+    def _stack(self, name, default):
+        """matrix `name` as a stack (Bk, rows, cols) with Bk = B for a per-instance override (this
+        runner's slice of it), else 1"""
+        ov = getattr(self, "_overrides", None) or {}
+        B = self.batch
+        arr = np.asarray(ov[name], dtype=np.float64) if name in ov else np.asarray(default, dtype=np.float64)
+        base = np.asarray(default)
+        if arr.ndim == base.ndim + 1:
+            arr = arr[..., self.first:self.first + B] if arr.shape[-1] != B else arr
+            arr = np.moveaxis(arr, -1, 0)
+        else:
+            arr = arr[None]
+        return arr.reshape(arr.shape[0], *(base.shape if base.ndim == 2 else (base.shape[0], 1)))
+
+    def _steady(self, u=None):
         """Batched ``steadystate(model, u)`` (ACME.jl:474-497): the state every instance settles to
         for a constant input ``u`` (``(nu,)`` shared or ``(nu, B)`` per instance).  The non-linear
         part -- one Newton/homotopy solve per sub-problem with the state recursion folded into
         ``fq``/``q0`` and tolerance 1e-15 -- runs on the device through the same C ABI: a derived
-        zero-state model whose single "sample" is that solve.  Returns x of shape (nx, B)."""
+        zero-state model whose single "sample" is that solve.  Returns (x (nx, B), z (nn_total, B),
+        u (nu, B))."""
         from .model import DiscreteModel, SubProblem
         m = self.model
         B = self.batch
         u = np.zeros((m.nu, B)) if u is None else np.broadcast_to(
             np.asarray(u, dtype=np.float64).reshape(m.nu, -1), (m.nu, B)).copy()
-        ov = getattr(self, "_overrides", None) or {}
-
-        def stk(name, default):
-            """matrix `name` as a stack (Bk, rows, cols) with Bk = B for a per-instance override (this
-            runner's slice of it), else 1"""
-            arr = np.asarray(ov[name], dtype=np.float64) if name in ov else np.asarray(default, dtype=np.float64)
-            base = np.asarray(default)
-            if arr.ndim == base.ndim + 1:
-                arr = arr[..., self.first:self.first + B] if arr.shape[-1] != B else arr
-                arr = np.moveaxis(arr, -1, 0)
-            else:
-                arr = arr[None]
-            return arr.reshape(arr.shape[0], *(base.shape if base.ndim == 2 else (base.shape[0], 1)))
-
+        stk = self._stack
         A_, B_, C_, X0 = stk("a", m.a), stk("b", m.b), stk("c", m.c), stk("x0", m.x0)
         IAinv = np.linalg.inv(np.eye(m.nx)[None] - A_) if m.nx else np.zeros((1, 0, 0))
         uB = u.T[:, :, None]                                        # (B, nu, 1)
         if not m.subs:  # linear: x = (I - a) \ (b u + x0), possibly per-instance matrices
-            return (IAinv @ (B_ @ uB + X0))[:, :, 0].T if m.nx else np.zeros((0, B))
+            return ((IAinv @ (B_ @ uB + X0))[:, :, 0].T if m.nx else np.zeros((0, B))), np.zeros((0, B)), u
         nnt = m.nn_total
         steady_z = np.zeros((nnt, B))
         zoff = 0
@@ -284,15 +290,77 @@ class BatchRunner:
             steady_z[zoff:zoff + s.nn] = z
             zoff += s.nn
         if not m.nx:
-            return np.zeros((0, B))
+            return np.zeros((0, B)), steady_z, u
         rhs = B_ @ uB + C_ @ steady_z.T[:, :, None] + X0
-        return (IAinv @ rhs)[:, :, 0].T
+        return (IAinv @ rhs)[:, :, 0].T, steady_z, u
 
     def steadystate_(self, u=None) -> np.ndarray:
         """``steadystate!``: also makes it the current state of every instance (ACME.jl:499-503)."""
         x = self.steadystate(u)
         self.x = x
         return x
+
+    # ------------------------------------------------------------------ linearize (batched)
+    def linearize(self, usteady=None, **runner_kw) -> "BatchRunner":
+        """Batched ``linearize(model, usteady)`` (ACME.jl:505-550): the small-signal linear model of
+        every instance around its own steady state, as a new runner of B linear instances (which the
+        linear path of the sample loop then runs at memory speed).  The steady states come from the
+        device (``_steady``); the Jacobians at those points and the chain rule through the
+        sub-problems (ACME.jl:520-546) are host work, done once per instance.  Instances that share
+        everything give a runner without per-instance matrices."""
+        from dataclasses import replace
+        from . import hostsolve
+        from .model import DiscreteModel
+        m, B = self.model, self.batch
+        xs, zs, u = self._steady(usteady)
+        stk = self._stack
+        bc = lambda arr: np.broadcast_to(arr, (B,) + arr.shape[1:])
+        a, b, c, x0 = (bc(stk(n, d)).copy() for n, d in (("a", m.a), ("b", m.b), ("c", m.c), ("x0", m.x0)))
+        dy, ey, fy, y0 = (bc(stk(n, d)).copy() for n, d in (("dy", m.dy), ("ey", m.ey), ("fy", m.fy), ("y0", m.y0)))
+        xB, uB, zB = xs.T[:, :, None], u.T[:, :, None], zs.T[:, :, None]
+        zranges, dzdps, dqlins, eqlins = [], [], [], []
+        zoff = 0
+        for i, s in enumerate(m.subs):
+            dq, eq, fqprev = bc(stk(f"dq{i}", s.dq)), bc(stk(f"eq{i}", s.eq)), bc(stk(f"fqprev{i}", s.fqprev))
+            pexp, q0, fq = bc(stk(f"pexp{i}", s.pexp)), bc(stk(f"q0{i}", s.q0)), bc(stk(f"fq{i}", s.fq))
+            zr = slice(zoff, zoff + s.nn)
+            psteady = dq @ xB + eq @ uB + fqprev @ zB                     # (B, np, 1)
+            q = (q0 + pexp @ psteady + fq @ zB[:, zr])[:, :, 0]            # (B, nq)
+            par = None
+            if getattr(self, "_params", None) is not None and self._params[i] is not None:
+                par = np.asarray(self._params[i])[:, self.first:self.first + B]
+            Jq = np.empty((B, s.nn, s.nq))
+            for k in range(B):
+                table = s.elems
+                if par is not None:
+                    table, o = [], 0
+                    for e, off in s.elems:
+                        table.append((replace(e, params=tuple(par[o:o + len(e.params), k])), off))
+                        o += len(e.params)
+                Jq[k] = hostsolve.eval_table(table, q[k], s.nn)[1]
+            try:
+                dzdp = -np.linalg.solve(Jq @ fq, Jq @ pexp)               # solvers.jl:407-414
+            except np.linalg.LinAlgError:
+                raise ValueError("Cannot linearize: singular Jacobian at the steady state")
+            fqdzdps = [fqprev[:, :, zranges[n]] @ dzdps[n] for n in range(i)]
+            dqlin = dq + sum((f @ d for f, d in zip(fqdzdps, dqlins)), np.zeros_like(dq))
+            eqlin = eq + sum((f @ e for f, e in zip(fqdzdps, eqlins)), np.zeros_like(eq))
+            zranges.append(zr); dzdps.append(dzdp); dqlins.append(dqlin); eqlins.append(eqlin)
+            zlin = zB[:, zr] - dzdp @ psteady
+            x0 = x0 + c[:, :, zr] @ zlin
+            a = a + c[:, :, zr] @ dzdp @ dqlin
+            b = b + c[:, :, zr] @ dzdp @ eqlin
+            y0 = y0 + fy[:, :, zr] @ zlin
+            dy = dy + fy[:, :, zr] @ dzdp @ dqlin
+            ey = ey + fy[:, :, zr] @ dzdp @ eqlin
+            zoff += s.nn
+        lin0 = DiscreteModel.from_matrices(a=a[0], b=b[0], c=np.zeros((m.nx, 0)), x0=x0[0, :, 0], dy=dy[0],
+                                           ey=ey[0], fy=np.zeros((m.ny, 0)), y0=y0[0, :, 0], subs=[],
+                                           solver=m.solver)
+        mats = {"a": a, "b": b, "dy": dy, "ey": ey, "x0": x0[:, :, 0], "y0": y0[:, :, 0]}
+        ov = {k: np.asfortranarray(np.moveaxis(v, 0, -1)) for k, v in mats.items()
+              if v.size and not np.all(v == v[:1])}
+        return BatchRunner(lin0, B, overrides=ov or None, **runner_kw)
 
     def raise_for_status(self):
         """Re-raises the reference's failure semantics (ACME.jl:688-694)."""

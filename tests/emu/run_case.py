@@ -78,6 +78,41 @@ elif case == "steady":
     base, kw, B = A.derive_sweep(lambda R: ex.sallenkey(fs=96000, r1=R, r2=R), Rs, workers=1)
     r = BatchRunner(base, B, **kw); xs = r.steadystate(np.array([[0.3, 0.3, 0.3]])); r.close()
     out["linear"] = max(float(np.abs(xs[:, b] - ex.sallenkey(fs=96000, r1=R, r2=R).steadystate([0.3])).max()) for b, R in enumerate(Rs))
+elif case == "linearize":
+    # batched linearize (ACME.jl:505-550): per-instance steady inputs, element parameters and baked matrices;
+    # each instance's small-signal model == the host linearize of the separately built circuit
+    def lin_err(lr, refs):
+        e = 0.0
+        for b, ref in enumerate(refs):
+            for nme in ("a", "b", "dy", "ey", "x0", "y0"):
+                got = lr._stack(nme, getattr(lr.model, nme))
+                got = got[b if got.shape[0] > 1 else 0]
+                want = np.asarray(getattr(ref, nme), dtype=float).reshape(got.shape)
+                e = max(e, float(np.abs(got - want).max() / max(1.0, np.abs(want).max())))
+        return e
+    m = ex.birdie(vol=0.8)
+    us = [0.0, 0.1, -0.2]
+    r = BatchRunner(m, 3); lr = r.linearize(np.array([us])); r.close()
+    out["inputs"] = lin_err(lr, [m.linearize([uv]) for uv in us]); out["inputs_kernel"] = lr.kernel_name
+    # the linearised batch run from its steady state tracks the non-linear one for a small signal (runtests.jl:673-682)
+    N = 400
+    u = np.asfortranarray(np.array(us)[None, None, :] + 1e-4 * sine(N)[:, :, None])
+    lr.x = lr.steadystate(np.array([us])); yl = lr.run(u); lr.close()
+    r = BatchRunner(m, 3); r.steadystate_(np.array([us])); yn = r.run(u); r.close()
+    out["tracking"] = float(np.abs(yl - yn).max())
+    base = ex.diodeclipper()
+    isv, etav = [1e-15, 3e-14, 2e-13], [1.0, 1.5, 2.0]
+    par = np.array([[i, e, 1.8 * i, e] for i, e in zip(isv, etav)]).T.copy()
+    r = BatchRunner(base, 3, params=[par]); lr = r.linearize(np.array([[0.2, 0.2, 0.2]])); r.close()
+    out["params"] = lin_err(lr, [ex.diodeclipper(is1=i, is2=1.8 * i, η1=e, η2=e).linearize([0.2]) for i, e in zip(isv, etav)])
+    lr.close()
+    pts = [(0.2, 0.5), (0.7, 0.4), (0.45, 0.9)]
+    base, kw, B = A.derive_sweep(lambda d, t: ex.superover(d, t, 1.0), pts, workers=1)
+    r = BatchRunner(base, B, **kw); lr = r.linearize(); r.close()
+    out["baked"] = lin_err(lr, [ex.superover(*p, 1.0).linearize() for p in pts]); lr.close()
+    # identical instances -> no per-instance matrices
+    r = BatchRunner(m, 4); lr = r.linearize(); r.close()
+    out["shared_has_overrides"] = bool(lr._has_overrides); lr.close()
 elif case == "failure":
     m = ex.superover()
     B, N = 2, 25

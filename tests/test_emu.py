@@ -68,6 +68,17 @@ def test_batched_steadystate_with_per_instance_matrices(emu_lib):
     assert out["y_span"] < 1e-4          # the output only up to the Newton stopping rule (res < 1e-10 A at high-impedance nodes)
 
 
+def test_batched_linearize(emu_lib):
+    """BatchRunner.linearize (ACME.jl:505-550 per instance): per-instance steady inputs, element parameters and
+    baked matrices give each instance the small-signal model of its own separately built circuit (up to the
+    host reference's 1e-10 steady-state tolerance; the device solves to 1e-15), and the linear batch tracks
+    the non-linear one for a small signal (runtests.jl:673-682)"""
+    out = run_case(emu_lib, "linearize")
+    assert out["inputs"] < 1e-9 and out["params"] < 1e-7 and out["baked"] < 1e-4
+    assert out["tracking"] < 1e-7
+    assert out["shared_has_overrides"] is False
+
+
 def test_emulated_rows_kernel_failure_semantics(emu_lib):
     out = run_case(emu_lib, "failure")
     for solver in (H, "SimpleSolver"):

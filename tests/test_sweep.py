@@ -106,3 +106,27 @@ def test_steadystate_of_a_baked_sweep():
     r.run(np.asfortranarray(np.repeat(udc[:, None, :], 64, axis=1)))
     assert np.abs(r.x - xs).max() < 1e-9
     r.close()
+
+
+@pytest.mark.gpu
+def test_linearize_of_a_baked_sweep():
+    """batched linearize: every instance's small-signal model == linearize of its own circuit, and the
+    linear batch follows the non-linear batch for a small signal around the steady state"""
+    from acme_jl_b200 import BatchRunner
+    pts = [(0.2, 0.5), (0.7, 0.4), (0.45, 0.9)]
+    base, kw, B = A.derive_sweep(build_so, pts, workers=1)
+    r = BatchRunner(base, B, **kw)
+    lr = r.linearize()
+    for b, p in enumerate(pts):
+        ref = build_so(*p).linearize()
+        for name in ("a", "b", "dy", "ey", "x0", "y0"):
+            got = lr._stack(name, getattr(lr.model, name))
+            got = got[b if got.shape[0] > 1 else 0]
+            want = np.asarray(getattr(ref, name), dtype=float).reshape(got.shape)
+            assert np.abs(got - want).max() <= 1e-4 * max(1.0, np.abs(want).max()), name
+    N = 512
+    u = np.asfortranarray(np.repeat((1e-4 * np.sin(2 * np.pi * 1000 / 44100 * np.arange(N)))[None, :, None], B, axis=2))
+    lr.x = lr.steadystate()
+    r.steadystate_()
+    assert np.abs(lr.run(u) - r.run(u)).max() < 1e-4          # runtests.jl:749's bound for this circuit
+    lr.close(); r.close()
