@@ -117,6 +117,16 @@ extern "C" int acmeb200_model_create(const acmeb200_model_desc* d, int64_t first
     if (d->nx < 0 || d->nu < 0 || d->ny < 0 || d->nsub < 0) return fail(ACMEB200_EINVAL, "negative dimension");
     if (d->nsub > MAX_SUBS) return fail(ACMEB200_EUNSUPPORTED, "%d sub-problems, at most %d supported", d->nsub, MAX_SUBS);
     if (d->solver < 0 || d->solver > 2) return fail(ACMEB200_EINVAL, "unknown solver %d", d->solver);
+    if (d->nsub > 0 && !d->subs) return fail(ACMEB200_EINVAL, "nsub = %d but subs is null", d->nsub);
+    for (int i = 0; i < d->nsub; i++) {  // pointer checks up front, so a bad descriptor never reaches the device
+        const acmeb200_sub_desc& sd = d->subs[i];
+        if (sd.nn < 0 || sd.nq < 0 || sd.np < 0 || sd.nelem < 0 || sd.nparams < 0) return fail(ACMEB200_EINVAL, "sub %d: negative dimension", i);
+        if (sd.nelem > 0 && !sd.elems) return fail(ACMEB200_EINVAL, "sub %d: nelem = %d but elems is null", i, sd.nelem);
+        if (sd.nparams > 0 && !sd.params.ptr) return fail(ACMEB200_EINVAL, "sub %d: nparams = %d but params is null", i, sd.nparams);
+        const acmeb200_cache& c = sd.cache;
+        if (c.n_points > 0 && (!c.ps_idx || (sd.np > 0 && !c.ps) || (sd.nn > 0 && !c.zs) || (c.n_points > 1 && (!c.cut_dim || !c.cut_val)) || c.n_columns < c.n_points))
+            return fail(ACMEB200_EINVAL, "sub %d: incomplete frozen cache (null array or n_columns < n_points)", i);
+    }
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
         return fail(ACMEB200_ENODEVICE, "no CUDA device available (this library has no CPU fallback)");
@@ -317,7 +327,7 @@ static int select_kernel(acmeb200_model* m) {
                                             (m->coop_static ? "compile-time dims [superover]" : "runtime dims") + ", state in shared memory" +
                                             (m->dm.solver == ACMEB200_SOLVER_HOMOTOPY_CACHING ? ", dynamic solution cache>" : ">");
     else m->kernel_name = "generic<thread-per-instance, runtime dims>";
-    // dynamic solution caches (cooperative kernel + CachingSolver only)
+    // dynamic (learning) solution caches
     for (void* p : m->d_dyn) cudaFree(p);
     m->d_dyn.clear();
     for (int i = 0; i < m->dm.nsub; i++) {
@@ -408,12 +418,6 @@ static int ensure_staging(acmeb200_model* m, size_t ubytes, size_t ybytes) {
         m->stage_y_bytes = ybytes;
     }
     return ACMEB200_OK;
-}
-
-static bool is_pinned_or_managed(const void* p) {
-    cudaPointerAttributes at;
-    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
-    return at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged;
 }
 
 extern "C" int acmeb200_run(acmeb200_model* m, const double* U, int64_t u_stride, double* Y,

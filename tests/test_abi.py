@@ -65,3 +65,25 @@ def test_bad_descriptor_rejected():
     out = C.c_void_p()
     assert lib().acmeb200_model_create(C.byref(h.desc), 0, 1, C.byref(out)) == -1
     assert b"ABI version" in lib().acmeb200_last_error()
+
+
+def test_null_pointers_in_descriptor_rejected():
+    """a descriptor with counts but no arrays is refused before anything touches the device"""
+    out = C.c_void_p()
+
+    def create(h):
+        return lib().acmeb200_model_create(C.byref(h.desc), 0, 1, C.byref(out))
+
+    h = _abi.make_desc(ex.diodeclipper(), 1)
+    h.desc.subs[0].elems = None
+    assert create(h) == -1 and b"elems is null" in lib().acmeb200_last_error()
+    h = _abi.make_desc(ex.diodeclipper(), 1)
+    h.desc.subs[0].params.ptr = None
+    assert create(h) == -1 and b"params is null" in lib().acmeb200_last_error()
+    h = _abi.make_desc(ex.diodeclipper(), 1)
+    h.desc.subs[0].cache.n_points = 4          # a frozen cache without its arrays
+    assert create(h) == -1 and b"incomplete frozen cache" in lib().acmeb200_last_error()
+    h = _abi.make_desc(ex.diodeclipper(), 1)
+    h.desc.subs = None
+    assert create(h) == -1 and b"subs is null" in lib().acmeb200_last_error()
+    assert not out.value
