@@ -28,6 +28,7 @@ STATUS_NOT_CONVERGED = 1
 STATUS_NONFINITE = 2
 U_DEVICE = 1
 Y_DEVICE = 2
+SAMPLE_MAJOR = 4  # (nu, B, N) / (ny, B, N) streams, strides = sample pitches
 
 
 class Array(C.Structure):

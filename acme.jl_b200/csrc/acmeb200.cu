@@ -426,9 +426,19 @@ extern "C" int acmeb200_run(acmeb200_model* m, const double* U, int64_t u_stride
     if (N < 0) return fail(ACMEB200_EINVAL, "negative sample count");
     if (N >= (1ll << 27)) return fail(ACMEB200_EUNSUPPORTED, "at most 2^27-1 samples per call; split the run");
     const DevModel& dm = m->dm;
-    if (y_stride == 0) y_stride = (int64_t)dm.ny * N;
-    if (u_stride != 0 && u_stride < (int64_t)dm.nu * N) return fail(ACMEB200_EINVAL, "u_stride smaller than nu*N");
-    if (y_stride < (int64_t)dm.ny * N) return fail(ACMEB200_EINVAL, "y_stride smaller than ny*N");
+    const bool smaj = (flags & ACMEB200_SAMPLE_MAJOR) != 0;  // strides are sample pitches, (nu, B, N) / (ny, B, N) streams
+    if (smaj) {
+        if (!m->tpi)
+            return fail(ACMEB200_EUNSUPPORTED, "sample-major streams are implemented by the thread-per-instance kernels only; this model runs on %s",
+                        m->kernel_name.c_str());
+        if (y_stride == 0) y_stride = (int64_t)dm.ny * m->B;
+        if (u_stride != 0 && u_stride < (int64_t)dm.nu * m->B) return fail(ACMEB200_EINVAL, "sample-major u_stride smaller than nu*B");
+        if (y_stride < (int64_t)dm.ny * m->B) return fail(ACMEB200_EINVAL, "sample-major y_stride smaller than ny*B");
+    } else {
+        if (y_stride == 0) y_stride = (int64_t)dm.ny * N;
+        if (u_stride != 0 && u_stride < (int64_t)dm.nu * N) return fail(ACMEB200_EINVAL, "u_stride smaller than nu*N");
+        if (y_stride < (int64_t)dm.ny * N) return fail(ACMEB200_EINVAL, "y_stride smaller than ny*N");
+    }
     if (N == 0) return ACMEB200_OK;
     if ((dm.nu > 0 && !U) || (dm.ny > 0 && !Y)) return fail(ACMEB200_EINVAL, "null stream pointer");
     CUDA_TRY(cudaSetDevice(m->device));
@@ -438,6 +448,7 @@ extern "C" int acmeb200_run(acmeb200_model* m, const double* U, int64_t u_stride
     if (udev && ydev) {
         RunArgs a = base_args(m);
         a.U = U; a.u_stride = u_stride; a.Y = Y; a.y_stride = y_stride; a.N = N; a.inst0 = 0; a.ninst = m->B;
+        a.smaj = smaj;
         CUDA_TRY(launch(m, a, stream));
         m->n_done += N;
         return ACMEB200_OK;
@@ -472,30 +483,36 @@ extern "C" int acmeb200_run(acmeb200_model* m, const double* U, int64_t u_stride
         const int64_t nt = std::min<int64_t>(Tc, N - n0);
         RunArgs a = base_args(m);
         a.N = nt; a.inst0 = 0; a.ninst = m->B;
+        a.smaj = smaj;
         a.n_done = m->n_done + n0;
+        // sample-major streams: a chunk of time is `nt` whole rows of B instances, staged densely
+        const int64_t u_step = smaj && !shared_u ? u_stride : dm.nu, y_step = smaj ? y_stride : dm.ny;  // doubles per sample
         // ---- H2D of chunk c into staging buffer `buf` (free once kernel c-2 has consumed it)
         if (!udev && dm.nu > 0) {
             if (c >= 2) CUDA_TRY(cudaStreamWaitEvent(s_in, m->ev_k[buf], 0));
             if (shared_u)
                 CUDA_TRY(cudaMemcpyAsync(m->d_stage_u[buf], U + n0 * dm.nu, row_u * nt, cudaMemcpyHostToDevice, s_in));
+            else if (smaj)
+                CUDA_TRY(cudaMemcpy2DAsync(m->d_stage_u[buf], row_u * m->B, U + n0 * u_stride, (size_t)u_stride * sizeof(double),
+                                           row_u * m->B, (size_t)nt, cudaMemcpyHostToDevice, s_in));
             else
                 CUDA_TRY(cudaMemcpy2DAsync(m->d_stage_u[buf], row_u * nt, U + n0 * dm.nu, (size_t)u_stride * sizeof(double),
                                            row_u * nt, (size_t)m->B, cudaMemcpyHostToDevice, s_in));
             CUDA_TRY(cudaEventRecord(m->ev_in[buf], s_in));
             CUDA_TRY(cudaStreamWaitEvent(s_k, m->ev_in[buf], 0));
             a.U = m->d_stage_u[buf];
-            a.u_stride = shared_u ? 0 : dm.nu * nt;
+            a.u_stride = shared_u ? 0 : (smaj ? dm.nu * m->B : dm.nu * nt);
         } else {
-            a.U = U ? U + n0 * dm.nu : nullptr;
+            a.U = U ? U + n0 * u_step : nullptr;
             a.u_stride = u_stride;
         }
         // ---- kernel c (needs the output staging buffer `buf` drained by D2H c-2)
         if (!ydev && dm.ny > 0) {
             if (c >= 2) CUDA_TRY(cudaStreamWaitEvent(s_k, m->ev_out[buf], 0));
             a.Y = m->d_stage_y[buf];
-            a.y_stride = dm.ny * nt;
+            a.y_stride = smaj ? dm.ny * m->B : dm.ny * nt;
         } else {
-            a.Y = Y ? Y + n0 * dm.ny : nullptr;
+            a.Y = Y ? Y + n0 * y_step : nullptr;
             a.y_stride = y_stride;
         }
         CUDA_TRY(launch(m, a, s_k));
@@ -503,8 +520,12 @@ extern "C" int acmeb200_run(acmeb200_model* m, const double* U, int64_t u_stride
         // ---- D2H of chunk c
         if (!ydev && dm.ny > 0) {
             CUDA_TRY(cudaStreamWaitEvent(s_out, m->ev_k[buf], 0));
-            CUDA_TRY(cudaMemcpy2DAsync(Y + n0 * dm.ny, (size_t)y_stride * sizeof(double), m->d_stage_y[buf], row_y * nt,
-                                       row_y * nt, (size_t)m->B, cudaMemcpyDeviceToHost, s_out));
+            if (smaj)
+                CUDA_TRY(cudaMemcpy2DAsync(Y + n0 * y_stride, (size_t)y_stride * sizeof(double), m->d_stage_y[buf], row_y * m->B,
+                                           row_y * m->B, (size_t)nt, cudaMemcpyDeviceToHost, s_out));
+            else
+                CUDA_TRY(cudaMemcpy2DAsync(Y + n0 * dm.ny, (size_t)y_stride * sizeof(double), m->d_stage_y[buf], row_y * nt,
+                                           row_y * nt, (size_t)m->B, cudaMemcpyDeviceToHost, s_out));
             CUDA_TRY(cudaEventRecord(m->ev_out[buf], s_out));
         }
     }

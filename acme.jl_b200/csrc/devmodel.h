@@ -88,6 +88,7 @@ struct RunArgs {
     long long* first_fail;
     DevStats* stats;
     int init;                // 1: (re)initialise the solver state, process no samples
+    int smaj;                // 1: sample-major streams (ACMEB200_SAMPLE_MAJOR): u_stride / y_stride are sample pitches
 };
 
 }  // namespace acme

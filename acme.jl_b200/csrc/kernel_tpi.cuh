@@ -487,13 +487,18 @@ __host__ __device__ constexpr int tpi_swizzle_mask(int row_bytes) {
 
 // per-warp shared memory: TPI_STAGES input tiles and 2 output tiles (TMA multi-buffering;
 // box layout, row = instance, swizzled), 8 histogram counters per lane, one mbarrier per input stage.
-template <class C>
+//
+// Sample-major streams (SMAJ, ACMEB200_SAMPLE_MAJOR): the tile is transposed -- one row per SAMPLE holding the
+// 32 instances of the warp (box {32*channels, TPI_T} of a (channels*B, N) tensor).  Lanes read consecutive
+// words of a row, which is conflict-free without a swizzle, and every box row is one contiguous
+// 256*channels-byte segment of HBM instead of 32 segments of TPI_T*channels*8 bytes.
+template <class C, bool SMAJ = false>
 struct TpiSmem {
-    static constexpr int IROW = TPI_T * C::NU * 8;  // bytes per instance row, input
-    static constexpr int OROW = TPI_T * C::NY * 8;
+    static constexpr int IROW = (SMAJ ? 32 : TPI_T) * C::NU * 8;  // bytes per tile row, input
+    static constexpr int OROW = (SMAJ ? 32 : TPI_T) * C::NY * 8;
     static constexpr int ISW = tpi_swizzle_mask(IROW), OSW = tpi_swizzle_mask(OROW);
-    static constexpr int IN_TX = 32 * IROW;  // bytes one TMA tile load delivers
-    static constexpr int IN_BYTES = (32 * IROW + 1023) / 1024 * 1024, OUT_BYTES = (32 * OROW + 1023) / 1024 * 1024;
+    static constexpr int IN_TX = 32 * TPI_T * C::NU * 8;  // bytes one TMA tile load delivers
+    static constexpr int IN_BYTES = (IN_TX + 1023) / 1024 * 1024, OUT_BYTES = (32 * TPI_T * C::NY * 8 + 1023) / 1024 * 1024;
     static constexpr int OUT_OFF = TPI_STAGES * IN_BYTES;
     static constexpr int HIST_OFF = OUT_OFF + TPI_OSTAGES * OUT_BYTES;
     static constexpr int BAR_OFF = HIST_OFF + 32 * 8 * 4;
@@ -507,6 +512,7 @@ struct TpiSmem {
 
 template <class C>
 constexpr size_t tpi_smem_bytes() {
+    static_assert(TpiSmem<C, true>::PER_WARP == TpiSmem<C, false>::PER_WARP, "both tile orientations have the same footprint");
     return (size_t)(TPI_TPB / 32) * TpiSmem<C>::PER_WARP;
 }
 
@@ -640,13 +646,13 @@ __device__ __noinline__ int tpi_step_cold(const M* mp, const double* Cn_, TpiSta
     return iters;
 }
 
-template <class C, bool PERINST>
+template <class C, bool PERINST, bool SMAJ>
 __global__ void __launch_bounds__(TPI_TPB, ACME_TPI_MINB) k_tpi(const __grid_constant__ TpiMats<C> Msh, const RunArgs a,
                                                  const __grid_constant__ SolverCfg sc, const __grid_constant__ DevSub cache,
                                                  const __grid_constant__ TpiMaps maps) {
     constexpr int NX = C::NX, NU = C::NU, NY = C::NY, NN = C::NN, NP = C::NP;
     constexpr int T = TPI_T;
-    using SM = TpiSmem<C>;
+    using SM = TpiSmem<C, SMAJ>;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned char* wsm = smem_raw + (size_t)warp * SM::PER_WARP;
@@ -718,8 +724,15 @@ __global__ void __launch_bounds__(TPI_TPB, ACME_TPI_MINB) k_tpi(const __grid_con
     const bool wact = w0 < (int)a.ninst;    // warp has at least one instance (lane 0 is active)
     const int n_samp = (int)a.N;            // N < 2^27 (checked by the host)
     const int n_tiles = (n_samp + T - 1) / T;
-    auto urow = [&](int n) { return a.U + (shared_u ? 0 : (int64_t)t32 * a.u_stride) + (int64_t)n * NU; };
-    auto yrow = [&](int n) { return a.Y + (int64_t)t32 * a.y_stride + (int64_t)n * NY; };
+    // first value of sample n of this lane's instance (the synchronous paths)
+    auto urow = [&](int n) {
+        if constexpr (SMAJ) return a.U + (int64_t)n * a.u_stride + (int64_t)t32 * NU;
+        else return a.U + (shared_u ? 0 : (int64_t)t32 * a.u_stride) + (int64_t)n * NU;
+    };
+    auto yrow = [&](int n) {
+        if constexpr (SMAJ) return a.Y + (int64_t)n * a.y_stride + (int64_t)t32 * NY;
+        else return a.Y + (int64_t)t32 * a.y_stride + (int64_t)n * NY;
+    };
     unsigned int* const hist_s = reinterpret_cast<unsigned int*>(wsm + SM::HIST_OFF) + lane;  // [bin*32]
     const uint32_t bar0 = smem_u32(wsm + SM::BAR_OFF);  // bar1 = bar0 + 8
     const int ixr = SM::in_xor(lane), oxr = SM::out_xor(lane);  // swizzle terms of this lane's rows
@@ -735,7 +748,8 @@ __global__ void __launch_bounds__(TPI_TPB, ACME_TPI_MINB) k_tpi(const __grid_con
         if (lane == 0 && wact)
             for (int k = 0; k < TPI_STAGES && k < n_tiles; k++) {
                 mbar_arrive_expect_tx(bar0 + 8 * k, SM::IN_TX);
-                tma_load_2d(smem_u32(wsm + k * SM::IN_BYTES), &maps.u, k * T * NU, w0, bar0 + 8 * k);
+                if constexpr (SMAJ) tma_load_2d(smem_u32(wsm + k * SM::IN_BYTES), &maps.u, w0 * NU, k * T, bar0 + 8 * k);
+                else tma_load_2d(smem_u32(wsm + k * SM::IN_BYTES), &maps.u, k * T * NU, w0, bar0 + 8 * k);
             }
     }
 
@@ -748,16 +762,29 @@ __global__ void __launch_bounds__(TPI_TPB, ACME_TPI_MINB) k_tpi(const __grid_con
         unsigned char* const out_tile = wsm + SM::OUT_OFF + (k & (TPI_OSTAGES - 1)) * SM::OUT_BYTES;
         unsigned char* const in_row = in_tile + lane * SM::IROW;
         unsigned char* const out_row = out_tile + lane * SM::OROW;
-        auto in_at = [&](int c) -> double& { return *reinterpret_cast<double*>(in_row + ((c * 8) ^ ixr)); };
-        auto out_at = [&](int c) -> double& { return *reinterpret_cast<double*>(out_row + ((c * 8) ^ oxr)); };
+        // value c = tt*channels + q of this lane's instance within the tile
+        auto in_at = [&](int c) -> double& {
+            if constexpr (SMAJ) return *reinterpret_cast<double*>(in_tile + ((c / dim1(NU)) * 32 * NU + lane * NU + c % dim1(NU)) * 8);
+            else return *reinterpret_cast<double*>(in_row + ((c * 8) ^ ixr));
+        };
+        auto out_at = [&](int c) -> double& {
+            if constexpr (SMAJ) return *reinterpret_cast<double*>(out_tile + ((c / dim1(NY)) * 32 * NY + lane * NY + c % dim1(NY)) * 8);
+            else return *reinterpret_cast<double*>(out_row + ((c * 8) ^ oxr));
+        };
         if (!shared_u) {
             if (tma_in) {
                 if (wact) mbar_wait(bar0 + 8 * buf, (uint32_t)((k / TPI_STAGES) & 1));
             } else {
                 // synchronous path (unaligned streams): own-row loads
                 __syncwarp();
-                if (active)
-                    for (int c = 0; c < cnt * NU; c++) in_at(c) = __ldcs(urow(n0) + c);
+                if (active) {
+                    if constexpr (SMAJ) {
+                        for (int ts = 0; ts < cnt; ts++)
+                            for (int q = 0; q < NU; q++) in_at(ts * NU + q) = __ldcs(urow(n0 + ts) + q);
+                    } else {
+                        for (int c = 0; c < cnt * NU; c++) in_at(c) = __ldcs(urow(n0) + c);
+                    }
+                }
             }
         }
         if (tma_out && k >= TPI_OSTAGES) {  // the store of tile k-TPI_OSTAGES has drained this output buffer
@@ -765,7 +792,7 @@ __global__ void __launch_bounds__(TPI_TPB, ACME_TPI_MINB) k_tpi(const __grid_con
             __syncwarp();
         }
         int tt = 0;
-        if constexpr (NN == 0 && (SM::IROW % 16 == 0) && (SM::OROW % 16 == 0)) {
+        if constexpr (NN == 0 && (SMAJ || ((SM::IROW % 16 == 0) && (SM::OROW % 16 == 0)))) {
             // ---- linear model: the whole tile row through registers.  128-bit loads/stores of the
             //      swizzled rows are bank-conflict free; the per-sample work is a handful of DFMAs
             //      (ACME.jl:699-714 with nn = 0), so this path is what makes the kernel HBM-bound.
@@ -776,6 +803,8 @@ __global__ void __launch_bounds__(TPI_TPB, ACME_TPI_MINB) k_tpi(const __grid_con
                         constexpr int c = decltype(cc)::value;
                         ub[c] = c < cnt * NU ? __ldg(a.U + (int64_t)n0 * NU + c) : 0.0;
                     });
+                } else if constexpr (SMAJ) {
+                    static_for<0, T * NU>([&](auto cc) { ub[decltype(cc)::value] = in_at(decltype(cc)::value); });
                 } else {
                     static_for<0, SM::IROW / 16>([&](auto cc) {
                         constexpr int c = decltype(cc)::value;
@@ -792,10 +821,14 @@ __global__ void __launch_bounds__(TPI_TPB, ACME_TPI_MINB) k_tpi(const __grid_con
                     if (ti < cnt) tpi_output_update<C>(m, S, u, znone, y);  // warp-uniform: only the last tile is short
                     static_for<0, NY>([&](auto kk) { yb[ti * NY + decltype(kk)::value] = y[decltype(kk)::value]; });
                 });
-                static_for<0, SM::OROW / 16>([&](auto cc) {
-                    constexpr int c = decltype(cc)::value;
-                    *reinterpret_cast<double2*>(out_row + ((c * 16) ^ oxr)) = make_double2(yb[2 * c], yb[2 * c + 1]);
-                });
+                if constexpr (SMAJ) {
+                    static_for<0, T * NY>([&](auto cc) { out_at(decltype(cc)::value) = yb[decltype(cc)::value]; });
+                } else {
+                    static_for<0, SM::OROW / 16>([&](auto cc) {
+                        constexpr int c = decltype(cc)::value;
+                        *reinterpret_cast<double2*>(out_row + ((c * 16) ^ oxr)) = make_double2(yb[2 * c], yb[2 * c + 1]);
+                    });
+                }
                 tt = cnt;
             }
         } else {
@@ -839,19 +872,27 @@ __global__ void __launch_bounds__(TPI_TPB, ACME_TPI_MINB) k_tpi(const __grid_con
         //      lie outside the tensor and are clipped), or own-row stores
         if (NY > 0) {
             if (tma_out) fence_async_smem();  // generic-proxy writes -> visible to the async proxy
-            else if (active)
-                for (int c = 0; c < cnt * NY; c++) __stcs(yrow(n0) + c, out_at(c));
+            else if (active) {
+                if constexpr (SMAJ) {
+                    for (int ts = 0; ts < cnt; ts++)
+                        for (int q = 0; q < NY; q++) __stcs(yrow(n0 + ts) + q, out_at(ts * NY + q));
+                } else {
+                    for (int c = 0; c < cnt * NY; c++) __stcs(yrow(n0) + c, out_at(c));
+                }
+            }
         }
         if (tma_in || tma_out) __syncwarp();  // all lanes are done with in_tile / have written out_tile
         if (lane == 0 && wact) {
             if (tma_out) {
-                tma_store_2d(&maps.y, n0 * NY, w0, smem_u32(out_tile));
+                if constexpr (SMAJ) tma_store_2d(&maps.y, w0 * NY, n0, smem_u32(out_tile));
+                else tma_store_2d(&maps.y, n0 * NY, w0, smem_u32(out_tile));
                 bulk_commit();
             }
             // ---- refill this input buffer with tile k+TPI_STAGES
             if (tma_in && k + TPI_STAGES < n_tiles) {
                 mbar_arrive_expect_tx(bar0 + 8 * buf, SM::IN_TX);
-                tma_load_2d(smem_u32(in_tile), &maps.u, (k + TPI_STAGES) * T * NU, w0, bar0 + 8 * buf);
+                if constexpr (SMAJ) tma_load_2d(smem_u32(in_tile), &maps.u, w0 * NU, (k + TPI_STAGES) * T, bar0 + 8 * buf);
+                else tma_load_2d(smem_u32(in_tile), &maps.u, (k + TPI_STAGES) * T * NU, w0, bar0 + 8 * buf);
             }
         }
     }

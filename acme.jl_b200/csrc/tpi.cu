@@ -45,11 +45,13 @@ static EncodeTiledFn encode_tiled_fn() {
 }
 
 // Tensor map of one f64 stream of a launch: dim0 = the `inner` contiguous values of an instance,
-// dim1 = `ninst` instances `stride` values apart, box {box_inner, 32} = one warp tile.
+// dim1 = `ninst` instances `stride` values apart, box {box_inner, box_outer = 32} = one warp tile.
+// Sample-major streams swap the roles: dim0 = the channels of all instances at one sample, dim1 = samples
+// `stride` values apart, box {32*channels, TPI_T}.
 // False when the stream does not meet TMA's 16-byte alignment rules (the kernel then uses its
 // synchronous path).
 static bool make_tile_map(CUtensorMap* tm, const double* base, int64_t stride, int64_t ninst, int64_t inner,
-                          int box_inner) {
+                          int box_inner, int box_outer = 32) {
     EncodeTiledFn enc = encode_tiled_fn();
     if (!enc || !base || inner <= 0 || ninst <= 0) return false;
     if (ninst == 1 && stride < inner) stride = (inner + 1) & ~int64_t(1);  // a single row: the pitch is unused
@@ -57,7 +59,7 @@ static bool make_tile_map(CUtensorMap* tm, const double* base, int64_t stride, i
     if ((box_inner & 1) || box_inner > 256 || inner >= (int64_t(1) << 32) || ninst >= (int64_t(1) << 32)) return false;
     const cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)ninst};
     const cuuint64_t strides[1] = {(cuuint64_t)stride * 8};
-    const cuuint32_t box[2] = {(cuuint32_t)box_inner, 32};
+    const cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
     const cuuint32_t estr[2] = {1, 1};
     // the swizzle the kernel's tile accessors assume (tpi_swizzle_mask): by the row length of the box
     const int mask = tpi_swizzle_mask(box_inner * 8);
@@ -78,7 +80,11 @@ static cudaError_t launch_tpi(const acmeb200_model* m, const RunArgs& a, cudaStr
     if (m->dm.nsub > 0) cache = m->dm.subs[0];
     TpiMaps maps;
     memset(&maps, 0, sizeof maps);
-    if (!a.init) {
+    if (!a.init && a.smaj) {
+        maps.in_ok = C::NU > 0 && a.u_stride != 0 &&
+                     make_tile_map(&maps.u, a.U, a.u_stride, a.N, a.ninst * C::NU, 32 * C::NU, TPI_T);
+        maps.out_ok = C::NY > 0 && make_tile_map(&maps.y, a.Y, a.y_stride, a.N, a.ninst * C::NY, 32 * C::NY, TPI_T);
+    } else if (!a.init) {
         maps.in_ok = C::NU > 0 && a.u_stride != 0 &&
                      make_tile_map(&maps.u, a.U, a.u_stride, a.ninst, a.N * C::NU, TPI_T * C::NU);
         maps.out_ok = C::NY > 0 && make_tile_map(&maps.y, a.Y, a.y_stride, a.ninst, a.N * C::NY, TPI_T * C::NY);
@@ -88,9 +94,10 @@ static cudaError_t launch_tpi(const acmeb200_model* m, const RunArgs& a, cudaStr
     if (smem > 48 * 1024) {  // long tiles: opt in to the large dynamic shared memory carve-out
         static bool attr_set = false;
         if (!attr_set) {
-            cudaError_t e = cudaFuncSetAttribute(k_tpi<C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e == cudaSuccess) e = cudaFuncSetAttribute(k_tpi<C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) return e;
+            for (auto* k : {k_tpi<C, true, false>, k_tpi<C, false, false>, k_tpi<C, true, true>, k_tpi<C, false, true>}) {
+                const cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                if (e != cudaSuccess) return e;
+            }
             attr_set = true;
         }
     }
@@ -110,15 +117,20 @@ static cudaError_t launch_tpi(const acmeb200_model* m, const RunArgs& a, cudaStr
         const int64_t need = resident * (int64_t)(smem + 1024);
         const int pct = (int)std::min<int64_t>(100, (need * 100 + max_smem - 1) / std::max(max_smem, 1));
         if (pct != last_pct) {
-            cudaFuncSetAttribute(k_tpi<C, true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-            cudaFuncSetAttribute(k_tpi<C, false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+            for (auto* k : {k_tpi<C, true, false>, k_tpi<C, false, false>, k_tpi<C, true, true>, k_tpi<C, false, true>})
+                cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
             last_pct = pct;
         }
     }
-    if (m->blob_stride)
-        ACME_LAUNCH((k_tpi<C, true>), (unsigned)blocks, TPI_TPB, smem, stream, M, a, sc, cache, maps);
+    if (a.smaj) {  // sample-major streams: transposed tiles (kernel_tpi.cuh)
+        if (m->blob_stride)
+            ACME_LAUNCH((k_tpi<C, true, true>), (unsigned)blocks, TPI_TPB, smem, stream, M, a, sc, cache, maps);
+        else
+            ACME_LAUNCH((k_tpi<C, false, true>), (unsigned)blocks, TPI_TPB, smem, stream, M, a, sc, cache, maps);
+    } else if (m->blob_stride)
+        ACME_LAUNCH((k_tpi<C, true, false>), (unsigned)blocks, TPI_TPB, smem, stream, M, a, sc, cache, maps);
     else
-        ACME_LAUNCH((k_tpi<C, false>), (unsigned)blocks, TPI_TPB, smem, stream, M, a, sc, cache, maps);
+        ACME_LAUNCH((k_tpi<C, false, false>), (unsigned)blocks, TPI_TPB, smem, stream, M, a, sc, cache, maps);
     return cudaGetLastError();
 }
 

@@ -134,8 +134,15 @@ class BatchRunner:
         if y_cols is not None and u_cols != y_cols:
             raise DimensionMismatch(f"input matrix has {u_cols} columns, output matrix has {y_cols} columns")
 
-    def run(self, u, y=None, *, stream=None, check_status: bool = True):
+    def run(self, u, y=None, *, stream=None, check_status: bool = True, layout: str = "instance"):
         """``run!`` for all instances.
+
+        ``layout="sample"`` selects the sample-major streams of the C ABI
+        (ACMEB200_SAMPLE_MAJOR; thread-per-instance kernels only): per-instance
+        input (nu, B, N) and output (ny, B, N) in Julia layout -- torch tensors
+        (N, B, nu) / (N, B, ny) -- so that one time step of all instances is
+        contiguous.  A shared (nu, N) input is the same in both layouts.  The
+        values are bit-identical to the default layout.
 
         u: numpy array (host) or torch CUDA tensor (device), shape (nu, N) -- one
         input shared by all instances -- or (nu, N, B) in Julia (column-major)
@@ -145,6 +152,10 @@ class BatchRunner:
         Returns y with the matching convention.
         """
         m = self.model
+        if layout not in ("instance", "sample"):
+            raise ValueError("layout must be 'instance' or 'sample'")
+        if layout == "sample":
+            return self._run_sample_major(u, y, stream, check_status)
         if _is_torch_cuda(u):
             return self._run_torch(u, y, stream, check_status)
         u = np.asarray(u, dtype=np.float64)
@@ -207,6 +218,66 @@ class BatchRunner:
         if check_status:
             self.raise_for_status()
         return y
+
+    def _run_sample_major(self, u, y, stream, check_status):
+        """sample-major streams: numpy (nu, B, N) / (ny, B, N) Fortran order, torch (N, B, nu) / (N, B, ny)"""
+        m, B = self.model, self.batch
+        if _is_torch_cuda(u):
+            import torch
+            if u.dtype != torch.float64 or not u.is_contiguous():
+                raise ValueError("device input must be a contiguous float64 tensor")
+            if u.dim() == 2:
+                N, nu = u.shape
+                ustride = 0
+            elif u.dim() == 3:
+                N, Bu, nu = u.shape
+                if Bu != B:
+                    raise DimensionMismatch(f"input has {Bu} instances, runner has {B}")
+                ustride = B * nu
+            else:
+                raise DimensionMismatch("sample-major device u must be (N, nu) or (N, B, nu)")
+            self._check_sizes(nu, N)
+            if y is None:
+                y = torch.empty((N, B, m.ny), dtype=torch.float64, device=u.device)
+            elif tuple(y.shape) != (N, B, m.ny) or y.dtype != torch.float64 or not y.is_contiguous():
+                raise DimensionMismatch(f"sample-major device y must be a contiguous float64 tensor of shape {(N, B, m.ny)}")
+            s = stream if stream is not None else torch.cuda.current_stream(u.device)
+            check(lib().acmeb200_run(self._h, C.c_void_p(u.data_ptr()), ustride, C.c_void_p(y.data_ptr()), B * m.ny, N,
+                                     _abi.U_DEVICE | _abi.Y_DEVICE | _abi.SAMPLE_MAJOR, C.c_void_p(s.cuda_stream)))
+            if check_status:
+                self.raise_for_status()
+            return y
+        u = np.asarray(u, dtype=np.float64)
+        if u.ndim == 2:
+            N = u.shape[1]
+            ustride = 0
+        elif u.ndim == 3:
+            N = u.shape[2]
+            if u.shape[1] != B:
+                raise DimensionMismatch(f"input has {u.shape[1]} instances, runner has {B}")
+            ustride = m.nu * B
+        else:
+            raise DimensionMismatch("sample-major u must be (nu, N) or (nu, B, N)")
+        self._check_sizes(u.shape[0], N)
+        ubuf = np.ascontiguousarray(u.ravel(order="F"))
+        if y is None:
+            ybuf = np.empty(max(m.ny * N * B, 1))
+        else:
+            if y.shape != (m.ny, B, N):
+                self._check_sizes(u.shape[0], N, y.shape[0], y.shape[-1])
+                raise DimensionMismatch(f"sample-major y must have shape {(m.ny, B, N)}")
+            if not (y.flags.f_contiguous and y.dtype == np.float64):
+                raise ValueError("y must be a Fortran-contiguous float64 array")
+            ybuf = y.reshape(-1, order="F") if y.size else np.empty(1)
+        if ubuf.size == 0:
+            ubuf = np.zeros(1)
+        check(lib().acmeb200_run(self._h, ubuf.ctypes.data_as(C.c_void_p), ustride, ybuf.ctypes.data_as(C.c_void_p),
+                                 m.ny * B, N, _abi.SAMPLE_MAJOR, None))
+        if check_status:
+            self.raise_for_status()
+        if y is not None:
+            return y
+        return ybuf[:m.ny * N * B].reshape((m.ny, B, N), order="F")
 
     def run_host_pinned(self, u_ptr: int, ustride: int, y_ptr: int, N: int):
         """raw-pointer host run (used by bench.py for the end-to-end leg with pinned torch buffers)"""

@@ -83,6 +83,15 @@ extern "C" {
 /* run flags */
 #define ACMEB200_U_DEVICE 1u /* U is a device pointer (else host)  */
 #define ACMEB200_Y_DEVICE 2u /* Y is a device pointer (else host)  */
+/* Sample-major ("instance-fastest") streams, SURVEY.md section 8(d) "I/O layout": U is
+ * (nu, B, N) and Y is (ny, B, N) column-major, i.e. sample n of instance b is the nu
+ * values at U + n*u_stride + b*nu; u_stride / y_stride are then the distances in doubles
+ * between consecutive SAMPLES (>= nu*B / ny*B; y_stride == 0 -> ny*B; u_stride == 0 still
+ * means one nu x N input shared by all instances).  Every time step of a warp's 32
+ * instances is one contiguous segment, so the tiles of the thread-per-instance kernels
+ * move as 256-byte rows.  Only models run by those kernels accept the flag
+ * (ACMEB200_EUNSUPPORTED otherwise); results are bit-identical to the default layout. */
+#define ACMEB200_SAMPLE_MAJOR 4u
 
 #define ACMEB200_HIST_BINS 32 /* iteration histogram: bins 1..31, last bin = 32 and more */
 

@@ -143,6 +143,25 @@ end
 ACME.run!(r::BatchRunner, U::Array{Float64,3}) = ACME.run!(r, Array{Float64,3}(undef, ny(r.model), size(U, 2), r.batch), U)
 
 """
+    run_samplemajor!(runner::BatchRunner, Y::Array{Float64,3}, U::Array{Float64,3})
+
+Same computation on sample-major streams (`ACMEB200_SAMPLE_MAJOR`, thread-per-instance kernels only):
+`size(U) == (nu, B, N)`, `size(Y) == (ny, B, N)`, i.e. `U[:, :, n]` is one time step of the whole batch.
+Bit-identical results; the device tiles then move as contiguous 256-byte rows.
+"""
+function run_samplemajor!(r::BatchRunner, Y::Array{Float64,3}, U::Array{Float64,3})
+    m = r.model
+    size(U, 1) == nu(m) || throw(DimensionMismatch("input matrix has $(size(U,1)) rows, but model has $(nu(m)) inputs"))
+    size(Y, 1) == ny(m) || throw(DimensionMismatch("output matrix has $(size(Y,1)) rows, but model has $(ny(m)) outputs"))
+    size(U, 3) == size(Y, 3) || throw(DimensionMismatch("input matrix has $(size(U,3)) columns, output matrix has $(size(Y,3)) columns"))
+    (size(U, 2) == r.batch && size(Y, 2) == r.batch) || throw(DimensionMismatch("streams must hold $(r.batch) instances"))
+    GC.@preserve U Y check(ccall((:acmeb200_run, libacmeb200), Cint,
+        (Ptr{Cvoid}, Ptr{Float64}, Int64, Ptr{Float64}, Int64, Int64, UInt32, Ptr{Cvoid}),
+        r.handle, U, nu(m) * r.batch, Y, ny(m) * r.batch, size(U, 3), 0x4, C_NULL))
+    return Y
+end
+
+"""
     cache_sizes(runner; sub=1) -> (stored::Vector{Int32}, capacity::Int)
 
 Solutions the learning `CachingSolver` of sub-problem `sub` has stored so far, per instance

@@ -188,4 +188,61 @@ elif case == "tpi":
     out["birdie"] = dict(kernel=r.kernel_name, err=float(np.max(np.abs(y - yref) / np.maximum(np.abs(yref), 1e-3 * peak))),
                          stored=[int(v) for v in r.cache_sizes()[0]], bad=int((r.status()[0] != 0).sum()))
     r.close()
+elif case == "sample_major":
+    # ACMEB200_SAMPLE_MAJOR: (nu, B, N) / (ny, B, N) streams through the transposed tiles of k_tpi.  Every run is
+    # compared BIT FOR BIT with the instance-major run of the same library (same arithmetic, other data movement)
+    # and with the oracle.
+    smaj = lambda a: np.asfortranarray(np.transpose(a, (0, 2, 1)))   # (c, N, B) -> (c, B, N)
+    def both(mk, u, **kw):
+        r = mk(); y = r.run(u); st = r.stats(); r.close()
+        r = mk(); ys = r.run(smaj(u), layout="sample", **kw); sts = r.stats(); name = r.kernel_name; launches = r.launch_count; r.close()
+        return y, ys, dict(kernel=name, equal=bool(np.array_equal(smaj(y), ys)), hist_equal=st["iter_hist"] == sts["iter_hist"],
+                           samples=int(sts["samples"]), launches=int(launches))
+    # non-linear, per-instance element parameters, a batch that fills neither its last warp nor its last tile
+    B, N = 70, 203
+    Is = 10.0 ** (-16 + 4 * np.arange(B) / 69); eta = 1 + np.arange(B) / 69
+    P = np.vstack([Is, eta, 1.8 * Is, eta])
+    amp = 0.5 + np.arange(B) / B                                      # distinct inputs, so a transposition error shows
+    u = np.asfortranarray(sine(N)[:, :, None] * amp[None, None, :])
+    mk = lambda: BatchRunner(ex.diodeclipper(), B, params=[P], solver=HC)
+    y, ys, d = both(mk, u)
+    yref = OracleModel(ex.diodeclipper(), B, params=[P], solver=HC).run(u, threads=0)
+    d["err"] = float(np.abs(y - yref).max() / np.abs(yref).max())
+    out["clipper"] = d
+    # odd batch: the sample pitch nu*B is odd, the tensor maps cannot be built -> synchronous tile path
+    B3 = 37
+    u3 = np.asfortranarray(u[:, :, :B3])
+    mk3 = lambda: BatchRunner(ex.diodeclipper(), B3, params=[P[:, :B3].copy()], solver=H)
+    out["odd_batch"] = both(mk3, u3)[2]
+    # the host-buffer pipeline in time chunks (1 MiB staging chunks) == one device-resident chunk
+    N2 = 5003
+    u2 = np.asfortranarray(sine(N2)[:, :, None] * amp[None, None, :])
+    os.environ["ACMEB200_CHUNK_MB"] = "1"
+    out["chunks"] = both(mk, u2)[2]
+    del os.environ["ACMEB200_CHUNK_MB"]
+    # one shared input, sample-major output; output written into a caller-provided array
+    r = mk(); y1 = r.run(sine(N)); r.close()
+    r = mk(); yo = np.zeros((1, B, N), order="F"); r.run(sine(N), yo, layout="sample"); r.close()
+    out["shared_u"] = bool(np.array_equal(smaj(y1), yo))
+    # linear model with per-instance matrices: the whole-tile register path
+    base, kw, Bl = A.derive_sweep(lambda R: ex.sallenkey(fs=96000, r1=R, r2=R), [1e3 * (1 + k) for k in range(38)], workers=1)
+    ul = np.asfortranarray(sine(101)[:, :, None] * (1 + np.arange(Bl))[None, None, :])
+    yl, yls, d = both(lambda: BatchRunner(base, Bl, **kw), ul)
+    d["err"] = float(np.abs(yl - OracleModel(base, Bl, **kw).run(ul, threads=0)).max() / np.abs(yl).max())
+    out["linear"] = d
+    # two input channels (birdie with the volume pot as an input): 512-byte tile rows; learning cache
+    m = ex.birdie()
+    Bb, Nb = 6, 150
+    rng = np.random.default_rng(3)
+    ub = np.zeros((2, Nb, Bb), order="F"); ub[0] = np.clip(0.2 * rng.standard_normal((Nb, Bb)), -1, 1); ub[1] = (0.3 + 0.1 * np.arange(Bb))[None, :]
+    out["birdie_vol"] = both(lambda: BatchRunner(m, Bb, solver=HC), ub)[2]
+    # state persists across calls in either layout: first half sample-major, second half instance-major
+    r = mk(); ya = r.run(smaj(u[:, :100]), layout="sample"); yb = r.run(np.asfortranarray(u[:, 100:])); r.close()
+    out["mixed_calls"] = bool(np.array_equal(np.concatenate([np.transpose(ya, (0, 2, 1)), yb], axis=1), y))
+    # kernels without the transposed tiles refuse the flag loudly
+    try:
+        r = BatchRunner(ex.diodeclipper(), 2, solver=H, kernel="generic"); r.run(smaj(u[:, :8, :2]), layout="sample")
+        out["generic_refused"] = False
+    except Exception as e:
+        out["generic_refused"] = "thread-per-instance" in str(e)
 print(json.dumps(out))

@@ -106,6 +106,19 @@ def test_emulated_tpi_kernel_golden_vector_and_batches(emu_lib):
     assert out["birdie"]["bad"] == 0 and max(out["birdie"]["stored"]) > 1
 
 
+def test_emulated_sample_major_streams(emu_lib):
+    """ACMEB200_SAMPLE_MAJOR under emulation: transposed tensor-map tiles (box {32*channels, T} of the (channels*B, N)
+    stream), the synchronous path for odd pitches, the host time-chunk pipeline, linear whole-tile path, two input
+    channels, mixed-layout calls -- each bit-identical to the default layout, which the tests above pin to the oracle"""
+    out = run_case(emu_lib, "sample_major")
+    for key, samples in (("clipper", 70 * 203), ("odd_batch", 37 * 203), ("chunks", 70 * 5003), ("linear", 38 * 101), ("birdie_vol", 6 * 150)):
+        o = out[key]
+        assert o["kernel"].startswith("tpi<") and o["equal"] and o["hist_equal"] and o["samples"] == samples, (key, o)
+    assert out["chunks"]["launches"] >= 4                     # init + 3 time chunks
+    assert out["clipper"]["err"] < 1e-6 and out["linear"]["err"] < 1e-13
+    assert out["shared_u"] and out["mixed_calls"] and out["generic_refused"]
+
+
 def test_emulated_cooperative_kernel(emu_lib):
     """k_coop under emulation, including its sub-warp masks (two 16-lane groups per warp with independent control flow)"""
     out = run_case(emu_lib, "coop")
@@ -122,7 +135,8 @@ def test_gpu_parity_suite_subset_under_emulation(emu_lib):
     tile path), per-instance matrices of a non-linear model, size checks.  (The long-running ones -- full
     waveforms on the lane-parallel kernels -- stay GPU-only.)"""
     sel = ("K4 or K5 or K6 or K7 or K8 or K9 or empty_circuits or io_size or frozen_cache or steadystate_on_device or "
-           "run_bang or odd_lengths or per_instance_matrices_nonlinear or (K3 and not coop)")
+           "run_bang or odd_lengths or per_instance_matrices_nonlinear or (K3 and not coop) or "
+           "(sample_major and not device_tensors)")
     env = dict(os.environ, ACMEB200_LIB=emu_lib)
     res = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_parity.py"), "-m", "gpu", "-q", "-x",
                           "-p", "no:cacheprovider", "-k", sel], env=env, capture_output=True, text=True, timeout=900, cwd=ROOT)

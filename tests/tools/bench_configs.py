@@ -1,7 +1,8 @@
 """All five BASELINE.json configs on one GPU (kernel-only, streams resident in HBM), with the CPU
 oracle on a bounded sample beside each.  Writes a markdown table (stdout) -- the numbers quoted in
 DESIGN.md section 7 / profiles/configs_r1.md.  Not the driver's bench (that is bench.py = config 2).
-CONFIGS=3,5 restricts the run; NO_CPU=1 skips the oracle columns."""
+CONFIGS=3,5 restricts the run; NO_CPU=1 skips the oracle columns.  Configs 2 and 3 (thread-per-instance kernels) add a
+second row timed on sample-major streams (ACMEB200_SAMPLE_MAJOR)."""
 import json, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
@@ -16,12 +17,12 @@ NO_CPU = os.environ.get("NO_CPU", "0") == "1"
 rows, notes = [], []
 
 
-def timed(runner, U, Y, steps=2, warm=1):
-    for _ in range(warm): runner.run(U, Y, check_status=False)
+def timed(runner, U, Y, steps=2, warm=1, **kw):
+    for _ in range(warm): runner.run(U, Y, check_status=False, **kw)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(steps): runner.run(U, Y, check_status=False)
+    for _ in range(steps): runner.run(U, Y, check_status=False, **kw)
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / steps
 
@@ -46,6 +47,11 @@ def cfg2():  # diode clipper B=65536, 1 s @ 44.1 kHz
     ms = timed(r, U, Y); st = r.stats()
     c, ci = cpu(m, 32 * CORES, sine(N, 44100).reshape(1, -1), params=[P[:, ::B // (32 * CORES)][:, :32 * CORES]])
     rows.append(("2 diode clipper, B=65536 swept Is/eta, 1 s @44.1 kHz", r.kernel_name, B * N / ms / 1e3, 16 * B * N / ms / 1e6, st["newton_iters"] / st["solves"], c, ci))
+    r.reset()
+    Us = U.transpose(0, 1).contiguous(); Ys = torch.empty_like(Us)   # (N, B, nu): sample-major streams
+    ms = timed(r, Us, Ys, layout="sample"); st = r.stats()
+    assert torch.equal(Ys.transpose(0, 1), Y), "sample-major result differs from the default layout"
+    rows.append(("2 (same, sample-major streams)", r.kernel_name, B * N / ms / 1e3, 16 * B * N / ms / 1e6, st["newton_iters"] / st["solves"], float("nan"), float("nan")))
     r.close()
 
 
@@ -62,6 +68,13 @@ def cfg3():  # Sallen-Key, per-instance matrices, 1 s @ 96 kHz (256 distinct (R,
     ms = timed(r, U, Y)
     c, ci = cpu(base, 64 * CORES, sine(N, 96000).reshape(1, -1), overrides={k: v[..., :64 * CORES] for k, v in ov.items()})
     rows.append(("3 Sallen-Key, B=65536 per-instance matrices (256 distinct R/C pairs tiled), 1 s @96 kHz", r.kernel_name, B * N / ms / 1e3, 16 * B * N / ms / 1e6, 0.0, c, ci))
+    r.reset()
+    Yk = Y[:, ::97].clone(); del Y                                    # 4 x 50 GB would not fit: keep every 97th sample
+    Us = U.transpose(0, 1).contiguous(); del U                        # (N, B, nu): sample-major streams
+    Ys = torch.empty_like(Us)
+    ms = timed(r, Us, Ys, layout="sample")
+    assert torch.equal(Ys[::97].transpose(0, 1), Yk), "sample-major result differs from the default layout"
+    rows.append(("3 (same, sample-major streams)", r.kernel_name, B * N / ms / 1e3, 16 * B * N / ms / 1e6, 0.0, float("nan"), float("nan")))
     r.close()
 
 
