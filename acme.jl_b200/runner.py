@@ -279,8 +279,13 @@ class BatchRunner:
             return y
         return ybuf[:m.ny * N * B].reshape((m.ny, B, N), order="F")
 
-    def run_host_pinned(self, u_ptr: int, ustride: int, y_ptr: int, N: int):
-        """raw-pointer host run (used by bench.py for the end-to-end leg with pinned torch buffers)"""
+    def run_host_pinned(self, u_ptr: int, ustride: int, y_ptr: int, N: int, layout: str = "instance"):
+        """raw-pointer host run (used by bench.py for the end-to-end leg with pinned torch buffers);
+        ``ustride`` is the instance pitch, or the sample pitch with ``layout="sample"``"""
+        if layout == "sample":
+            check(lib().acmeb200_run(self._h, C.c_void_p(u_ptr), ustride, C.c_void_p(y_ptr),
+                                     self.model.ny * self.batch, N, _abi.SAMPLE_MAJOR, None))
+            return
         check(lib().acmeb200_run(self._h, C.c_void_p(u_ptr), ustride, C.c_void_p(y_ptr),
                                  self.model.ny * N, N, 0, None))
 

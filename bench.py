@@ -380,6 +380,9 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--kernel", default="auto")
+    ap.add_argument("--layout", default="instance", choices=["instance", "sample"],
+                    help="stream layout of config 2: instance-major (nu,N,B) = the reference's per-instance blocks (default, "
+                         "the measured headline) or sample-major (nu,B,N) (ACMEB200_SAMPLE_MAJOR, DESIGN.md 4.1b)")
     ap.add_argument("--config", type=int, default=2, choices=[2, 4],
                     help="BASELINE.json configs index: 2 = diode clipper sweep (the headline, default, weak scaling); "
                          "4 = superover B=8192 sharded over the GPUs (strong scaling, final output gather timed separately)")
@@ -422,8 +425,13 @@ def main():
     P = Pglobal[:, rank * Bper:(rank + 1) * Bper]
 
     row = torch.from_numpy(sine_row()).to(dev)
-    U = row.reshape(1, N_SAMPLES, 1).expand(Bper, N_SAMPLES, 1).contiguous()  # (B, N, nu): per-instance streams in HBM
-    Y = torch.empty((Bper, N_SAMPLES, 1), dtype=torch.float64, device=dev)
+    smaj = args.layout == "sample"
+    if smaj:  # (N, B, nu): one time step of the whole shard contiguous
+        U = row.reshape(N_SAMPLES, 1, 1).expand(N_SAMPLES, Bper, 1).contiguous()
+        Y = torch.empty((N_SAMPLES, Bper, 1), dtype=torch.float64, device=dev)
+    else:     # (B, N, nu): per-instance streams in HBM
+        U = row.reshape(1, N_SAMPLES, 1).expand(Bper, N_SAMPLES, 1).contiguous()
+        Y = torch.empty((Bper, N_SAMPLES, 1), dtype=torch.float64, device=dev)
     stream = torch.cuda.current_stream(dev)
 
     def barrier():
@@ -431,7 +439,7 @@ def main():
             dist.barrier()
 
     for _ in range(args.warmup):
-        runner.run(U, Y, check_status=False)
+        runner.run(U, Y, check_status=False, layout=args.layout)
     torch.cuda.synchronize()
     launches0 = runner.launch_count
     sampler = ClockSampler(local)
@@ -442,7 +450,7 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for _ in range(args.steps):
-        runner.run(U, Y, check_status=False)
+        runner.run(U, Y, check_status=False, layout=args.layout)
     e1.record(stream)
     torch.cuda.synchronize(); barrier()
     ms = e0.elapsed_time(e1)
@@ -470,16 +478,18 @@ def main():
         del U, Y
         torch.cuda.empty_cache()
         r2 = runner if Be == Bper else BatchRunner(model, Be, params=[P[:, :Be]], solver=SOLVER, kernel=args.kernel)
-        hu = torch.empty((Be, N_SAMPLES, 1), dtype=torch.float64, pin_memory=True)
-        hy = torch.empty((Be, N_SAMPLES, 1), dtype=torch.float64, pin_memory=True)
-        hu.copy_(row.cpu().reshape(1, N_SAMPLES, 1).expand(Be, N_SAMPLES, 1))
+        hshape = (N_SAMPLES, Be, 1) if smaj else (Be, N_SAMPLES, 1)
+        hu = torch.empty(hshape, dtype=torch.float64, pin_memory=True)
+        hy = torch.empty(hshape, dtype=torch.float64, pin_memory=True)
+        hu.copy_(row.cpu().reshape((N_SAMPLES, 1, 1) if smaj else (1, N_SAMPLES, 1)).expand(*hshape))
         e2e_steps = max(1, min(args.steps, 3))
-        r2.run_host_pinned(hu.data_ptr(), N_SAMPLES, hy.data_ptr(), N_SAMPLES)  # warm-up (allocates staging)
+        hstride = Be if smaj else N_SAMPLES  # doubles between samples / between instances
+        r2.run_host_pinned(hu.data_ptr(), hstride, hy.data_ptr(), N_SAMPLES, layout=args.layout)  # warm-up (allocates staging)
         barrier(); torch.cuda.synchronize()
         t0 = time.perf_counter()
         l0 = r2.launch_count
         for _ in range(e2e_steps):
-            r2.run_host_pinned(hu.data_ptr(), N_SAMPLES, hy.data_ptr(), N_SAMPLES)
+            r2.run_host_pinned(hu.data_ptr(), hstride, hy.data_ptr(), N_SAMPLES, layout=args.layout)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         le = r2.launch_count - l0
@@ -491,7 +501,7 @@ def main():
         e2e = {"value": Be * world * N_SAMPLES * e2e_steps / dt / 1e6, "unit": "Msamples/s",
                "h2d_bytes_per_step": int(Be * N_SAMPLES * 8), "d2h_bytes_per_step": int(Be * N_SAMPLES * 8),
                "batch_per_gpu": Be, "steps": e2e_steps, "kernel_launches": int(le),
-               "checksum": float(hy[0, :, 0].abs().sum())}
+               "checksum": float((hy[:, 0, 0] if smaj else hy[0, :, 0]).abs().sum())}
 
     if rank == 0:
         from acme_jl_b200._lib import measure_fp64_peak
@@ -508,7 +518,8 @@ def main():
                        "batch_per_gpu": Bper, "global_batch": Bper * world, "samples": N_SAMPLES, "solver": SOLVER,
                        "parallelism": f"instances sharded over {world} GPU(s), no data-path collective",
                        "l2": "inputs larger than L2 (23 GB U + 23 GB Y per GPU per step)",
-                       "kernel": runner.kernel_name},
+                       "kernel": runner.kernel_name,
+                       "layout": "sample-major (nu,B,N) streams" if smaj else "instance-major (nu,N,B) streams"},
             "clocks": clocks,
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
