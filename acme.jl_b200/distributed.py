@@ -40,20 +40,36 @@ class ShardedBatchRunner:
         """u_local: this rank's (count, N, nu) device tensor (or a shared (N, nu) one)."""
         return self.runner.run(u_local, y_local, **kw)
 
-    def gather(self, y_local, group=None):
-        return gather_outputs(y_local, self.batch_total, group=group)
+    def gather(self, y_local, group=None, layout: str = "instance"):
+        return gather_outputs(y_local, self.batch_total, group=group, layout=layout)
 
 
-def gather_outputs(y_local, batch_total: int, group=None):
+def gather_outputs(y_local, batch_total: int, group=None, layout: str = "instance"):
     """all-gather the (count_r, N, ny) output shards into the full (B, N, ny) tensor on every
-    rank.  Uneven shards are padded to the largest one for the collective and trimmed after."""
+    rank.  Uneven shards are padded to the largest one for the collective and trimmed after.
+    ``layout="sample"``: sample-major shards (N, count_r, ny) -> (N, B, ny) (the shards interleave
+    in memory, so the gathered blocks are re-assembled along the instance axis)."""
     import torch
     import torch.distributed as dist
+    if layout not in ("instance", "sample"):
+        raise ValueError("layout must be 'instance' or 'sample'")
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
         return y_local
     world = dist.get_world_size(group)
     counts = [shard_range(batch_total, world, r)[1] for r in range(world)]
     cmax = max(counts)
+    if layout == "sample":
+        N, cnt, ny = y_local.shape
+        if cnt != counts[dist.get_rank(group)]:
+            raise ValueError("y_local does not have this rank's shard size")
+        padded = y_local
+        if cnt != cmax:
+            padded = torch.zeros((N, cmax, ny), dtype=y_local.dtype, device=y_local.device)
+            padded[:, :cnt] = y_local
+        out = torch.empty((world * N, cmax, ny), dtype=y_local.dtype, device=y_local.device)
+        dist.all_gather_into_tensor(out, padded.contiguous(), group=group)
+        out = out.view(world, N, cmax, ny)
+        return torch.cat([out[r, :, :counts[r]] for r in range(world)], dim=1)
     tail = tuple(y_local.shape[1:])
     if y_local.shape[0] != counts[dist.get_rank(group)]:
         raise ValueError("y_local does not have this rank's shard size")

@@ -38,6 +38,9 @@ def _worker(rank, world, port, batch, N, ny, q):
         y = gather_outputs(y_local, batch)
         bb = torch.arange(batch, dtype=torch.float64).reshape(-1, 1, 1)
         ok = torch.equal(y, bb + 0.001 * n + 100 * k)
+        # sample-major shards (N, count, ny) gather into (N, B, ny)
+        ys = gather_outputs(y_local.transpose(0, 1).contiguous(), batch, layout="sample")
+        ok = ok and tuple(ys.shape) == (N, batch, ny) and torch.equal(ys, (bb + 0.001 * n + 100 * k).transpose(0, 1))
         q.put((rank, bool(ok), tuple(y.shape)))
     finally:
         dist.destroy_process_group()
