@@ -143,3 +143,12 @@ def test_gpu_parity_suite_subset_under_emulation(emu_lib):
     tail = res.stdout.strip().splitlines()[-1] if res.stdout.strip() else res.stderr[-500:]
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-1000:]
     assert " passed" in tail and int(tail.split(" passed")[0].split()[-1]) >= 20, tail
+
+
+def test_cuda_kernels_against_independent_full_system_solve_under_emulation(emu_lib):
+    """tests/test_independent.py's GPU test -- the four BASELINE circuits through the kernels' own sources against a
+    full-system Newton solve of the circuit equations (no DK reduction, no oracle) -- on the emulated library"""
+    env = dict(os.environ, ACMEB200_LIB=emu_lib)
+    res = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_independent.py"), "-m", "gpu", "-q", "-x",
+                          "-p", "no:cacheprovider"], env=env, capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert res.returncode == 0 and "1 passed" in res.stdout, res.stdout[-3000:] + res.stderr[-1000:]
