@@ -346,6 +346,29 @@ __device__ __forceinline__ int tpi_cache_nearest(const DevSub& c, int64_t inst, 
     }
     return cidx;
 }
+#ifndef ACME_TPI_CACHE_REG
+#define ACME_TPI_CACHE_REG 0  // experiment (off: unmeasured): the stored-solution count lives in a register for the whole
+                              // call and a cache that still holds only its initial entry (0, init_z) is searched without
+                              // touching memory -- config 2's common case pays two dependent loads per sample for it
+#endif
+#if ACME_TPI_CACHE_REG
+// same result as tpi_cache_nearest for a known count n: with n == 1 the only entry is slot 0 = (p = 0, init_z)
+// (written at initialisation, overwritten only when the ring wraps), whose squared distance is |p|^2
+template <class C>
+__device__ __forceinline__ int tpi_cache_nearest_reg(const DevSub& c, int64_t inst, int64_t ld,
+                                                     const double (&p)[dim1(C::NP)], const double (&lp)[dim1(C::NP)], int n) {
+    double best = 0.0, d0 = 0.0;
+    static_for<0, C::NP>([&](auto ii) {
+        constexpr int i = decltype(ii)::value;
+        const double d = p[i] - lp[i];
+        best = fma(d, d, best);
+        d0 = fma(p[i], p[i], d0);
+    });
+    if (n == 1) return d0 < best ? 0 : -1;
+    int dummy;
+    return tpi_cache_nearest<C>(c, inst, ld, p, lp, dummy);
+}
+#endif
 template <class C>
 __device__ __forceinline__ void tpi_cache_append(const DevSub& c, int64_t inst, int64_t ld, int n,
                                                  const double (&p)[dim1(C::NP)], const double (&z)[dim1(C::NN)]) {
@@ -562,7 +585,11 @@ __device__ __forceinline__ void tpi_output_update(const M& m, TpiState<C>& S, co
 template <class C, class M>
 __device__ __forceinline__ int tpi_step_hot(const M& m, const double (&Cn)[dim1(C::NC)], TpiState<C>& S,
                                             const double (&u)[dim1(C::NU)], double (&y)[dim1(C::NY)],
-                                            const SolverCfg& sc, const DevSub& cache, int64_t inst, int64_t ld) {
+                                            const SolverCfg& sc, const DevSub& cache, int64_t inst, int64_t ld
+#if ACME_TPI_CACHE_REG
+                                            , int& ncache  // stored solutions of this instance (register copy of dyn_n[inst])
+#endif
+) {
     constexpr int NN = C::NN, NP = C::NP;
     double zall[dim1(NN)];
     int iters = 0;
@@ -573,7 +600,11 @@ __device__ __forceinline__ int tpi_step_hot(const M& m, const double (&Cn)[dim1(
         const bool caching = sc.solver == ACMEB200_SOLVER_HOMOTOPY_CACHING;
         if (caching) {
             if (cache.cache_n > 0) return -1;  // frozen k-d tree: the cold path does the lookup
+#if ACME_TPI_CACHE_REG
+            if (cache.dyn_cap > 0) { n_cache = ncache; cidx = tpi_cache_nearest_reg<C>(cache, inst, ld, p, S.lp, ncache); }
+#else
             if (cache.dyn_cap > 0) cidx = tpi_cache_nearest<C>(cache, inst, ld, p, S.lp, n_cache);
+#endif
         }
         const int64_t e = cidx < 0 ? 0 : cidx;
         if (!tpi_simple_solve<C>(m, Cn, S, p, zall, sc, iters, cidx >= 0, cache.dyn_ps + (e * NP) * ld + inst,
@@ -581,7 +612,11 @@ __device__ __forceinline__ int tpi_step_hot(const M& m, const double (&Cn)[dim1(
             if (sc.solver != ACMEB200_SOLVER_SIMPLE) return -(iters + 1);
             return -(iters + 1) - (1 << 20);  // SimpleSolver only: no homotopy, the failure is final
         }
+#if ACME_TPI_CACHE_REG
+        if (caching && iters > 5 && cache.dyn_cap > 0) { tpi_cache_append<C>(cache, inst, ld, n_cache, p, zall); ncache = n_cache + 1; }
+#else
         if (caching && iters > 5 && cache.dyn_cap > 0) tpi_cache_append<C>(cache, inst, ld, n_cache, p, zall);
+#endif
     }
     tpi_output_update<C>(m, S, u, zall, y);
     return iters;
@@ -714,6 +749,11 @@ __global__ void __launch_bounds__(TPI_TPB, ACME_TPI_MINB) k_tpi(const __grid_con
     static_for<0, NN>([&](auto i) { S.lz[decltype(i)::value] = st[(int64_t)(C::S_LZ + decltype(i)::value) * a.ld]; });
     static_for<0, NN * NP>([&](auto i) { S.Mx[decltype(i)::value] = st[(int64_t)(C::S_MX + decltype(i)::value) * a.ld]; });
 
+#if ACME_TPI_CACHE_REG
+    int ncache = 0;
+    if constexpr (NN > 0)
+        if (sc.solver == ACMEB200_SOLVER_HOMOTOPY_CACHING && cache.cache_n == 0 && cache.dyn_cap > 0) ncache = cache.dyn_n[inst];
+#endif
     bool dead = !active || (a.status[inst] & ACMEB200_STATUS_NONFINITE);
     int dead_at = dead ? 0 : -1;  // sample index (this call) at which the instance halted, -1 = alive
     const bool shared_u = (a.u_stride == 0) || NU == 0;
@@ -842,7 +882,11 @@ __global__ void __launch_bounds__(TPI_TPB, ACME_TPI_MINB) k_tpi(const __grid_con
                         constexpr int q = decltype(kk)::value;
                         u[q] = shared_u ? __ldg(a.U + (int64_t)(n0 + tt) * NU + q) : in_at(tt * NU + q);
                     });
+#if ACME_TPI_CACHE_REG
+                    code = tpi_step_hot<C>(m, Cn, S, u, y, sc, cache, inst, a.ld, ncache);
+#else
                     code = tpi_step_hot<C>(m, Cn, S, u, y, sc, cache, inst, a.ld);
+#endif
                     if (code < 0) break;
                     if (NN > 0) {
                         if (code <= 8) hist_s[(code - 1) * 32] += 1u;
@@ -859,6 +903,10 @@ __global__ void __launch_bounds__(TPI_TPB, ACME_TPI_MINB) k_tpi(const __grid_con
                         u[q] = shared_u ? __ldg(a.U + (int64_t)(n0 + tt) * NU + q) : in_at(tt * NU + q);
                     });
                     const int it = tpi_step_cold<C>(&m, Cn, &S, u, y, &sc, &cache, &a, inst, n0 + tt, code);
+#if ACME_TPI_CACHE_REG
+                    if constexpr (NN > 0)
+                        if (cache.dyn_cap > 0) ncache = cache.dyn_n[inst];  // the cold solve may have stored a solution
+#endif
                     if (it < 0) { dead = true; dead_at = n0 + tt; break; }
                     if (it >= 1 && it <= 8) hist_s[(it - 1) * 32] += 1u;
                     static_for<0, NY>([&](auto kk) { out_at(tt * NY + decltype(kk)::value) = y[decltype(kk)::value]; });

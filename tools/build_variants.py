@@ -1,7 +1,8 @@
 """Kernel tuning: build variants of the thread-per-instance translation unit (tpi.cu) with different
 CTA sizes / tile lengths / pipeline depths and link each into its own library under tools/libs/
 (select one with ACMEB200_LIB=tools/libs/lib_<name>.so; tools/kbench_cfg3.py times configs 2 and 3).
-usage: python tools/build_variants.py name:TPB:MINB:T:STAGES:OSTAGES [...]   e.g.  base:64:8:8:2:2 t16:64:8:16:2:1"""
+usage: python tools/build_variants.py name:TPB:MINB:T:STAGES:OSTAGES[:DEFINE=VALUE,...] [...]
+e.g.  base:64:8:8:2:2 t16:64:8:16:2:1 creg:64:8:8:2:2:ACME_TPI_CACHE_REG=1"""
 import os
 import subprocess
 import sys
@@ -14,10 +15,11 @@ libs = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libs")
 os.makedirs(libs, exist_ok=True)
 procs = []
 for spec in sys.argv[1:]:
-    name, tpb, mb, T, st, ost = spec.split(":")
+    name, tpb, mb, T, st, ost, *extra = spec.split(":")
+    defines = [f"-D{d}" for d in extra[0].split(",")] if extra else []
     obj = f"{libs}/tpi_{name}.o"
     cmd = [b.nvcc()] + b.NVCC_FLAGS + [f"-DACME_TPI_TPB={tpb}", f"-DACME_TPI_MINB={mb}", f"-DACME_TPI_T={T}",
-                                      f"-DACME_TPI_STAGES={st}", f"-DACME_TPI_OSTAGES={ost}", "-Xptxas", "-v", "-c", "-o", obj,
+                                      f"-DACME_TPI_STAGES={st}", f"-DACME_TPI_OSTAGES={ost}"] + defines + ["-Xptxas", "-v", "-c", "-o", obj,
                                       os.path.join(b.CSRC, "tpi.cu")]
     procs.append((name, obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
 for name, obj, p in procs:
