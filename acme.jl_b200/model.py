@@ -329,8 +329,21 @@ def split_nl_model_matrices(mats, model_qidxs, model_nns):
         q0s=[mats["q0"][qidxs].copy() for qidxs in model_qidxs])
 
 
-def reduce_pdims(mats):
-    """ACME.jl:403-451"""
+def reduce_pdims(mats, fix: bool = False):
+    """ACME.jl:403-451.
+
+    When the projection lowers the rank of ``pexp`` the component of ``pexp*p`` inside the column space of
+    ``fq`` is absorbed into z: ``z = z' - P (dq x + eq u + fqprev z_prev)`` with ``P = fq_pinv * pexp``, and every
+    user of z has to be corrected.  AS WRITTEN the reference corrects ``a, b, dy, ey`` and the later sub-problems'
+    ``dq_full, eq_full``, but (1) its correction of the later sub-problems' ``fqprev_full[:, 1:offset]``
+    (ACME.jl:435-438) is a ``copyto!`` into ``X[:, 1:offset]`` -- a fresh copy in Julia, so it has no effect -- and
+    (2) ``c[:, 1:offset]`` and ``fy[:, 1:offset]`` are not corrected for the ``fqprev z_prev`` term at all.  Both only
+    matter for models with several sub-problems whose reduced one has ``offset > 0`` and a non-zero ``fqprev`` (none of
+    the BASELINE configs; the three-sub-problem "simplified superover" of runtests.jl:751-756 is one): there the
+    as-written model deviates from the circuit equations (tests/test_independent.py measures 3 V on that circuit
+    against a full-system solve).  ``fix=False`` (default) restates the reference as written, because parity is
+    against the reference; ``fix=True`` applies all corrections and agrees with the full-system solve to 1e-10.
+    """
     subcount = len(mats["dq_fulls"])
     dqs, eqs, fqprevs, pexps = [None] * subcount, [None] * subcount, [None] * subcount, [None] * subcount
     offset = 0
@@ -355,11 +368,14 @@ def reduce_pdims(mats):
             mats["b"] = mats["b"] - _dot(cproj, eqs[idx])
             mats["dy"] = mats["dy"] - _dot(fyproj, dqs[idx])
             mats["ey"] = mats["ey"] - _dot(fyproj, eqs[idx])
+            if fix and offset:
+                mats["c"][:, :offset] = mats["c"][:, :offset] - _dot(cproj, fqprevs[idx][:, :offset])
+                mats["fy"][:, :offset] = mats["fy"][:, :offset] - _dot(fyproj, fqprevs[idx][:, :offset])
             for idx2 in range(idx + 1, subcount):
                 q = _dot(mats["fqprev_fulls"][idx2][:, cols], proj)
                 mats["dq_fulls"][idx2] = mats["dq_fulls"][idx2] - _dot(q, dqs[idx])
                 mats["eq_fulls"][idx2] = mats["eq_fulls"][idx2] - _dot(q, eqs[idx])
-                if offset:
+                if fix and offset:  # ACME.jl:435-438 writes this into a temporary copy: no effect as written
                     mats["fqprev_fulls"][idx2][:, :offset] = (
                         mats["fqprev_fulls"][idx2][:, :offset] - _dot(q, fqprevs[idx][:, :offset]))
             pexps[idx] = pexp
@@ -403,8 +419,9 @@ class DiscreteModel:
     """Float64 model, field for field the reference's struct (ACME.jl:118-148)."""
 
     def __init__(self, circ: Optional[Circuit] = None, t=None, *, decompose_nonlinearity=True,
-                 solver="HomotopySolver{CachingSolver{SimpleSolver}}"):
+                 solver="HomotopySolver{CachingSolver{SimpleSolver}}", fix_reduce_pdims: bool = False):
         self.solver = solver
+        self.fix_reduce_pdims = fix_reduce_pdims  # see reduce_pdims: False = the reference as written
         if circ is None:
             return
         self._derive(circ, fr(t), decompose_nonlinearity)
@@ -425,7 +442,7 @@ class DiscreteModel:
         qr = consecranges(nqs)
         model_qidxs = [[r for e in nles for r in qr[e]] for nles in nl_elems]
         mats.update(split_nl_model_matrices(mats, model_qidxs, model_nns))
-        mats = reduce_pdims(mats)
+        mats = reduce_pdims(mats, self.fix_reduce_pdims)
         model_nqs = [p.shape[0] for p in mats["pexps"]]
         assert circ.nn == sum(model_nns)
         tables = [circ.nl_table(nles) for nles in nl_elems]
@@ -462,7 +479,7 @@ class DiscreteModel:
             nl_elems = [nl_elems[i] for i in keep]
             mats["fy"] = mats["fy"][:, varying]
             mats["c"] = mats["c"][:, varying]
-            mats = reduce_pdims(mats)
+            mats = reduce_pdims(mats, self.fix_reduce_pdims)
 
         self.a = _f64(mats["a"]); self.b = _f64(mats["b"]); self.c = _f64(mats["c"])
         self.x0 = _f64(mats["x0"])

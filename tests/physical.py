@@ -90,8 +90,10 @@ def full_system_run(circ, fs, u, newton_tol=1e-13, maxiter=400):
                 return w, False
             w = w + lam * dw
             r, Jq = r1, Jq1
-            if r0 < 1e-12 and np.abs(r1).max() > 0.5 * r0:
-                return w, True   # the residual sits at its rounding floor (quadratic convergence has ended)
+            if r0 < 1e-12 and np.abs(r1).max() > 0.5 * r0 and \
+                    np.abs(dw[2 * nb:]).max() <= 1e-10 * (1.0 + np.abs(w[2 * nb:]).max()):
+                return w, True   # residual at its rounding floor and the steps down to noise in a badly conditioned
+                                 # direction (a reverse-biased diode's 1e-12 A/V); larger steps are still refinement
         return w, False
 
     rhs_prev = np.zeros(nl + nb)   # w = 0 solves the source-free circuit (every element law has f(0) = 0)

@@ -91,3 +91,62 @@ def test_cuda_path_against_full_system_solve():
         r.close()
         assert np.array_equal(y[:, :, 0], y[:, :, 1])
         assert rel_err(y[:, :, 0], yp) < 1e-7, r.kernel_name
+
+
+def test_reference_test_circuits_against_full_system_solve():
+    """the circuits of the reference's known-answer tests (RC ladder G2, decomposed diode network K6, Gummel-Poon BJTs K7,
+    MOSFET K8, op-amps K9) and the three-sub-problem "simplified superover" (runtests.jl:751-756), stepped through
+    time: every element law and the non-linearity decomposition / sub-problem chaining against the un-reduced system"""
+    import acme_jl_b200 as A
+    from fractions import Fraction
+    N = 120
+    # drive levels that make the probed diode currents (is*exp(v/vt)) large against the 1e-13 A stopping rule
+    two = np.vstack([sine(N, amp=1.2), 0.6 * np.cos(2 * np.pi * 300 / 44100 * np.arange(N)).reshape(1, -1)])
+    jobs = [("rc_ladder", cases.rc_ladder(), sine(N)),
+            ("three_diodes", cases.three_diodes(), two),
+            ("npn", cases.bjt_circuit("npn", ile=1e-8, ilc=2e-8, ηcl=1.5, ηel=1.4, vaf=10, var=50, ikf=5e-2, ikr=1e-1), cases.bjt_input("npn", N)),
+            ("pnp", cases.bjt_circuit("pnp", vaf=10, ikr=1e-1), cases.bjt_input("pnp", N)),
+            ("nmos", cases.mosfet_circuit("n", vt=1, α=1e-4, λ=0.1), np.vstack([2 + sine(N), 1.5 + 2 * sine(N, amp=1)[:, ::-1]])),
+            ("shelving", cases.opamp_shelving(1000, 5e5), sine(N)),
+            ("tanh", cases.opamp_tanh(), sine(N, amp=0.2))]
+    for name, circ, u in jobs:
+        model = A.DiscreteModel(circ, Fraction(1, 44100))
+        yp, _ = physical.full_system_run(circ, 44100, u)
+        # current-driven high-impedance nodes turn the 1e-13 A stopping rule into 1e-8 V: tighten it further there
+        yo = OracleModel(model, 1, solver=H, tol=1e-15 if name == "npn" else 1e-13).run(u, threads=0)[:, :, 0]
+        for k in range(yo.shape[0]):                                      # every probe against its own peak
+            assert rel_err(yo[k], yp[k]) < 1e-7, (name, k)
+    assert len(A.DiscreteModel(cases.three_diodes(), Fraction(1, 44100)).subs) == 2      # K6: decomposed
+
+
+def test_multi_subproblem_model_and_the_reference_reduce_pdims_quirk():
+    """The three-sub-problem "simplified superover" (runtests.jl:751-756; the reference checks np = 2, 1, 2 and leaves
+    `# TODO: further validate y`).  Its derivation goes through the rank-lowering branch of reduce_pdims!
+    (ACME.jl:425-447) with offset > 0 and a non-zero fqprev -- where the reference AS WRITTEN drops the fqprev
+    correction (a copyto! into a slice copy, ACME.jl:435-438) and never corrects c / fy for the fqprev term
+    (acme_jl_b200/model.py::reduce_pdims).  Measured against the full-system solve: the as-written model is off by
+    volts, the fully corrected one (fix_reduce_pdims=True) agrees to 1e-10, as does the undecomposed single-sub model.
+    The restatement defaults to "as written" because parity is against the reference; this test pins the finding."""
+    import acme_jl_b200 as A
+    from fractions import Fraction
+    N = 80
+    u = sine(N)
+    circ = lambda: ex.superover_circuit(1.0, 1.0, 1.0, vb_source=True)
+    yp, _ = physical.full_system_run(circ(), 44100, u)
+    as_written = A.DiscreteModel(circ(), Fraction(1, 44100))
+    fixed = A.DiscreteModel(circ(), Fraction(1, 44100), fix_reduce_pdims=True)
+    single = A.DiscreteModel(circ(), Fraction(1, 44100), decompose_nonlinearity=False)
+    assert [s.nn for s in as_written.subs] == [s.nn for s in fixed.subs] == [2, 3, 2] and len(single.subs) == 1
+    assert [s.np_ for s in as_written.subs] == [2, 1, 2]                  # runtests.jl:757-759
+    assert rel_err(oracle_run(fixed, u), yp) < 1e-7
+    assert rel_err(oracle_run(single, u), yp) < 1e-7
+    assert np.abs(oracle_run(as_written, u) - yp).max() > 1.0             # volts: the quirk is real on this circuit
+    # none of the BASELINE circuits takes that branch: their models are identical with and without the corrections
+    for c in (ex.diodeclipper_circuit, ex.sallenkey_circuit, ex.birdie_circuit, lambda: ex.birdie_circuit(0.8),
+              ex.superover_circuit, lambda: ex.superover_circuit(0.6, 0.4, 1.0)):
+        m0, m1 = A.DiscreteModel(c(), Fraction(1, 44100)), A.DiscreteModel(c(), Fraction(1, 44100), fix_reduce_pdims=True)
+        for key in ("a", "b", "c", "dy", "ey", "fy", "x0", "y0"):
+            assert np.array_equal(getattr(m0, key), getattr(m1, key))
+        for s0, s1 in zip(m0.subs, m1.subs):
+            for key in ("dq", "eq", "fqprev", "pexp", "q0", "fq"):
+                assert np.array_equal(getattr(s0, key), getattr(s1, key))
