@@ -118,6 +118,63 @@ def full_system_run(circ, fs, u, newton_tol=1e-13, maxiter=400):
     return y, x
 
 
+def dc_solve(circ, u):
+    """steady state of the continuous-time circuit for a constant input u: the element equations with x' = x and
+    xdot = 0 (mv v + mi i + mx x + mq q = u0 + mu u), Kirchhoff, element laws -- source stepping + damped Newton as
+    above.  Returns the state vector x (what steadystate(model, u) computes through (I - a)^-1, ACME.jl:474-497)."""
+    nb, nx, nq = circ.nb, circ.nx, circ.nq
+    mv, mi, mx, mq, mu = (_f(circ.blockdiag(k)) for k in ("mv", "mi", "mx", "mq", "mu"))
+    u0 = _f(circ.u0()).reshape(-1)
+    tv, ti = (_f(m).reshape(-1, nb) for m in circ.topomat())
+    nl = mv.shape[0]
+    table = circ.nl_table()
+    nn = sum(e.nn for e, _ in table)
+    nw = 2 * nb + nx + nq
+    L = np.zeros((nl + nb, nw))
+    L[:nl, :nb], L[:nl, nb:2 * nb], L[:nl, 2 * nb:2 * nb + nx], L[:nl, 2 * nb + nx:] = mv, mi, mx, mq
+    L[nl:nl + len(tv), :nb] = tv
+    L[nl + len(tv):, nb:2 * nb] = ti
+    rhs_full = np.concatenate([u0 + mu @ np.asarray(u, float).reshape(-1), np.zeros(nb)])
+    J = np.zeros((nw, nw))
+    J[:nl + nb] = L
+
+    def newton(w, rhs):
+        for it in range(300):
+            res, Jq = eval_table(table, w[2 * nb + nx:], nn)
+            r = np.concatenate([L @ w - rhs, res])
+            J[nl + nb:, :] = 0.0
+            J[nl + nb:, 2 * nb + nx:] = Jq
+            dr = 1.0 / np.maximum(np.abs(J).max(axis=1), 1e-300)
+            dc = 1.0 / np.maximum(np.abs(J * dr[:, None]).max(axis=0), 1e-300)
+            dw = dc * np.linalg.lstsq(J * dr[:, None] * dc[None, :], -r * dr, rcond=1e-15)[0]
+            if np.abs(dw).max() <= 1e-13 * (1.0 + np.abs(w).max()):
+                return w + dw, True
+            lam, r0 = 1.0, np.abs(r).max()
+            while lam >= 1e-6:
+                with np.errstate(over="ignore", invalid="ignore"):
+                    w1 = w + lam * dw
+                    res1, _ = eval_table(table, w1[2 * nb + nx:], nn)
+                    r1 = np.concatenate([L @ w1 - rhs, res1])
+                if np.all(np.isfinite(r1)) and np.abs(r1).max() <= r0:
+                    break
+                lam /= 2
+            if lam < 1e-6:
+                return w, np.abs(r).max() < 1e-12
+            w = w1
+        return w, False
+
+    w, a, da = np.zeros(nw), 0.0, 0.25
+    while a < 1.0:
+        w2, ok = newton(w, min(1.0, a + da) * rhs_full)
+        if ok:
+            a, w, da = min(1.0, a + da), w2, min(2 * da, 0.25)
+        else:
+            da /= 2
+            if da < 1e-6:
+                raise RuntimeError("dc_solve: no convergence")
+    return w[2 * nb:2 * nb + nx]
+
+
 def sallenkey_lfilter(u, fs, r1=10e3, r2=10e3, c1=10e-9, c2=10e-9):
     """unity-gain Sallen-Key low-pass H(s) = 1 / (1 + s c2 (r1 + r2) + s^2 r1 r2 c1 c2) (c1 = feedback capacitor,
     examples/sallenkey.jl:6-17), bilinear transform s = 2 fs (z-1)/(z+1) -- what trapezoidal capacitors amount to"""

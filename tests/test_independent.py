@@ -150,3 +150,17 @@ def test_multi_subproblem_model_and_the_reference_reduce_pdims_quirk():
         for s0, s1 in zip(m0.subs, m1.subs):
             for key in ("dq", "eq", "fqprev", "pexp", "q0", "fq"):
                 assert np.array_equal(getattr(s0, key), getattr(s1, key))
+
+
+def test_steadystate_against_dc_solve_of_the_circuit():
+    """steadystate(model, u) (ACME.jl:474-497: through (I - a)^-1 and a derived non-linear system) against the DC
+    solution of the un-reduced circuit equations (xdot = 0): all four example circuits, both superover / birdie readings"""
+    for name, circ, model, u in (("clipper", ex.diodeclipper_circuit(), ex.diodeclipper(), [0.3]),
+                                 ("sallenkey", ex.sallenkey_circuit(), ex.sallenkey(), [0.3]),
+                                 ("birdie", ex.birdie_circuit(0.8), ex.birdie(vol=0.8), [0.1]),
+                                 ("birdie_vol", ex.birdie_circuit(), ex.birdie(), [0.1, 0.6]),
+                                 ("superover", ex.superover_circuit(), ex.superover(), [0.05, 0.6, 0.4, 1.0]),
+                                 ("superover_fixed", ex.superover_circuit(0.6, 0.4, 1.0), ex.superover(0.6, 0.4, 1.0), [0.05])):
+        xd = physical.dc_solve(circ, u)
+        xs = np.asarray(model.steadystate(u)).reshape(-1)
+        assert np.abs(xd - xs).max() <= 1e-9 * np.abs(xs).max(), name
