@@ -164,3 +164,18 @@ def test_steadystate_against_dc_solve_of_the_circuit():
         xd = physical.dc_solve(circ, u)
         xs = np.asarray(model.steadystate(u)).reshape(-1)
         assert np.abs(xd - xs).max() <= 1e-9 * np.abs(xs).max(), name
+
+
+def test_g1_doctest_vector_from_the_independent_solve():
+    """config 1 at full length: the full-system solve itself reproduces the reference's printed doctest samples
+    (docs/src/gettingstarted.md:106-113 -- the first four and, after 44 100 steps, the last three), and the oracle
+    agrees with it over the whole second"""
+    u = cases.sine()
+    yp, _ = physical.full_system_run(ex.diodeclipper_circuit(), 44100, u)
+    g = cases.golden()["G1_diodeclipper_doctest"]
+    assert yp.shape[1] == g["n"]
+    for got, want in zip(yp[0, :4], g["first"]):
+        cases.assert_printed_equal(got, want, g["printed_digits"])
+    for got, want in zip(yp[0, -3:], g["last"]):
+        cases.assert_printed_equal(got, want, g["printed_digits"])
+    assert rel_err(oracle_run(ex.diodeclipper(), u), yp) < 1e-7
