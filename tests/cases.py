@@ -145,6 +145,34 @@ def opamp_tanh():
     ])
 
 
+def ja_inductor():
+    """runtests.jl:433-440: Jiles-Atherton inductor next to its approximate linear equivalent (174 mH)"""
+    from acme_jl_b200 import inductor
+    return circuit([("Jin", voltagesource(), {}),
+                    ("Jout1", currentprobe(), {"+": ("Jin", "+")}),
+                    ("Jout2", currentprobe(), {"+": ("Jin", "+")}),
+                    ("L_JA", inductor(ja=True), {"1": ("Jout1", "-"), "2": ("Jin", "-")}),
+                    ("L_lin", inductor(174e-3), {"1": ("Jout2", "-"), "2": ("Jin", "-")})])
+
+
+def ja_transformer():
+    """runtests.jl:459-468: Jiles-Atherton transformer next to its approximate small-signal equivalent"""
+    from acme_jl_b200 import transformer
+    return circuit([("Jin", voltagesource(), {}),
+                    ("R1", resistor(10), {"1": ("Jin", "+")}),
+                    ("R2", resistor(10), {"1": ("Jin", "+")}),
+                    ("T_JA", transformer(ja=True, ns=[10, 100]), {"1": ("R1", "2"), "2": ("Jin", "-")}),
+                    ("T_lin", transformer(330e-6, 33e-3), {"primary1": ("R2", "2"), "primary2": ("Jin", "-")}),
+                    ("Jout1", voltageprobe(gp=1e-3), {"+": ("T_JA", "3"), "-": ("T_JA", "4")}),
+                    ("Jout2", voltageprobe(gp=1e-3), {"+": ("T_lin", "secondary1"), "-": ("T_lin", "secondary2")})])
+
+
+def julia_isapprox(a, b, rtol):
+    """isapprox for arrays: norm(a - b) <= rtol * max(norm(a), norm(b))"""
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    return bool(np.linalg.norm(a - b) <= rtol * max(np.linalg.norm(a), np.linalg.norm(b)))
+
+
 def test_quad_model(p0=0.0, z0=1.0):
     """The scalar equation z^2 - 1 + p = 0 of runtests.jl:207-219 as a one-sub
     model: q = [z; p], u = p, y = z."""

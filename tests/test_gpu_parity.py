@@ -911,3 +911,30 @@ def test_sample_major_device_tensors():
     r.reset()
     assert np.array_equal(r.run(_smaj(u_host), layout="sample"), _smaj(y_host))
     r.close()
+
+
+@pytest.mark.parametrize("kernel", ["auto", "generic"])
+def test_K12_jiles_atherton_elements(kernel):
+    """the Jiles-Atherton inductor / transformer circuits of runtests.jl:431-480 on the device: parity with the
+    oracle through a hysteresis loop, a batch of different drive levels, state carried across run! calls"""
+    B = 5
+    lv = np.linspace(0.5, 1.5, B)
+    m = A.DiscreteModel(cases.ja_inductor(), 1 / 44100)
+    u = np.concatenate([np.full(400, 0.1), np.full(700, -0.1), np.zeros(100)])
+    U = np.asfortranarray(u[None, :, None] * lv[None, None, :])
+    yref = OracleModel(m, B, solver=H).run(U, threads=0)
+    r = BatchRunner(m, B, solver=H, kernel=kernel)
+    y = np.concatenate([r.run(np.asfortranarray(U[:, :500])), r.run(np.asfortranarray(U[:, 500:]))], axis=1)
+    r.close()
+    for k in range(2):
+        assert_parity(y[k], yref[k])
+    assert np.all(y[0, 1099] < 0) and np.allclose(y[0, 1100], y[0, -1], rtol=1e-8)   # remanence, shorted: constant
+    m = A.DiscreteModel(cases.ja_transformer(), 1 / 44100)
+    s = np.sin(2 * np.pi * 1000 / 44100 * np.arange(400))
+    U = np.asfortranarray(np.concatenate([0.002 * s, 10 * s])[None, :, None] * lv[None, None, :])
+    yref = OracleModel(m, B, solver=H).run(U, threads=0)
+    r = BatchRunner(m, B, solver=H, kernel=kernel)
+    y = r.run(U)
+    r.close()
+    for k in range(2):
+        assert_parity(y[k], yref[k])

@@ -179,3 +179,23 @@ def test_g1_doctest_vector_from_the_independent_solve():
     for got, want in zip(yp[0, -3:], g["last"]):
         cases.assert_printed_equal(got, want, g["printed_digits"])
     assert rel_err(oracle_run(ex.diodeclipper(), u), yp) < 1e-7
+
+
+def test_jiles_atherton_against_full_system_solve():
+    """the Jiles-Atherton inductor and transformer circuits of runtests.jl:431-480 through their hysteresis loops:
+    the C restatement of the element law (oracle) against the Python one inside the full-system solve"""
+    import acme_jl_b200 as A
+    from fractions import Fraction
+    u = np.concatenate([np.full(300, 0.1), np.full(500, -0.1), np.zeros(100)]).reshape(1, -1)
+    circ = cases.ja_inductor()
+    yp, _ = physical.full_system_run(circ, 44100, u)
+    yo = oracle_run(A.DiscreteModel(circ, Fraction(1, 44100)), u)
+    for k in range(2):
+        assert rel_err(yo[k], yp[k]) < 1e-7
+    s = np.sin(2 * np.pi * 1000 / 44100 * np.arange(300)).reshape(1, -1)
+    u = np.hstack([0.002 * s, 10 * s])
+    circ = cases.ja_transformer()
+    yp, _ = physical.full_system_run(circ, 44100, u)
+    yo = oracle_run(A.DiscreteModel(circ, Fraction(1, 44100)), u)
+    for k in range(2):
+        assert rel_err(yo[k], yp[k]) < 1e-7

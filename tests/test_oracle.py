@@ -306,3 +306,38 @@ def test_K11_linearization_bounds():
     assert linearization_error(ex.superover(1.0, 1.0, 1.0), 1e-4) < 1.5e-4
     assert linearization_error(ex.birdie(vol=0.8), 1e-4, tol=1e-13) < 1e-7
     assert linearization_error(ex.superover(1.0, 1.0, 1.0), 1e-4, tol=1e-13) < 1e-4
+
+
+# ------------------------------------------------------------------ K12: Jiles-Atherton inductor / transformer
+def test_K12_jiles_atherton_inductor():
+    """runtests.jl:431-457: hysteresis of the Jiles-Atherton inductor against its linear equivalent; state persists
+    across the run! calls (here: one stream cut at the same points)"""
+    m = A.DiscreteModel(cases.ja_inductor(), 1 / 44100)
+    o = OracleModel(m, 1)
+    run = lambda u: o.run(np.asarray(u, float).reshape(1, -1), threads=0)[:, :, 0]
+    y = run(np.full(750, 0.1))
+    assert cases.julia_isapprox(y[0, :9], y[1, :9], 1e-2)        # almost linear at first
+    assert np.all(y[0] < y[1])                                   # sub-linear while unmagnetised
+    run(np.full(500, 0.1))
+    y = run(np.full(750, 0.1))
+    assert np.all(y[0] > y[1])                                   # super-linear in saturation
+    y = run(np.full(2000, -0.1))
+    assert y[0, -1] < -2e-3                                      # hysteresis drives the current below zero
+    y = run(np.zeros(1000))
+    assert y[0, 0] < -2e-3 and np.allclose(y[:, :1], y, rtol=1e-8, atol=0)   # shorted: the current stays
+    assert o.status()[0][0] == 0
+
+
+def test_K12_jiles_atherton_transformer():
+    """runtests.jl:458-480"""
+    m = A.DiscreteModel(cases.ja_transformer(), 1 / 44100)
+    o = OracleModel(m, 1)
+    u = np.sin(2 * np.pi * 1000 / 44100 * np.arange(500)).reshape(1, -1)
+    y = o.run(0.001 * u, threads=0)[:, 199:, 0]
+    assert cases.julia_isapprox(y[0], y[1], 1.2e-3)              # almost linear for small input
+    y = o.run(0.002 * u, threads=0)[:, 199:, 0]
+    assert cases.julia_isapprox(y[0], y[1], 1.2e-3)
+    # `run!(model, 10*u)[200:end]` indexes the 2 x 500 matrix linearly; `y[1,:]`, `y[2,:]` are then its first two entries
+    y = o.run(10 * u, threads=0)[:, :, 0].ravel(order="F")[199:]
+    assert not cases.julia_isapprox(y[0:1], y[1:2], 0.75)        # not at all linear for large input
+    assert o.status()[0][0] == 0
