@@ -4,6 +4,7 @@ Each builder mirrors a circuit of the reference's test suite
 (/root/reference/test/runtests.jl, line numbers in the docstrings).
 """
 import math
+from fractions import Fraction
 
 import numpy as np
 
@@ -143,6 +144,51 @@ def opamp_tanh():
         ("op", opamp("macak", 100, -3, 4), {"in+": ("input", "+"), "in-": [("op", "out-"), "gnd"]}),
         ("output", voltageprobe(), {"+": ("op", "out+"), "-": "gnd"}),
     ])
+
+
+def source_probe_circuits():
+    """runtests.jl:386-429: sources and probes with internal resistance / conductance; entries
+    (circuit, input column, expected output)"""
+    R = 100000
+    g = Fraction(1, R)
+    mk = lambda src, probe: circuit([("src", src, {}), ("probe", probe, {"+": ("src", "+"), "-": ("src", "-")})])
+    return [(mk(currentsource(100e-3, gp=g), voltageprobe()), [], R * 100e-3),
+            (mk(currentsource(gp=g), voltageprobe()), [100e-3], R * 100e-3),
+            (mk(currentsource(100e-3), voltageprobe(gp=g)), [], R * 100e-3),
+            (mk(voltagesource(10, rs=R), currentprobe()), [], 10 / R),
+            (mk(voltagesource(rs=R), currentprobe()), [10.0], 10 / R),
+            (mk(voltagesource(10), currentprobe(rs=R)), [], 10 / R)]
+
+
+def bjt_internal_resistances(typ):
+    """runtests.jl:547-587: a BJT with external base/collector/emitter resistors next to one with the same internal
+    resistances, same bias; the four probes of each must agree"""
+    ib, vce = (1e-3, 1) if typ == "npn" else (-1e-3, -1)
+    rb, re, rc = 100, 10, 20
+    bj = dict(BJT_BASE)
+    c = circuit([
+        ("t1", bjt(typ, **bj), {}), ("rbref", resistor(rb), {}), ("rcref", resistor(rc), {}), ("reref", resistor(re), {}),
+        ("isrc1", currentsource(ib), {}), ("vscr1", voltagesource(vce), {}),
+        ("veprobe1", voltageprobe(), {}), ("vcprobe1", voltageprobe(), {}),
+        ("ieprobe1", currentprobe(), {}), ("icprobe1", currentprobe(), {})])
+    c.connect(("t1", "base"), ("rbref", "1"))
+    c.connect(("rbref", "2"), ("isrc1", "+"), ("veprobe1", "+"), ("vcprobe1", "+"))
+    c.connect(("t1", "collector"), ("rcref", "1"))
+    c.connect(("rcref", "2"), ("icprobe1", "+"))
+    c.connect(("vcprobe1", "-"), ("icprobe1", "-"), ("vscr1", "+"))
+    c.connect(("t1", "emitter"), ("reref", "1"))
+    c.connect(("reref", "2"), ("ieprobe1", "+"))
+    c.connect(("veprobe1", "-"), ("ieprobe1", "-"), ("vscr1", "-"), ("isrc1", "-"))
+    for name, el in (("t2", bjt(typ, rb=rb, re=re, rc=rc, **bj)), ("isrc2", currentsource(ib)), ("vscr2", voltagesource(vce)),
+                     ("veprobe2", voltageprobe()), ("vcprobe2", voltageprobe()),
+                     ("ieprobe2", currentprobe()), ("icprobe2", currentprobe())):
+        c.add(name, el)
+    c.connect(("t2", "base"), ("isrc2", "+"), ("veprobe2", "+"), ("vcprobe2", "+"))
+    c.connect(("t2", "collector"), ("icprobe2", "+"))
+    c.connect(("vcprobe2", "-"), ("icprobe2", "-"), ("vscr2", "+"))
+    c.connect(("t2", "emitter"), ("ieprobe2", "+"))
+    c.connect(("veprobe2", "-"), ("ieprobe2", "-"), ("vscr2", "-"), ("isrc2", "-"))
+    return c
 
 
 def ja_inductor():

@@ -136,7 +136,7 @@ def test_gpu_parity_suite_subset_under_emulation(emu_lib):
     waveforms on the lane-parallel kernels -- stay GPU-only.)"""
     sel = ("K4 or K5 or K6 or K7 or K8 or K9 or empty_circuits or io_size or frozen_cache or steadystate_on_device or "
            "run_bang or odd_lengths or per_instance_matrices_nonlinear or (K3 and not coop) or "
-           "(sample_major and not device_tensors) or K12")
+           "(sample_major and not device_tensors) or K12 or K13")
     env = dict(os.environ, ACMEB200_LIB=emu_lib)
     res = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_parity.py"), "-m", "gpu", "-q", "-x",
                           "-p", "no:cacheprovider", "-k", sel], env=env, capture_output=True, text=True, timeout=900, cwd=ROOT)

@@ -938,3 +938,16 @@ def test_K12_jiles_atherton_elements(kernel):
     r.close()
     for k in range(2):
         assert_parity(y[k], yref[k])
+
+
+def test_K13_K14_sources_probes_and_bjt_internal_resistances():
+    """runtests.jl:386-429 and 547-587 on the device: models without inputs (`run!(model, zeros(0, 1))`), constant
+    sub-problems folded into x0 / y0"""
+    for c, u, want in cases.source_probe_circuits():
+        y = gpu_run(A.DiscreteModel(c, 1), np.array(u, dtype=float).reshape(len(u), 1))
+        assert y.shape == (1, 1) and np.isclose(y[0, 0], want)
+    for typ in ("npn", "pnp"):
+        m = A.DiscreteModel(cases.bjt_internal_resistances(typ), 1)
+        y = gpu_run(m, np.zeros((0, 1)))
+        assert y.shape == (8, 1) and np.allclose(y[:4], y[4:], rtol=1e-8)
+        assert_parity(y, cpu_run(m, np.zeros((0, 1))), rtol=1e-12)

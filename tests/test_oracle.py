@@ -341,3 +341,18 @@ def test_K12_jiles_atherton_transformer():
     y = o.run(10 * u, threads=0)[:, :, 0].ravel(order="F")[199:]
     assert not cases.julia_isapprox(y[0:1], y[1:2], 0.75)        # not at all linear for large input
     assert o.status()[0][0] == 0
+
+
+# ------------------------------------------------------------------ K13 / K14: run!-level known answers of the element tests
+def test_K13_sources_and_probes_with_internal_resistance():
+    """runtests.jl:386-429 (models without inputs run on `zeros(0, 1)`)"""
+    for c, u, want in cases.source_probe_circuits():
+        y = run(A.DiscreteModel(c, 1), np.array(u, dtype=float).reshape(len(u), 1))
+        assert y.shape == (1, 1) and np.isclose(y[0, 0], want)
+
+
+@pytest.mark.parametrize("typ", ["npn", "pnp"])
+def test_K14_bjt_internal_resistances(typ):
+    """runtests.jl:547-587: output[1:4] ≈ output[5:8]"""
+    y = run(A.DiscreteModel(cases.bjt_internal_resistances(typ), 1), np.zeros((0, 1)))
+    assert y.shape == (8, 1) and np.allclose(y[:4], y[4:], rtol=1e-8) and abs(y[0, 0]) > 0.5
