@@ -428,7 +428,7 @@ extern "C" int acmeb200_run(acmeb200_model* m, const double* U, int64_t u_stride
     const DevModel& dm = m->dm;
     const bool smaj = (flags & ACMEB200_SAMPLE_MAJOR) != 0;  // strides are sample pitches, (nu, B, N) / (ny, B, N) streams
     if (smaj) {
-        if (!m->tpi)
+        if (!m->tpi && (m->rows || m->coop_lanes))
             return fail(ACMEB200_EUNSUPPORTED, "sample-major streams are implemented by the thread-per-instance kernels only; this model runs on %s",
                         m->kernel_name.c_str());
         if (y_stride == 0) y_stride = (int64_t)dm.ny * m->B;

@@ -393,8 +393,13 @@ __global__ void __launch_bounds__(128) k_generic(const __grid_constant__ DevMode
         return;
     }
 
-    const double* u = a.U + t * a.u_stride;
-    double* y = a.Y + t * a.y_stride;
+    // streams: instance-major (instance pitch u_stride, sample pitch nu) or, with ACMEB200_SAMPLE_MAJOR, sample-major
+    // (instance pitch nu, sample pitch u_stride; then consecutive threads read consecutive words); u_stride == 0 is
+    // one shared nu x N input in both layouts
+    const int64_t u_is = a.smaj && a.u_stride != 0 ? m.nu : a.u_stride, u_ss = a.smaj && a.u_stride != 0 ? a.u_stride : m.nu;
+    const int64_t y_is = a.smaj ? m.ny : a.y_stride, y_ss = a.smaj ? a.y_stride : m.ny;
+    const double* u = a.U + t * u_is;
+    double* y = a.Y + t * y_is;
     LocalStats st;
     unsigned int hist_lo[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // bins 1..8; the rest go straight to global
     uint32_t status = a.status[inst];
@@ -402,7 +407,7 @@ __global__ void __launch_bounds__(128) k_generic(const __grid_constant__ DevMode
     if (!(status & ACMEB200_STATUS_NONFINITE)) {
         for (; n < a.N; n++) {
             // ---- step!  (ACME.jl:666-715)
-            for (int k = 0; k < m.nu; k++) g.w(m.w_u + k) = __ldg(u + n * m.nu + k);
+            for (int k = 0; k < m.nu; k++) g.w(m.w_u + k) = __ldg(u + n * u_ss + k);
             for (int k = 0; k < m.nnt; k++) g.w(m.w_zall + k) = 0.0;
             bool fatal = false;
             for (int si = 0; si < m.nsub; si++) {
@@ -448,7 +453,7 @@ __global__ void __launch_bounds__(128) k_generic(const __grid_constant__ DevMode
                 for (int j = 0; j < m.nx; j++) acc = fma(g.mat(m.o_dy, m.ny, i, j), g.w(m.w_x + j), acc);
                 for (int j = 0; j < m.nu; j++) acc = fma(g.mat(m.o_ey, m.ny, i, j), g.w(m.w_u + j), acc);
                 for (int j = 0; j < m.nnt; j++) acc = fma(g.mat(m.o_fy, m.ny, i, j), g.w(m.w_zall + j), acc);
-                y[n * m.ny + i] = acc;
+                y[n * y_ss + i] = acc;
             }
             for (int i = 0; i < m.nx; i++) {
                 double acc = g.mat(m.o_x0, m.nx, i, 0);
@@ -462,7 +467,7 @@ __global__ void __launch_bounds__(128) k_generic(const __grid_constant__ DevMode
         }
     }
     for (; n < a.N; n++)  // the reference throws here (ACME.jl:692); mark the rest
-        for (int i = 0; i < m.ny; i++) y[n * m.ny + i] = NAN;
+        for (int i = 0; i < m.ny; i++) y[n * y_ss + i] = NAN;
     a.status[inst] = status;
     if (st.samples) atomicAdd(&a.stats->samples, st.samples);
     if (st.solves) atomicAdd(&a.stats->solves, st.solves);

@@ -138,7 +138,7 @@ class BatchRunner:
         """``run!`` for all instances.
 
         ``layout="sample"`` selects the sample-major streams of the C ABI
-        (ACMEB200_SAMPLE_MAJOR; thread-per-instance kernels only): per-instance
+        (ACMEB200_SAMPLE_MAJOR; thread-per-instance kernels, specialised or generic): per-instance
         input (nu, B, N) and output (ny, B, N) in Julia layout -- torch tensors
         (N, B, nu) / (N, B, ny) -- so that one time step of all instances is
         contiguous.  A shared (nu, N) input is the same in both layouts.  The

@@ -89,8 +89,9 @@ extern "C" {
  * between consecutive SAMPLES (>= nu*B / ny*B; y_stride == 0 -> ny*B; u_stride == 0 still
  * means one nu x N input shared by all instances).  Every time step of a warp's 32
  * instances is one contiguous segment, so the tiles of the thread-per-instance kernels
- * move as 256-byte rows.  Only models run by those kernels accept the flag
- * (ACMEB200_EUNSUPPORTED otherwise); results are bit-identical to the default layout. */
+ * move as 256-byte rows.  Only models run by those kernels (specialised or generic) accept
+ * the flag -- the lane-parallel kernels (warp / sub-warp group per instance) gain nothing
+ * from it and return ACMEB200_EUNSUPPORTED; results are bit-identical to the default layout. */
 #define ACMEB200_SAMPLE_MAJOR 4u
 
 #define ACMEB200_HIST_BINS 32 /* iteration histogram: bins 1..31, last bin = 32 and more */

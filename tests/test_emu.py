@@ -116,7 +116,9 @@ def test_emulated_sample_major_streams(emu_lib):
         assert o["kernel"].startswith("tpi<") and o["equal"] and o["hist_equal"] and o["samples"] == samples, (key, o)
     assert out["chunks"]["launches"] >= 4                     # init + 3 time chunks
     assert out["clipper"]["err"] < 1e-6 and out["linear"]["err"] < 1e-13
-    assert out["shared_u"] and out["mixed_calls"] and out["generic_refused"]
+    assert out["shared_u"] and out["mixed_calls"] and out["rows_refused"]
+    g = out["generic"]
+    assert g["kernel"].startswith("generic<") and g["equal"] and g["hist_equal"] and g["samples"] == 37 * 203
 
 
 def test_emulated_cooperative_kernel(emu_lib):

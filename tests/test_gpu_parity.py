@@ -869,8 +869,8 @@ def test_sample_major_streams_linear_and_two_inputs():
 
 
 def test_sample_major_state_persists_and_errors():
-    """state carries over between calls in either layout; strides are checked; kernels without the transposed
-    tiles refuse the flag (no silent relayout)"""
+    """state carries over between calls in either layout; strides are checked; the generic kernel takes the flag,
+    the lane-parallel kernels refuse it (no silent relayout)"""
     m = ex.diodeclipper()
     B, N = 40, 300
     P = clipper_sweep(B)
@@ -886,10 +886,18 @@ def test_sample_major_state_persists_and_errors():
     with pytest.raises(ValueError):
         r.run(u, layout="rows")
     r.close()
-    rg = BatchRunner(m, 2, solver=H, kernel="generic")
-    with pytest.raises(Exception, match="thread-per-instance"):
-        rg.run(_smaj(u[:, :8, :2]), layout="sample")
+    # the generic thread-per-instance kernel takes the flag (same bits) ...
+    rg = BatchRunner(m, B, params=[P], solver=H, kernel="generic")
+    yg = rg.run(u)
+    rg.reset()
+    assert np.array_equal(rg.run(_smaj(u), layout="sample"), _smaj(yg))
     rg.close()
+    # ... the lane-parallel kernels (here: rows) refuse it
+    us = np.zeros((4, 8, 2), order="F"); us[1:] = 0.5
+    rr = BatchRunner(ex.superover(), 2, solver=H)
+    with pytest.raises(Exception, match="thread-per-instance"):
+        rr.run(_smaj(us), layout="sample")
+    rr.close()
 
 
 def test_sample_major_device_tensors():
