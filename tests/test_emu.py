@@ -137,14 +137,21 @@ def test_gpu_parity_suite_subset_under_emulation(emu_lib):
     tile path), per-instance matrices of a non-linear model, size checks.  (The long-running ones -- full
     waveforms on the lane-parallel kernels -- stay GPU-only.)"""
     sel = ("K4 or K5 or K6 or K7 or K8 or K9 or empty_circuits or io_size or frozen_cache or steadystate_on_device or "
-           "run_bang or odd_lengths or per_instance_matrices_nonlinear or (K3 and not coop) or "
-           "(sample_major and not device_tensors) or K12 or K13")
+           "run_bang or odd_lengths or per_instance_matrices_nonlinear or (K3 and not coop) or K12 or K13")
     env = dict(os.environ, ACMEB200_LIB=emu_lib)
     res = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_parity.py"), "-m", "gpu", "-q", "-x",
                           "-p", "no:cacheprovider", "-k", sel], env=env, capture_output=True, text=True, timeout=900, cwd=ROOT)
     tail = res.stdout.strip().splitlines()[-1] if res.stdout.strip() else res.stderr[-500:]
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-1000:]
     assert " passed" in tail and int(tail.split(" passed")[0].split()[-1]) >= 20, tail
+
+
+def test_sample_major_gpu_tests_under_emulation(emu_lib):
+    """tests/test_z_sample_major.py (all but the torch-device-tensor one) against the emulated library"""
+    env = dict(os.environ, ACMEB200_LIB=emu_lib)
+    res = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_z_sample_major.py"), "-m", "gpu", "-q", "-x",
+                          "-p", "no:cacheprovider", "-k", "not device_tensors"], env=env, capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert res.returncode == 0 and "6 passed" in res.stdout, res.stdout[-3000:] + res.stderr[-1000:]
 
 
 def test_cuda_kernels_against_independent_full_system_solve_under_emulation(emu_lib):
