@@ -50,6 +50,8 @@ class BatchRunner:
         self.batch_total = batch
         self.first = first
         self.batch = batch - first if count is None else count
+        if first < 0 or self.batch <= 0 or first + self.batch > batch:
+            raise ValueError(f"instance range [{first}, {first}+{self.batch}) outside the batch of {batch}")
         self._params = desc_kw.get("params")
         self._overrides = desc_kw.get("overrides")
         self._has_overrides = bool(desc_kw.get("overrides"))
@@ -176,8 +178,11 @@ class BatchRunner:
         if y is None:
             ybuf = np.empty(max(m.ny * N * self.batch, 1))
         else:
-            if y.shape[:2] != (m.ny, N):
-                self._check_sizes(u.shape[0], N, y.shape[0], y.shape[1])
+            if y.ndim < 2 or y.shape[:2] != (m.ny, N):
+                self._check_sizes(u.shape[0], N, y.shape[0] if y.ndim else -1, y.shape[1] if y.ndim > 1 else -1)
+            # the instance axis too: acmeb200_run writes ny*N*batch doubles
+            if not (y.shape == (m.ny, N, self.batch) or (y.ndim == 2 and self.batch == 1)):
+                raise DimensionMismatch(f"output has shape {tuple(y.shape)}, runner needs {(m.ny, N, self.batch)}")
             if not (y.flags.f_contiguous and y.dtype == np.float64):
                 raise ValueError("y must be a Fortran-contiguous float64 array")
             ybuf = y.reshape(-1, order="F") if y.size else np.empty(1)

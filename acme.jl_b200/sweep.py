@@ -73,8 +73,8 @@ def _cuda_initialised() -> bool:
 def derive_sweep(builder: Callable, points: Iterable, workers: Optional[int] = None, chunk: int = 16):
     """Derive ``builder(point)`` (a :class:`DiscreteModel`) for every sweep point.
 
-    Returns ``(base_model, kwargs)``: ``BatchRunner(base_model, len(points), **kwargs)`` runs the
-    sweep.  ``kwargs`` holds ``overrides`` (only the matrices that actually differ between
+    Returns ``(base_model, kwargs, B)`` with ``B = len(points)``: ``BatchRunner(base_model, B, **kwargs)``
+    runs the sweep.  ``kwargs`` holds ``overrides`` (only the matrices that actually differ between
     instances; shape + (B,)), ``params`` (per sub, (nparams, B)) and ``init_z`` (per sub, (nn, B)).
     ``points`` are passed to ``builder`` as is (tuples are unpacked).
     """
