@@ -140,6 +140,7 @@ extern "C" int acmeb200_model_create(const acmeb200_model_desc* d, int64_t first
     dm.solver = d->solver;
     dm.maxiter = d->maxiter > 0 ? d->maxiter : 500;
     dm.tol = d->tol > 0 ? d->tol : 1e-10;
+    m->cache_capacity = d->cache_capacity >= 2 && d->cache_capacity <= (1 << 20) ? d->cache_capacity : 0;
     int nnt = 0;
     for (int i = 0; i < d->nsub; i++) nnt += d->subs[i].nn;
     dm.nnt = nnt;
@@ -264,28 +265,32 @@ extern "C" int acmeb200_model_create(const acmeb200_model_desc* d, int64_t first
         CT(cudaMemcpy(m->d_initz, flat.data(), sizeof(double) * flat.size(), cudaMemcpyHostToDevice));
     }
     for (int i = 0; i < d->nsub; i++) {
+        // frozen, host-built cache (acmeb200_cache = the fields of KDTree + CachingSolver.zs): uploaded as ONE store image
+        // (kdcache.cuh layout) shared by all instances and never written
         const acmeb200_cache& c = d->subs[i].cache;
         DevSub& s = dm.subs[i];
-        s.cache_n = 0;
+        s.kd_base = nullptr; s.kd_scr = nullptr; s.kd_stride = 0; s.kd_sstride = 0; s.kd_cap = 0; s.kd_frozen = 0;
         if (c.n_points <= 0) continue;
-        if (c.n_points > (1 << 20)) return destroy_fail(fail(ACMEB200_EUNSUPPORTED, "cache with %d points", c.n_points));
+        if (c.n_points > (1 << 20) || c.n_columns > (1 << 20)) return destroy_fail(fail(ACMEB200_EUNSUPPORTED, "cache with %d points", c.n_points));
+        if (s.np > KD_MAXNP) return destroy_fail(fail(ACMEB200_EUNSUPPORTED, "solution caches support np <= %d", KD_MAXNP));
         for (int k = 0; k < c.n_points; k++)
             if (c.ps_idx[k] < 1 || c.ps_idx[k] > c.n_columns) return destroy_fail(fail(ACMEB200_EINVAL, "cache index out of range"));
-        auto up = [&](const void* src, size_t bytes, const void** dst) -> cudaError_t {
-            void* p = nullptr;
-            cudaError_t e = cudaMalloc(&p, std::max<size_t>(bytes, 8));
-            if (e != cudaSuccess) return e;
-            m->d_cache.push_back(p);
-            *dst = p;
-            return bytes ? cudaMemcpy(p, src, bytes, cudaMemcpyHostToDevice) : cudaSuccess;
-        };
-        CT(up(c.cut_dim, sizeof(int32_t) * (size_t)(c.n_points - 1), (const void**)&s.cut_dim));
-        CT(up(c.cut_val, sizeof(double) * (size_t)(c.n_points - 1), (const void**)&s.cut_val));
-        CT(up(c.ps_idx, sizeof(int32_t) * (size_t)c.n_points, (const void**)&s.ps_idx));
-        CT(up(c.ps, sizeof(double) * (size_t)s.np * c.n_columns, (const void**)&s.ps));
-        CT(up(c.zs, sizeof(double) * (size_t)s.nn * c.n_columns, (const void**)&s.zs));
-        s.cache_n = c.n_points;
-        s.cache_cols = c.n_columns;
+        for (int k = 0; k < c.n_points - 1; k++)
+            if (c.cut_dim[k] < 1 || c.cut_dim[k] > s.np) return destroy_fail(fail(ACMEB200_EINVAL, "cache cut dimension out of range"));
+        const int cap = c.n_columns;
+        std::vector<double> img((size_t)kd_store_doubles(s.np, s.nn, cap), 0.0);
+        KdStore st = KdStore::at(img.data(), nullptr, s.np, s.nn, cap);
+        st.hdr[KD_H_NUM] = c.n_columns; st.hdr[KD_H_NEW] = 0; st.hdr[KD_H_LIMIT] = 2 * cap; st.hdr[KD_H_CAPREF] = cap;
+        st.hdr[KD_H_TREEN] = c.n_points; st.hdr[KD_H_FLAGS] = KD_F_FROZEN;
+        for (int k = 0; k < c.n_points - 1; k++) st.set_cut(k + 1, c.cut_dim[k], c.cut_val[k]);
+        for (int k = 0; k < c.n_points; k++) st.set_psidx(k + 1, c.ps_idx[k]);
+        if (s.np > 0) memcpy(st.ps, c.ps, sizeof(double) * (size_t)s.np * cap);
+        if (s.nn > 0) memcpy(st.zs, c.zs, sizeof(double) * (size_t)s.nn * cap);
+        void* p = nullptr;
+        CT(cudaMalloc(&p, sizeof(double) * img.size()));
+        m->d_cache.push_back(p);
+        CT(cudaMemcpy(p, img.data(), sizeof(double) * img.size(), cudaMemcpyHostToDevice));
+        s.kd_base = (double*)p; s.kd_cap = cap; s.kd_frozen = 1;
         m->has_cache = true;
     }
     CT(cudaMalloc(&m->d_status, sizeof(uint32_t) * (size_t)count));
@@ -327,29 +332,33 @@ static int select_kernel(acmeb200_model* m) {
                                             (m->coop_static ? "compile-time dims [superover]" : "runtime dims") + ", state in shared memory" +
                                             (m->dm.solver == ACMEB200_SOLVER_HOMOTOPY_CACHING ? ", dynamic solution cache>" : ">");
     else m->kernel_name = "generic<thread-per-instance, runtime dims>";
-    // dynamic (learning) solution caches
+    // learning solution stores of the CachingSolver (kdcache.cuh), one per instance and sub-problem
     for (void* p : m->d_dyn) cudaFree(p);
     m->d_dyn.clear();
+    m->dyn_bytes.clear();
     for (int i = 0; i < m->dm.nsub; i++) {
         DevSub& s = m->dm.subs[i];
-        s.dyn_ps = nullptr; s.dyn_zs = nullptr; s.dyn_n = nullptr; s.dyn_cap = 0;
-        // learning caches for every kernel (the thread-per-instance kernels use their own SoA layout)
-        if (m->dm.solver != ACMEB200_SOLVER_HOMOTOPY_CACHING || s.cache_n > 0) continue;
+        if (s.kd_frozen) continue;
+        s.kd_base = nullptr; s.kd_scr = nullptr; s.kd_stride = 0; s.kd_sstride = 0; s.kd_cap = 0;
+        if (m->dm.solver != ACMEB200_SOLVER_HOMOTOPY_CACHING || s.np > KD_MAXNP) continue;
         size_t free_b = 0, total_b = 0;
         CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
-        // ring-buffer capacity: the start points that matter are the recently stored ones (superover: the
-        // iteration statistics are identical for 64, 256 and 1024), and every stored point is scanned per sample
-        int cap = m->tpi ? 128 : 256;
-        if (const char* e = getenv("ACMEB200_CACHE_CAP")) { const long v = atol(e); if (v >= 2 && v <= (1 << 20)) cap = (int)v; }  // tuning knob
-        while (cap > 32 && (size_t)m->B * (s.np + s.nn) * cap * 8 > free_b / 8) cap /= 2;
-        void *ps = nullptr, *zs = nullptr, *nn_ = nullptr;
-        CUDA_TRY(cudaMalloc(&ps, std::max<size_t>(8, (size_t)m->B * s.np * cap * 8)));
-        m->d_dyn.push_back(ps);
-        CUDA_TRY(cudaMalloc(&zs, std::max<size_t>(8, (size_t)m->B * s.nn * cap * 8)));
-        m->d_dyn.push_back(zs);
-        CUDA_TRY(cudaMalloc(&nn_, sizeof(int) * (size_t)m->B));
-        m->d_dyn.push_back(nn_);
-        s.dyn_ps = (double*)ps; s.dyn_zs = (double*)zs; s.dyn_n = (int*)nn_; s.dyn_cap = cap;
+        // Physical capacity in stored solutions per instance (the reference's arrays double for ever, solvers.jl:376-382;
+        // superover stores ~900 solutions in its first second and ~150 per second after that): as large as a memory budget
+        // allows, at most 4096; the descriptor (cache_capacity) or ACMEB200_CACHE_CAP override it
+        int cap = 4096;
+        const size_t per_col = 8 * (size_t)(s.np + s.nn) + 12 + 24;
+        const size_t budget = std::min<size_t>(free_b / 8, (size_t)4 << 30);
+        while (cap > 64 && (size_t)m->B * cap * per_col > budget) cap /= 2;
+        if (m->cache_capacity > 0) cap = m->cache_capacity;
+        if (const char* e = getenv("ACMEB200_CACHE_CAP")) { const long v = atol(e); if (v >= 2 && v <= (1 << 20)) cap = (int)v; }  // tuning / test knob
+        const int64_t stride = (kd_store_doubles(s.np, s.nn, cap) + 1) & ~int64_t(1), sstride = (kd_scratch_doubles(cap) + 1) & ~int64_t(1);
+        void *st = nullptr, *sc = nullptr;
+        CUDA_TRY(cudaMalloc(&st, sizeof(double) * (size_t)stride * m->B));
+        m->d_dyn.push_back(st); m->dyn_bytes.push_back(sizeof(double) * (size_t)stride * m->B);
+        CUDA_TRY(cudaMalloc(&sc, sizeof(double) * (size_t)sstride * m->B));
+        m->d_dyn.push_back(sc); m->dyn_bytes.push_back(0);  // scratch needs no clearing
+        s.kd_base = (double*)st; s.kd_stride = stride; s.kd_scr = (double*)sc; s.kd_sstride = sstride; s.kd_cap = cap;
     }
     cudaFree(m->d_ws);
     m->d_ws = nullptr;
@@ -380,6 +389,9 @@ static cudaError_t launch(acmeb200_model* m, const RunArgs& a, cudaStream_t stre
 static int run_init(acmeb200_model* m) {
     RunArgs a = base_args(m);
     a.init = 1; a.inst0 = 0; a.ninst = m->B; a.N = 0;
+    // the spare columns of a learning store are the zero-filled spare capacity of the reference's arrays
+    for (size_t k = 0; k < m->d_dyn.size(); k++)
+        if (m->dyn_bytes[k]) CUDA_TRY(cudaMemsetAsync(m->d_dyn[k], 0, m->dyn_bytes[k], nullptr));
     CUDA_TRY(launch(m, a, nullptr));
     CUDA_TRY(cudaMemsetAsync(m->d_stats, 0, sizeof(DevStats), nullptr));
     CUDA_TRY(cudaDeviceSynchronize());
@@ -592,10 +604,15 @@ extern "C" int acmeb200_get_cache_sizes(acmeb200_model* m, int32_t sub, int32_t*
     CUDA_TRY(cudaSetDevice(m->device));
     CUDA_TRY(cudaDeviceSynchronize());
     const DevSub& s = m->dm.subs[sub];
-    if (capacity_out) *capacity_out = s.dyn_cap;
-    if (s.dyn_cap > 0 && s.dyn_n)
-        CUDA_TRY(cudaMemcpy(sizes_host, s.dyn_n, sizeof(int32_t) * (size_t)m->B, cudaMemcpyDeviceToHost));
-    else
+    if (capacity_out) *capacity_out = s.kd_cap;
+    if (s.kd_cap > 0 && !s.kd_frozen)  // hdr[KD_H_NUM] of every instance's store
+        CUDA_TRY(cudaMemcpy2D(sizes_host, sizeof(int32_t), reinterpret_cast<const int*>(s.kd_base) + KD_H_NUM, sizeof(double) * (size_t)s.kd_stride,
+                              sizeof(int32_t), (size_t)m->B, cudaMemcpyDeviceToHost));
+    else if (s.kd_cap > 0) {
+        int32_t n = 0;
+        CUDA_TRY(cudaMemcpy(&n, reinterpret_cast<const int*>(s.kd_base) + KD_H_NUM, sizeof n, cudaMemcpyDeviceToHost));
+        for (int64_t b = 0; b < m->B; b++) sizes_host[b] = n;
+    } else
         memset(sizes_host, 0, sizeof(int32_t) * (size_t)m->B);
     return ACMEB200_OK;
 }

@@ -36,19 +36,15 @@ struct DevSub {
     int o_dq, o_eq, o_fqprev, o_pexp, o_q0, o_fq;
     // generic-kernel workspace rows that persist across run calls
     int w_lastp, w_lastz, w_lastJp, w_LU[2], w_ipiv[2], w_sel;
-    // frozen solution cache (device pointers), kdtree.jl:4-9 + solvers.jl:321-323
-    int cache_n, cache_cols;
-    const int* cut_dim;
-    const double* cut_val;
-    const int* ps_idx;
-    const double* ps;
-    const double* zs;
-    // dynamic per-instance solution cache of the cooperative kernel (CachingSolver, solvers.jl:319-396):
-    // ps [inst][np][cap], zs [inst][nn][cap], n [inst]; entry 0 is the initial (0, init_z)
-    double* dyn_ps;
-    double* dyn_zs;
-    int* dyn_n;
-    int dyn_cap;
+    // solution store of the CachingSolver (kdcache.cuh: the reference's k-d tree + doubling arrays, solvers.jl:319-396,
+    // kdtree.jl): one instance-contiguous block per instance (kd_stride doubles apart; 0 = one frozen, host-built
+    // store shared by all instances, acmeb200_cache), scratch for the rebuilds, physical capacity in columns
+    double* kd_base;
+    int64_t kd_stride;
+    double* kd_scr;
+    int64_t kd_sstride;
+    int kd_cap;     // 0: no store (solver without cache, or np beyond what the search holds)
+    int kd_frozen;  // 1: the host-built store of the descriptor (read-only)
 };
 
 struct DevModel {

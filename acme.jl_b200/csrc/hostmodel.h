@@ -42,8 +42,10 @@ struct acmeb200_model {
     uint32_t* d_status = nullptr;
     long long* d_first_fail = nullptr;
     acme::DevStats* d_stats = nullptr;
-    std::vector<void*> d_cache;  // device copies of the frozen caches
-    std::vector<void*> d_dyn;    // dynamic per-instance caches of the cooperative kernel
+    std::vector<void*> d_cache;  // frozen, host-built solution stores (one image per sub-problem)
+    std::vector<void*> d_dyn;    // learning per-instance solution stores and their scratch (kdcache.cuh)
+    std::vector<size_t> dyn_bytes;  // bytes to clear at reset (0: scratch)
+    int cache_capacity = 0;      // stored solutions per instance asked for by the descriptor (0: automatic)
     // host copies needed to (re)build kernel parameters
     std::vector<double> h_blob;  // blob of instance 0 (or the shared blob)
     const TpiEntry* tpi = nullptr;

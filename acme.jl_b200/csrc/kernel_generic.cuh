@@ -9,6 +9,7 @@
 #pragma once
 #include "devmodel.h"
 #include "elements.cuh"
+#include "kdcache.cuh"
 
 namespace acme {
 
@@ -232,99 +233,42 @@ __device__ inline GSolveResult g_simple_solve(const GCtx& g, const DevSub& s, in
     return r;
 }
 
-// exact nearest neighbour in the frozen k-d tree, seeded with the distance to the
-// current origin (solvers.jl:348-366, kdtree.jl:192-234).  Depth-first with
-// pruning; returns the 1-based column of ps or 0 to keep the origin.
-template <class PF>
-__device__ inline int kd_nearest(const DevSub& s, PF p, double best) {
-    int best_idx = 0;
-    const int ncut = s.cache_n - 1;
-    int stk_node[48];
-    double stk_bound[48];
-    int sp = 0;
-    stk_node[0] = 1; stk_bound[0] = 0.0; sp = 1;
-    while (sp > 0) {
-        sp--;
-        int node = stk_node[sp];
-        const double bound = stk_bound[sp];
-        if (!(bound < best)) continue;
-        if (node > ncut) {
-            const int pidx = s.ps_idx[node - ncut - 1];
-            double d = 0.0;
-            for (int i = 0; i < s.np; i++) {
-                const double df = p(i) - s.ps[(int64_t)(pidx - 1) * s.np + i];
-                d = fma(df, df, d);
-            }
-            if (d < best) { best = d; best_idx = pidx; }
-        } else {
-            const int dim = s.cut_dim[node - 1] - 1;
-            const double diff = p(dim) - s.cut_val[node - 1];
-            const int near = diff <= 0 ? 2 * node : 2 * node + 1;
-            const int far = diff <= 0 ? 2 * node + 1 : 2 * node;
-            const double fb = fmax(bound, diff * diff);
-            if (sp < 46) {
-                stk_node[sp] = far; stk_bound[sp] = fb; sp++;
-                stk_node[sp] = near; stk_bound[sp] = bound; sp++;
-            }
-        }
-    }
-    return best_idx;
+// this instance's solution store of sub-problem s (kdcache.cuh); a frozen host-built store is shared (stride 0)
+__device__ __forceinline__ KdStore g_store(const DevSub& s, int64_t inst) {
+    return KdStore::at(s.kd_base + inst * s.kd_stride, s.kd_scr ? s.kd_scr + inst * s.kd_sstride : nullptr, s.np, s.nn, s.kd_cap);
 }
 
-// solve(::CachingSolver, p) (solvers.jl:347-396): frozen k-d tree supplied by the host, or the learning per-instance store
+// solve(::CachingSolver, p) (solvers.jl:347-396) on the device store: start from the nearest of {origin, newest stored
+// solutions, k-d tree}, solve, store the solution if it was expensive, rebuild the tree on the reference's schedule
 __device__ inline GSolveResult g_base_solve(const GCtx& g, const DevSub& s, int prow) {
     const DevModel& m = g.m;
     if (m.solver == ACMEB200_SOLVER_HOMOTOPY_CACHING) {
         double best = 0.0;
         for (int i = 0; i < s.np; i++) {
             const double d = g.w(prow + i) - g.w(s.w_lastp + i);
-            best = fma(d, d, best);
+            best = kd_add(best, kd_mul(d, d));
         }
-        if (s.cache_n > 0) {
-            const int idx = kd_nearest(s, [&](int i) { return g.w(prow + i); }, best);
+        if (s.kd_cap > 0) {
+            KdStore c = g_store(s, g.inst);
+            int ovf = 0;
+            const int idx = kd_lookup(c, [&](int i) { return g.w(prow + i); }, best, &ovf);
+            if (ovf) c.hdr[KD_H_FLAGS] |= KD_F_HEAP_OVERFLOW;
             if (idx != 0) {
-                for (int i = 0; i < s.np; i++) g.w(m.w_cp + i) = s.ps[(int64_t)(idx - 1) * s.np + i];
-                for (int i = 0; i < s.nn; i++) g.w(m.w_z + i) = s.zs[(int64_t)(idx - 1) * s.nn + i];
-                g_set_origin(g, s, m.w_cp, m.w_z);
-            }
-        } else if (s.dyn_cap > 0) {
-            // learning cache (solvers.jl:347-396), ring buffer of the newest dyn_cap solutions, layout
-            // [instance][dim][slot] shared with the cooperative / rows kernels: nearest stored point by scanning
-            double* const cps = s.dyn_ps + g.inst * (int64_t)s.np * s.dyn_cap;
-            double* const czs = s.dyn_zs + g.inst * (int64_t)s.nn * s.dyn_cap;
-            const int n = s.dyn_n[g.inst];
-            const int nvalid = n < s.dyn_cap ? n : s.dyn_cap;
-            int idx = -1;
-            for (int k = 0; k < nvalid; k++) {
-                double d2 = 0.0;
-                for (int i = 0; i < s.np; i++) {
-                    const double df = cps[(int64_t)i * s.dyn_cap + k] - g.w(prow + i);
-                    d2 = fma(df, df, d2);
-                }
-                if (d2 < best) { best = d2; idx = k; }
-            }
-            if (idx >= 0) {
-                for (int i = 0; i < s.np; i++) g.w(m.w_cp + i) = cps[(int64_t)i * s.dyn_cap + idx];
-                for (int i = 0; i < s.nn; i++) g.w(m.w_z + i) = czs[(int64_t)i * s.dyn_cap + idx];
+                for (int i = 0; i < s.np; i++) g.w(m.w_cp + i) = c.P(i, idx);
+                for (int i = 0; i < s.nn; i++) g.w(m.w_z + i) = c.Z(i, idx);
                 g_set_origin(g, s, m.w_cp, m.w_z);
             }
             const GSolveResult r = g_simple_solve(g, s, prow);
-            if (r.iters > 5 && r.converged) {  // solvers.jl:374-386
-                const int slot = n % s.dyn_cap;
-                for (int i = 0; i < s.np; i++) cps[(int64_t)i * s.dyn_cap + slot] = g.w(prow + i);
-                for (int i = 0; i < s.nn; i++) czs[(int64_t)i * s.dyn_cap + slot] = g.w(m.w_z + i);
-                s.dyn_n[g.inst] = n + 1;
-            }
+            kd_after_solve(c, r.iters > 5 && r.converged, [&](int i) { return g.w(prow + i); }, [&](int i) { return g.w(m.w_z + i); });
             return r;
-        } else {
-            // fresh CachingSolver without a store: the cache holds only (p = 0, z = init_z)  (solvers.jl:327-333)
-            double d0 = 0.0;
-            for (int i = 0; i < s.np; i++) d0 = fma(g.w(prow + i), g.w(prow + i), d0);
-            if (d0 < best) {
-                for (int i = 0; i < s.np; i++) g.w(m.w_cp + i) = 0.0;
-                for (int i = 0; i < s.nn; i++) g.w(m.w_z + i) = g.iz(s.o_initz + i);
-                g_set_origin(g, s, m.w_cp, m.w_z);
-            }
+        }
+        // no store (np beyond the search's delta vector): the cache holds only (p = 0, z = init_z)  (solvers.jl:327-333)
+        double d0 = 0.0;
+        for (int i = 0; i < s.np; i++) d0 = kd_add(d0, kd_mul(g.w(prow + i), g.w(prow + i)));
+        if (d0 < best) {
+            for (int i = 0; i < s.np; i++) g.w(m.w_cp + i) = 0.0;
+            for (int i = 0; i < s.nn; i++) g.w(m.w_z + i) = g.iz(s.o_initz + i);
+            g_set_origin(g, s, m.w_cp, m.w_z);
         }
     }
     return g_simple_solve(g, s, prow);
@@ -382,10 +326,9 @@ __global__ void __launch_bounds__(128) k_generic(const __grid_constant__ DevMode
             for (int i = 0; i < s.np; i++) g.w(m.w_cp + i) = 0.0;
             for (int i = 0; i < s.nn; i++) g.w(m.w_z + i) = g.iz(s.o_initz + i);
             g_set_origin(g, s, m.w_cp, m.w_z);
-            if (s.dyn_cap > 0) {  // CachingSolver ctor: the cache holds (0, init_z)  (solvers.jl:327-333)
-                for (int i = 0; i < s.np; i++) s.dyn_ps[(inst * s.np + i) * (int64_t)s.dyn_cap] = 0.0;
-                for (int i = 0; i < s.nn; i++) s.dyn_zs[(inst * s.nn + i) * (int64_t)s.dyn_cap] = g.iz(s.o_initz + i);
-                s.dyn_n[inst] = 1;
+            if (s.kd_cap > 0 && !s.kd_frozen) {  // CachingSolver ctor: the store holds (0, init_z)  (solvers.jl:327-333); memory zeroed by the host
+                KdStore c = g_store(s, inst);
+                kd_init(c, [&](int i) { return g.iz(s.o_initz + i); });
             }
         }
         a.status[inst] = 0;

@@ -393,10 +393,10 @@ def config3_record(args, D: Dist, pre) -> dict:
     out = None
     if D.rank == 0:
         best = res["sample"]
-        spots = [0, 255, 256 * 255, B - 1, 31337 % B, 777 % B]
+        spots = sorted({i % B for i in (0, 255, 256 * 255, B - 1, 31337, 777)})
         ovs = {k: np.ascontiguousarray(v[..., spots]) for k, v in ov.items()}
         par = parity_spot(base, len(spots), np.sin(2 * np.pi * 1000 / C3_FS * np.arange(N)).reshape(1, -1), SOLVER,
-                          "6 instances spread over the (R, kappa) grid, the full second", overrides=ovs)
+                          f"{len(spots)} instances spread over the (R, kappa) grid, the full second", overrides=ovs)
         cap = ncu_capture("r2/traffic_linear.json")
         out = {"workload": f"examples/sallenkey.jl topology, batch={B} instances/GPU with swept R (256) x kappa (256): per-instance "
                            f"matrices a,b,dy,ey derived on the host in exact rationals, 1 s of unit 1 kHz sine @ 96 kHz "
@@ -808,7 +808,7 @@ def main():
         cap = ncu_capture("r2/traffic_clipper.json")   # refreshed by tools/ncu_refresh.py; None when stale
         traffic = cap["dram_bytes_per_sample"] * Bper * N_SAMPLES if cap else None
         flops = cap["fp64_flops_per_sample"] if cap else None
-        spots = [0, 255, 256 * 255, 65535, 31337, 4242, 12345, 54321]
+        spots = sorted({i % (Bper * world) for i in (0, 255, 256 * 255, 65535, 31337, 4242, 12345, 54321)})
         out = {
             "metric": METRIC, "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -836,7 +836,7 @@ def main():
                        "homotopy_solves": st["homotopy_solves"], "not_converged": st["not_converged"],
                        "instances_with_status": status_bad},
             "parity": parity_spot(model, len(spots), sine_row().reshape(1, -1), SOLVER,
-                                  "8 instances spread over the (Is, eta) grid, the full second", params=[Pglobal[:, spots]]),
+                                  f"{len(spots)} instances spread over the (Is, eta) grid, the full second", params=[Pglobal[:, spots]]),
         }
         if flops:
             # the roofline that actually binds this kernel (FP64 CUDA-core pipe; dependent-issue latency keeps it

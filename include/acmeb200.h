@@ -142,7 +142,7 @@ typedef struct acmeb200_model_desc {
     int32_t nx, nu, ny, nsub;
     int32_t solver;      /* ACMEB200_SOLVER_*                                  */
     int32_t maxiter;     /* 0 -> 500 (src/solvers.jl:207)                      */
-    int32_t reserved;
+    int32_t cache_capacity; /* stored solutions per instance the learning CachingSolver can hold (0 = automatic) */
     double  tol;         /* 0 -> 1e-10 (src/solvers.jl:175)                    */
     acmeb200_array a;    /* nx x nx        ACME.jl:119 */
     acmeb200_array b;    /* nx x nu        ACME.jl:120 */

@@ -509,7 +509,13 @@ static void alts_update_best(Alts *a, double dist, int p_idx) { /* src/kdtree.jl
 }
 #undef E
 
-/* diagnostics (not part of the reference): how much work the tree search does; racy across threads, which is fine for a profile */
+/* diagnostics (not part of the reference; compiled in with -DORACLE_KD_PROFILE only: shared counters would make the
+ * threads of the CPU baseline fight over one cache line): how much work the tree search does */
+#ifdef ORACLE_KD_PROFILE
+#define KDPROF(x) x
+#else
+#define KDPROF(x)
+#endif
 static unsigned long long g_kd_queries, g_kd_leaves, g_kd_nodes, g_kd_maxheap, g_kd_rebuilds, g_kd_newscan, g_kd_maxleaves;
 void oracle_kd_counters(unsigned long long *out, int reset) {
     out[0] = g_kd_queries; out[1] = g_kd_leaves; out[2] = g_kd_nodes; out[3] = g_kd_maxheap; out[4] = g_kd_rebuilds; out[5] = g_kd_newscan; out[6] = g_kd_maxleaves;
@@ -520,10 +526,10 @@ void oracle_kd_counters(unsigned long long *out, int reset) {
 static int kd_indnearest(const KDTree *t, const double *p, Alts *a, double *delta_scratch) {
     int ncut = t->n_points - 1;
     if (ncut < 0) ncut = 0;
-    g_kd_queries++;
+    KDPROF(g_kd_queries++;)
     unsigned long long leaves_here = 0;
     while (a->number_valid > 0) {
-        if ((unsigned long long)a->number_valid > g_kd_maxheap) g_kd_maxheap = (unsigned long long)a->number_valid;
+        KDPROF(if ((unsigned long long)a->number_valid > g_kd_maxheap) g_kd_maxheap = (unsigned long long)a->number_valid;)
         /* dequeue!: copy the best entry out (its storage is recycled by enqueue) */
         int idx = a->entries[0].idx;
         double delta_norm = a->entries[0].delta_norm;
@@ -531,7 +537,7 @@ static int kd_indnearest(const KDTree *t, const double *p, Alts *a, double *delt
         alts_deleteat(a, 1);
         if (t->n_points == 0) break;
         while (idx <= ncut) {
-            g_kd_nodes++;
+            KDPROF(g_kd_nodes++;)
             int dim = t->cut_dim[idx - 1] - 1;
             double dcut = p[dim] - t->cut_val[idx - 1];
             double new_norm = delta_norm - delta_scratch[dim] * delta_scratch[dim] + dcut * dcut;
@@ -549,9 +555,10 @@ static int kd_indnearest(const KDTree *t, const double *p, Alts *a, double *delt
             dist += d * d;
         }
         alts_update_best(a, dist, p_idx);
-        g_kd_leaves++; leaves_here++;
+        KDPROF(g_kd_leaves++;) leaves_here++;
     }
-    if (leaves_here > g_kd_maxleaves) g_kd_maxleaves = leaves_here;
+    KDPROF(if (leaves_here > g_kd_maxleaves) g_kd_maxleaves = leaves_here;)
+    (void)leaves_here;
     return a->best_pidx;
 }
 
@@ -705,7 +712,7 @@ static double *caching_solve(SubSolver *s, const double *p) {
         for (int j = 0; j < np; j++) { double d = CM(s->tree.ps, np, j, i - 1) - p[j]; diff += d * d; }
         if (diff < best_diff) { best_diff = diff; idx = i; }
     }
-    g_kd_newscan += (unsigned long long)s->new_count;
+    KDPROF(g_kd_newscan += (unsigned long long)s->new_count;)
     alts_init(&s->alts, best_diff, idx);
     idx = kd_indnearest(&s->tree, p, &s->alts, s->delta_scratch);
     if (idx != 0)
@@ -730,7 +737,7 @@ static double *caching_solve(SubSolver *s, const double *p) {
     if (s->new_count > 0) s->new_count_limit -= 1;
     if (s->new_count > s->new_count_limit) {
         kdtree_build(&s->tree, s->num_ps);
-        g_kd_rebuilds++;
+        KDPROF(g_kd_rebuilds++;)
         s->new_count = 0;
         s->new_count_limit = 2 * s->tree.cap;
     }

@@ -13,6 +13,6 @@ try:
     print('top', d['value'], d['parity'])
 except Exception as e: print('parse failed', e)
 PY
-/usr/bin/time -v timeout 1500 python bench.py > gpurun_out/bench_$T.json 2> gpurun_out/bench_$T.err; echo "bench exit $?"
-grep -E "Elapsed|Maximum resident" gpurun_out/bench_$T.err
+SECONDS=0; timeout 1500 python bench.py > gpurun_out/bench_$T.json 2> gpurun_out/bench_$T.err; echo "bench exit $?"
+echo "bench wall seconds: $SECONDS"
 cat gpurun_out/bench_$T.json
