@@ -13,13 +13,14 @@ from .elements import (Element, NLElem, bjt, capacitor, currentprobe, currentsou
 from .circuit import Circuit, circuit, topomat
 from .model import DiscreteModel, SubProblem, gensolve, rank_factorize
 from . import examples
-from .runner import BatchRunner, ModelRunner, run_, DimensionMismatch
+from .runner import BatchRunner, ModelRunner, MultiGpuRunner, run_, DimensionMismatch
 from .sweep import derive_sweep
+from .kdtree import KDTree, frozen_cache
 
 __all__ = [
     "Element", "NLElem", "Circuit", "circuit", "topomat", "DiscreteModel", "SubProblem",
     "gensolve", "rank_factorize", "examples",
-    "BatchRunner", "ModelRunner", "run_", "DimensionMismatch", "derive_sweep",
+    "BatchRunner", "ModelRunner", "MultiGpuRunner", "run_", "DimensionMismatch", "derive_sweep", "KDTree", "frozen_cache",
     "resistor", "potentiometer", "capacitor", "inductor", "transformer",
     "voltagesource", "currentsource", "voltageprobe", "currentprobe",
     "diode", "bjt", "mosfet", "opamp",

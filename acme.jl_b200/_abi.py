@@ -58,7 +58,7 @@ class SubDesc(C.Structure):
 class ModelDesc(C.Structure):
     _fields_ = [("abi_version", C.c_int32), ("nx", C.c_int32), ("nu", C.c_int32),
                 ("ny", C.c_int32), ("nsub", C.c_int32), ("solver", C.c_int32),
-                ("maxiter", C.c_int32), ("reserved", C.c_int32), ("tol", C.c_double),
+                ("maxiter", C.c_int32), ("cache_capacity", C.c_int32), ("tol", C.c_double),
                 ("a", Array), ("b", Array), ("c", Array), ("x0", Array),
                 ("dy", Array), ("ey", Array), ("fy", Array), ("y0", Array),
                 ("subs", C.POINTER(SubDesc))]
@@ -114,14 +114,15 @@ def make_desc(model, batch: int = 1, *, params: Optional[Sequence[Optional[np.nd
               overrides: Optional[Dict[str, np.ndarray]] = None,
               init_z: Optional[Sequence[Optional[np.ndarray]]] = None,
               caches: Optional[Sequence[Optional[dict]]] = None,
-              solver: Optional[str] = None, tol: float = 0.0, maxiter: int = 0) -> DescHolder:
+              solver: Optional[str] = None, tol: float = 0.0, maxiter: int = 0, cache_capacity: int = 0) -> DescHolder:
     """Build the C descriptor.
 
     params[i]     (nparams_i, batch) element parameters of sub i (None -> shared, from the model)
     overrides     per-instance linear matrices: keys a,b,c,x0,dy,ey,fy,y0 (shape + (batch,)) and
                   ``dq{i}``, ``eq{i}``, ``fqprev{i}``, ``pexp{i}``, ``q0{i}``, ``fq{i}`` for sub i
     init_z[i]     (nn_i, batch) per-instance initial solutions (None -> the model's)
-    caches[i]     dict(cut_dim, cut_val, ps_idx, ps, zs) frozen k-d tree for sub i
+    caches[i]     dict(cut_dim, cut_val, ps_idx, ps, zs) frozen k-d tree for sub i (see acme_jl_b200.kdtree.frozen_cache)
+    cache_capacity  stored solutions per instance the learning CachingSolver can hold (0: automatic)
     """
     h = DescHolder()
     ov = overrides or {}
@@ -169,6 +170,7 @@ def make_desc(model, batch: int = 1, *, params: Optional[Sequence[Optional[np.nd
     d.nx, d.nu, d.ny, d.nsub = nx, nu, ny, nsub
     d.solver = SOLVERS[solver or model.solver]
     d.maxiter = maxiter
+    d.cache_capacity = cache_capacity
     d.tol = tol
     d.a = h.array(ov.get("a", model.a), (nx, nx), batch)
     d.b = h.array(ov.get("b", model.b), (nx, nu), batch)

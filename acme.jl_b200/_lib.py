@@ -38,6 +38,25 @@ def lib():
         L.acmeb200_get_status.argtypes = [vp, vp, vp]
         L.acmeb200_get_stats.argtypes = [vp, C.POINTER(Stats)]
         L.acmeb200_get_cache_sizes.argtypes = [vp, C.c_int32, vp, C.POINTER(C.c_int32)]
+        L.acmeb200_get_cache_info.argtypes = [vp, C.c_int32, vp]
+        i32, dbl = C.c_int32, C.c_double
+        L.acmeb200_kdtree_build.argtypes = [i32, i32, i32, vp, vp, vp, vp]
+        L.acmeb200_kdtree_indnearest.argtypes = [i32, i32, i32, vp, vp, vp, vp, i32, vp, dbl, i32, vp]
+        L.acmeb200_solver_state_size.argtypes = [vp]
+        L.acmeb200_solver_state_size.restype = i64
+        L.acmeb200_get_solver_state.argtypes = [vp, vp, i64]
+        L.acmeb200_set_solver_state.argtypes = [vp, vp, i64]
+        L.acmeb200_get_extrapolation_origin.argtypes = [vp, i32, vp, vp]
+        L.acmeb200_device_count.argtypes = [C.POINTER(i32)]
+        L.acmeb200_set_device.argtypes = [i32]
+        L.acmeb200_get_device.argtypes = [vp, C.POINTER(i32)]
+        L.acmeb200_multi_create.argtypes = [C.POINTER(ModelDesc), i64, i32, C.POINTER(vp)]
+        L.acmeb200_multi_destroy.argtypes = [vp]
+        L.acmeb200_multi_destroy.restype = None
+        L.acmeb200_multi_shards.argtypes = [vp]
+        L.acmeb200_multi_model.argtypes = [vp, i32, C.POINTER(i64), C.POINTER(i64)]
+        L.acmeb200_multi_model.restype = vp
+        L.acmeb200_multi_run.argtypes = [vp, vp, i64, vp, i64, i64, u32]
         L.acmeb200_set_kernel.argtypes = [vp, C.c_int32]
         L.acmeb200_kernel_name.argtypes = [vp]
         L.acmeb200_kernel_name.restype = C.c_char_p
@@ -57,6 +76,10 @@ def check(rc):
 
 EXPORTS = ["acmeb200_model_create", "acmeb200_model_destroy", "acmeb200_run", "acmeb200_get_state",
            "acmeb200_set_state", "acmeb200_reset", "acmeb200_get_status", "acmeb200_get_stats", "acmeb200_get_cache_sizes",
+           "acmeb200_get_cache_info", "acmeb200_kdtree_build", "acmeb200_kdtree_indnearest",
+           "acmeb200_solver_state_size", "acmeb200_get_solver_state", "acmeb200_set_solver_state", "acmeb200_get_extrapolation_origin",
+           "acmeb200_device_count", "acmeb200_set_device", "acmeb200_get_device", "acmeb200_multi_create", "acmeb200_multi_destroy",
+           "acmeb200_multi_shards", "acmeb200_multi_model", "acmeb200_multi_run",
            "acmeb200_set_kernel", "acmeb200_kernel_name", "acmeb200_launch_count", "acmeb200_measure_fp64_peak",
            "acmeb200_last_error", "acmeb200_abi_version"]
 

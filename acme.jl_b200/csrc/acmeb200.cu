@@ -12,6 +12,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/acmeb200.h"
@@ -284,13 +285,26 @@ extern "C" int acmeb200_model_create(const acmeb200_model_desc* d, int64_t first
         st.hdr[KD_H_TREEN] = c.n_points; st.hdr[KD_H_FLAGS] = KD_F_FROZEN;
         for (int k = 0; k < c.n_points - 1; k++) st.set_cut(k + 1, c.cut_dim[k], c.cut_val[k]);
         for (int k = 0; k < c.n_points; k++) st.set_psidx(k + 1, c.ps_idx[k]);
-        if (s.np > 0) memcpy(st.ps, c.ps, sizeof(double) * (size_t)s.np * cap);
-        if (s.nn > 0) memcpy(st.zs, c.zs, sizeof(double) * (size_t)s.nn * cap);
+        for (int k = 0; k < cap; k++) {
+            for (int j = 0; j < s.np; j++) st.col(k + 1)[j] = c.ps[(size_t)k * s.np + j];
+            for (int j = 0; j < s.nn; j++) st.col(k + 1)[s.np + j] = c.zs[(size_t)k * s.nn + j];
+        }
         void* p = nullptr;
         CT(cudaMalloc(&p, sizeof(double) * img.size()));
         m->d_cache.push_back(p);
         CT(cudaMemcpy(p, img.data(), sizeof(double) * img.size(), cudaMemcpyHostToDevice));
         s.kd_base = (double*)p; s.kd_cap = cap; s.kd_frozen = 1;
+        s.kd_mir = nullptr; s.kd_mld = 1; s.kd_mshared = 1;
+        if (s.np > 0) {  // shared leaf mirror (devmodel.h): the tree's points in leaf order, doubles [leaf][dimension]
+            std::vector<double> mir((size_t)std::max(c.n_points, 1) * s.np, 0.0);
+            for (int k = 0; k < c.n_points; k++)
+                for (int j = 0; j < s.np; j++) mir[(size_t)k * s.np + j] = c.ps[(size_t)(c.ps_idx[k] - 1) * s.np + j];
+            void* pm = nullptr;
+            CT(cudaMalloc(&pm, sizeof(double) * mir.size()));
+            m->d_cache.push_back(pm);
+            CT(cudaMemcpy(pm, mir.data(), sizeof(double) * mir.size(), cudaMemcpyHostToDevice));
+            s.kd_mir = (double*)pm;
+        }
         m->has_cache = true;
     }
     CT(cudaMalloc(&m->d_status, sizeof(uint32_t) * (size_t)count));
@@ -311,7 +325,7 @@ static int select_kernel(acmeb200_model* m) {
     if (m->kernel_mode == 0) m->tpi = find_tpi(m->dm);
     if (!m->tpi && (m->kernel_mode == 0 || m->kernel_mode == 3)) {
         // one warp per instance, LU rows in registers: compile-time shapes only
-        if (!m->has_cache && m->rows_ok) m->rows = rows_shape(m->dm);  // shared or per-instance matrices
+        if (m->rows_ok) m->rows = rows_shape(m->dm);  // shared or per-instance matrices, learning or frozen solution store
         if (m->kernel_mode == 3 && !m->rows)
             return fail(ACMEB200_EUNSUPPORTED, "the rows-in-registers kernel has no instantiation for this model shape");
     }
@@ -321,7 +335,7 @@ static int select_kernel(acmeb200_model* m) {
         if (lanes && (m->kernel_mode == 2 || m->max_nn >= 4)) m->coop_lanes = lanes;
         m->coop_static = (m->coop_lanes >= 16 && coop_static_matches(m->dm)) ? 1 : 0;
         if (m->kernel_mode == 2 && !m->coop_lanes)
-            return fail(ACMEB200_EUNSUPPORTED, "the cooperative kernel needs shared matrices, no frozen cache and nn <= %d", MAX_ROWS);
+            return fail(ACMEB200_EUNSUPPORTED, "the cooperative kernel needs shared matrices and nn <= %d", MAX_ROWS);
     }
     m->ws_rows = m->tpi ? m->tpi->state_rows : m->dm.w_rows;
     if (m->tpi) m->kernel_name = m->tpi->name;
@@ -340,6 +354,7 @@ static int select_kernel(acmeb200_model* m) {
         DevSub& s = m->dm.subs[i];
         if (s.kd_frozen) continue;
         s.kd_base = nullptr; s.kd_scr = nullptr; s.kd_stride = 0; s.kd_sstride = 0; s.kd_cap = 0;
+        s.kd_mir = nullptr; s.kd_mld = 0; s.kd_mshared = 0;
         if (m->dm.solver != ACMEB200_SOLVER_HOMOTOPY_CACHING || s.np > KD_MAXNP) continue;
         size_t free_b = 0, total_b = 0;
         CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
@@ -347,7 +362,7 @@ static int select_kernel(acmeb200_model* m) {
         // superover stores ~900 solutions in its first second and ~150 per second after that): as large as a memory budget
         // allows, at most 4096; the descriptor (cache_capacity) or ACMEB200_CACHE_CAP override it
         int cap = 4096;
-        const size_t per_col = 8 * (size_t)(s.np + s.nn) + 12 + 24;
+        const size_t per_col = 8 * (size_t)(s.np + s.nn) + 16 + 24 + 8 * (size_t)s.np;
         const size_t budget = std::min<size_t>(free_b / 8, (size_t)4 << 30);
         while (cap > 64 && (size_t)m->B * cap * per_col > budget) cap /= 2;
         if (m->cache_capacity > 0) cap = m->cache_capacity;
@@ -359,6 +374,21 @@ static int select_kernel(acmeb200_model* m) {
         CUDA_TRY(cudaMalloc(&sc, sizeof(double) * (size_t)sstride * m->B));
         m->d_dyn.push_back(sc); m->dyn_bytes.push_back(0);  // scratch needs no clearing
         s.kd_base = (double*)st; s.kd_stride = stride; s.kd_scr = (double*)sc; s.kd_sstride = sstride; s.kd_cap = cap;
+        if (m->rows && s.np > 0) {  // leaf mirror of the warp-per-instance kernel (kernel_rows.cuh: centre, radius, floats [dimension][leaf])
+            void* mir = nullptr;
+            const int64_t mstride = rows_mirror_doubles(m->rows, cap);
+            const size_t mbytes = sizeof(double) * (size_t)mstride * m->B;
+            CUDA_TRY(cudaMalloc(&mir, mbytes));
+            m->d_dyn.push_back(mir); m->dyn_bytes.push_back(mbytes);
+            s.kd_mir = (double*)mir; s.kd_mld = mstride; s.kd_mshared = 0;
+        }
+        if (m->tpi && s.np > 0) {  // leaf mirror of the thread-per-instance kernels (devmodel.h), [leaf][dimension][instance]
+            void* mir = nullptr;
+            const size_t mbytes = sizeof(double) * (size_t)cap * s.np * m->B;
+            CUDA_TRY(cudaMalloc(&mir, mbytes));
+            m->d_dyn.push_back(mir); m->dyn_bytes.push_back(mbytes);
+            s.kd_mir = (double*)mir; s.kd_mld = m->B; s.kd_mshared = 0;
+        }
     }
     cudaFree(m->d_ws);
     m->d_ws = nullptr;
@@ -605,15 +635,282 @@ extern "C" int acmeb200_get_cache_sizes(acmeb200_model* m, int32_t sub, int32_t*
     CUDA_TRY(cudaDeviceSynchronize());
     const DevSub& s = m->dm.subs[sub];
     if (capacity_out) *capacity_out = s.kd_cap;
-    if (s.kd_cap > 0 && !s.kd_frozen)  // hdr[KD_H_NUM] of every instance's store
-        CUDA_TRY(cudaMemcpy2D(sizes_host, sizeof(int32_t), reinterpret_cast<const int*>(s.kd_base) + KD_H_NUM, sizeof(double) * (size_t)s.kd_stride,
-                              sizeof(int32_t), (size_t)m->B, cudaMemcpyDeviceToHost));
-    else if (s.kd_cap > 0) {
+    if (s.kd_cap > 0 && !s.kd_frozen) {  // hdr[KD_H_NUM] of every instance's store
+        CUDA_TRY(cudaMemcpy2DAsync(sizes_host, sizeof(int32_t), reinterpret_cast<const int*>(s.kd_base) + KD_H_NUM, sizeof(double) * (size_t)s.kd_stride,
+                                   sizeof(int32_t), (size_t)m->B, cudaMemcpyDeviceToHost, nullptr));
+        CUDA_TRY(cudaDeviceSynchronize());
+    } else if (s.kd_cap > 0) {
         int32_t n = 0;
         CUDA_TRY(cudaMemcpy(&n, reinterpret_cast<const int*>(s.kd_base) + KD_H_NUM, sizeof n, cudaMemcpyDeviceToHost));
         for (int64_t b = 0; b < m->B; b++) sizes_host[b] = n;
     } else
         memset(sizes_host, 0, sizeof(int32_t) * (size_t)m->B);
+    return ACMEB200_OK;
+}
+
+extern "C" int acmeb200_get_cache_info(acmeb200_model* m, int32_t sub, int32_t* info_host) {
+    if (!m || !info_host) return fail(ACMEB200_EINVAL, "null argument");
+    if (sub < 0 || sub >= m->dm.nsub) return fail(ACMEB200_EINVAL, "sub-problem %d out of range", sub);
+    CUDA_TRY(cudaSetDevice(m->device));
+    CUDA_TRY(cudaDeviceSynchronize());
+    const DevSub& s = m->dm.subs[sub];
+    memset(info_host, 0, sizeof(int32_t) * KD_HDR_INTS * (size_t)m->B);
+    if (s.kd_cap <= 0) return ACMEB200_OK;
+    if (!s.kd_frozen) {
+        CUDA_TRY(cudaMemcpy2DAsync(info_host, sizeof(int32_t) * KD_HDR_INTS, s.kd_base, sizeof(double) * (size_t)s.kd_stride,
+                                   sizeof(int32_t) * KD_HDR_INTS, (size_t)m->B, cudaMemcpyDeviceToHost, nullptr));
+        CUDA_TRY(cudaDeviceSynchronize());
+    } else {
+        CUDA_TRY(cudaMemcpy(info_host, s.kd_base, sizeof(int32_t) * KD_HDR_INTS, cudaMemcpyDeviceToHost));
+        for (int64_t b = 1; b < m->B; b++) memcpy(info_host + b * KD_HDR_INTS, info_host, sizeof(int32_t) * KD_HDR_INTS);
+    }
+    return ACMEB200_OK;
+}
+
+// ------------------------------------------------------------------ solver state (checkpoint / deepcopy)
+namespace {
+struct StateHeader {
+    uint64_t magic;
+    int32_t abi, layout;  // layout: 1 = thread-per-instance kernel state rows, 0 = generic workspace
+    int64_t B, ws_rows, n_done, total_bytes;
+    int32_t nx, nu, ny, nsub, nnt, solver;
+    int32_t np[MAX_SUBS], nn[MAX_SUBS], kd_cap[MAX_SUBS];
+    int64_t kd_stride[MAX_SUBS];
+};
+constexpr uint64_t STATE_MAGIC = 0x41434d4542323030ull;  // "ACMEB200"
+
+StateHeader state_header(const acmeb200_model* m) {
+    StateHeader h;
+    memset(&h, 0, sizeof h);
+    h.magic = STATE_MAGIC; h.abi = ACMEB200_ABI_VERSION; h.layout = m->tpi ? 1 : 0;
+    h.B = m->B; h.ws_rows = m->ws_rows; h.n_done = m->n_done;
+    h.nx = m->dm.nx; h.nu = m->dm.nu; h.ny = m->dm.ny; h.nsub = m->dm.nsub; h.nnt = m->dm.nnt; h.solver = m->dm.solver;
+    int64_t bytes = sizeof(StateHeader) + sizeof(double) * m->ws_rows * m->B + sizeof(uint32_t) * m->B + sizeof(long long) * m->B + sizeof(DevStats);
+    for (int i = 0; i < m->dm.nsub; i++) {
+        const DevSub& s = m->dm.subs[i];
+        h.np[i] = s.np; h.nn[i] = s.nn;
+        if (s.kd_cap > 0 && !s.kd_frozen) {  // a frozen store belongs to the descriptor, not to the state
+            h.kd_cap[i] = s.kd_cap; h.kd_stride[i] = s.kd_stride;
+        }
+    }
+    for (size_t k = 0; k < m->d_dyn.size(); k++) bytes += (int64_t)m->dyn_bytes[k];  // learning stores and their leaf mirrors (scratch: 0)
+    h.total_bytes = bytes;
+    return h;
+}
+}  // namespace
+
+extern "C" int64_t acmeb200_solver_state_size(acmeb200_model* m) {
+    if (!m) return fail(ACMEB200_EINVAL, "null model");
+    return state_header(m).total_bytes;
+}
+
+extern "C" int acmeb200_get_solver_state(acmeb200_model* m, void* buf, int64_t bytes) {
+    if (!m || !buf) return fail(ACMEB200_EINVAL, "null argument");
+    const StateHeader h = state_header(m);
+    if (bytes < h.total_bytes) return fail(ACMEB200_EINVAL, "buffer of %lld bytes, the state needs %lld", (long long)bytes, (long long)h.total_bytes);
+    CUDA_TRY(cudaSetDevice(m->device));
+    CUDA_TRY(cudaDeviceSynchronize());
+    char* out = static_cast<char*>(buf);
+    memcpy(out, &h, sizeof h); out += sizeof h;
+    auto take = [&](const void* dsrc, size_t n) -> cudaError_t { const cudaError_t e = n ? cudaMemcpy(out, dsrc, n, cudaMemcpyDeviceToHost) : cudaSuccess; out += n; return e; };
+    CUDA_TRY(take(m->d_ws, sizeof(double) * (size_t)(m->ws_rows * m->B)));
+    CUDA_TRY(take(m->d_status, sizeof(uint32_t) * (size_t)m->B));
+    CUDA_TRY(take(m->d_first_fail, sizeof(long long) * (size_t)m->B));
+    CUDA_TRY(take(m->d_stats, sizeof(DevStats)));
+    for (size_t k = 0; k < m->d_dyn.size(); k++) CUDA_TRY(take(m->d_dyn[k], m->dyn_bytes[k]));
+    return ACMEB200_OK;
+}
+
+extern "C" int acmeb200_set_solver_state(acmeb200_model* m, const void* buf, int64_t bytes) {
+    if (!m || !buf) return fail(ACMEB200_EINVAL, "null argument");
+    if (bytes < (int64_t)sizeof(StateHeader)) return fail(ACMEB200_EINVAL, "not a solver state");
+    StateHeader h;
+    memcpy(&h, buf, sizeof h);
+    if (h.magic != STATE_MAGIC || h.abi != ACMEB200_ABI_VERSION) return fail(ACMEB200_EINVAL, "not a solver state of this ABI version");
+    if (bytes < h.total_bytes) return fail(ACMEB200_EINVAL, "truncated solver state");
+    CUDA_TRY(cudaSetDevice(m->device));
+    // a learning store saved with another physical capacity (the automatic capacity depends on the free memory of the
+    // device it was created on): re-create this model's stores with the saved one
+    for (int i = 0; i < std::min(h.nsub, m->dm.nsub); i++) {
+        const DevSub& s = m->dm.subs[i];
+        if (h.kd_cap[i] > 0 && !s.kd_frozen && s.kd_cap != h.kd_cap[i]) {
+            m->cache_capacity = h.kd_cap[i];
+            const int rc = select_kernel(m);
+            if (rc) return rc;
+            break;
+        }
+    }
+    const StateHeader mine = state_header(m);
+    bool same = h.B == mine.B && h.ws_rows == mine.ws_rows && h.layout == mine.layout && h.nx == mine.nx && h.nu == mine.nu && h.ny == mine.ny &&
+                h.nsub == mine.nsub && h.nnt == mine.nnt && h.solver == mine.solver && h.total_bytes == mine.total_bytes;
+    for (int i = 0; same && i < h.nsub; i++)
+        same = h.np[i] == mine.np[i] && h.nn[i] == mine.nn[i] && h.kd_cap[i] == mine.kd_cap[i] && h.kd_stride[i] == mine.kd_stride[i];
+    if (!same)
+        return fail(ACMEB200_EINVAL, "the solver state belongs to another model (dimensions, instance count, solver, cache capacity) or was "
+                                     "saved with another kernel selected (this model runs on %s)", m->kernel_name.c_str());
+    CUDA_TRY(cudaDeviceSynchronize());
+    const char* in = static_cast<const char*>(buf) + sizeof h;
+    auto put = [&](void* ddst, size_t n) -> cudaError_t { const cudaError_t e = n ? cudaMemcpy(ddst, in, n, cudaMemcpyHostToDevice) : cudaSuccess; in += n; return e; };
+    CUDA_TRY(put(m->d_ws, sizeof(double) * (size_t)(m->ws_rows * m->B)));
+    CUDA_TRY(put(m->d_status, sizeof(uint32_t) * (size_t)m->B));
+    CUDA_TRY(put(m->d_first_fail, sizeof(long long) * (size_t)m->B));
+    CUDA_TRY(put(m->d_stats, sizeof(DevStats)));
+    for (size_t k = 0; k < m->d_dyn.size(); k++) CUDA_TRY(put(m->d_dyn[k], m->dyn_bytes[k]));
+    m->n_done = h.n_done;
+    return ACMEB200_OK;
+}
+
+extern "C" int acmeb200_get_extrapolation_origin(acmeb200_model* m, int32_t sub, double* p_host, double* z_host) {
+    if (!m) return fail(ACMEB200_EINVAL, "null model");
+    if (sub < 0 || sub >= m->dm.nsub) return fail(ACMEB200_EINVAL, "sub-problem %d out of range", sub);
+    CUDA_TRY(cudaSetDevice(m->device));
+    CUDA_TRY(cudaDeviceSynchronize());
+    const DevSub& s = m->dm.subs[sub];
+    // rows of the [row][instance] state: the thread-per-instance kernels keep x | last_p | last_z | Mx, the others the generic workspace
+    const int prow = m->tpi ? m->dm.nx : s.w_lastp, zrow = m->tpi ? m->dm.nx + s.np : s.w_lastz;
+    auto rows_to = [&](int row0, int n, double* dst) -> int {
+        if (!dst || n == 0) return ACMEB200_OK;
+        std::vector<double> r((size_t)n * m->B);
+        CUDA_TRY(cudaMemcpy(r.data(), m->d_ws + (size_t)row0 * m->B, sizeof(double) * r.size(), cudaMemcpyDeviceToHost));
+        for (int64_t b = 0; b < m->B; b++)
+            for (int i = 0; i < n; i++) dst[b * n + i] = r[(size_t)i * m->B + b];
+        return ACMEB200_OK;
+    };
+    int rc = rows_to(prow, s.np, p_host);
+    if (rc) return rc;
+    return rows_to(zrow, s.nn, z_host);
+}
+
+// ------------------------------------------------------------------ devices, the batch over all GPUs
+extern "C" int acmeb200_device_count(int32_t* count_out) {
+    if (!count_out) return fail(ACMEB200_EINVAL, "null argument");
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) n = 0;
+    *count_out = n;
+    return ACMEB200_OK;
+}
+extern "C" int acmeb200_set_device(int32_t device) {
+    CUDA_TRY(cudaSetDevice(device));
+    return ACMEB200_OK;
+}
+extern "C" int acmeb200_get_device(acmeb200_model* m, int32_t* device_out) {
+    if (!m || !device_out) return fail(ACMEB200_EINVAL, "null argument");
+    *device_out = m->device;
+    return ACMEB200_OK;
+}
+
+struct acmeb200_multi {
+    std::vector<acmeb200_model*> shards;
+    std::vector<int64_t> first, count;
+    int nu = 0, ny = 0;
+};
+
+extern "C" void acmeb200_multi_destroy(acmeb200_multi* mm) {
+    if (!mm) return;
+    for (acmeb200_model* m : mm->shards) acmeb200_model_destroy(m);
+    delete mm;
+}
+
+extern "C" int acmeb200_multi_create(const acmeb200_model_desc* d, int64_t B, int32_t n_gpus, acmeb200_multi** out) {
+    if (!d || !out) return fail(ACMEB200_EINVAL, "null argument");
+    *out = nullptr;
+    if (B <= 0) return fail(ACMEB200_EINVAL, "no instances");
+    int ndev = 0, prev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(ACMEB200_ENODEVICE, "no CUDA device available (this library has no CPU fallback)");
+    if (n_gpus <= 0) n_gpus = ndev;
+    if (n_gpus > ndev) return fail(ACMEB200_EINVAL, "%d GPUs asked for, %d visible", n_gpus, ndev);
+    if ((int64_t)n_gpus > B) n_gpus = (int32_t)B;
+    cudaGetDevice(&prev);
+    acmeb200_multi* mm = new acmeb200_multi();
+    mm->nu = d->nu; mm->ny = d->ny;
+    const int64_t base = B / n_gpus, rem = B % n_gpus;
+    for (int g = 0; g < n_gpus; g++) {
+        const int64_t first = g * base + std::min<int64_t>(g, rem), count = base + (g < rem ? 1 : 0);
+        acmeb200_model* m = nullptr;
+        int rc = cudaSetDevice(g) == cudaSuccess ? acmeb200_model_create(d, first, count, &m) : fail(ACMEB200_ECUDA, "cudaSetDevice(%d) failed", g);
+        if (rc) { acmeb200_multi_destroy(mm); cudaSetDevice(prev); return rc; }
+        mm->shards.push_back(m); mm->first.push_back(first); mm->count.push_back(count);
+    }
+    cudaSetDevice(prev);
+    *out = mm;
+    return ACMEB200_OK;
+}
+
+extern "C" int acmeb200_multi_shards(const acmeb200_multi* mm) { return mm ? (int)mm->shards.size() : 0; }
+
+extern "C" acmeb200_model* acmeb200_multi_model(acmeb200_multi* mm, int32_t shard, int64_t* first_out, int64_t* count_out) {
+    if (!mm || shard < 0 || shard >= (int)mm->shards.size()) return nullptr;
+    if (first_out) *first_out = mm->first[shard];
+    if (count_out) *count_out = mm->count[shard];
+    return mm->shards[shard];
+}
+
+extern "C" int acmeb200_multi_run(acmeb200_multi* mm, const double* U, int64_t u_stride, double* Y, int64_t y_stride,
+                                  int64_t N, uint32_t flags) {
+    if (!mm) return fail(ACMEB200_EINVAL, "null argument");
+    if (flags & (ACMEB200_U_DEVICE | ACMEB200_Y_DEVICE | ACMEB200_SAMPLE_MAJOR))
+        return fail(ACMEB200_EUNSUPPORTED, "acmeb200_multi_run takes instance-major host streams (one device cannot address all shards' device memory)");
+    if (y_stride == 0) y_stride = (int64_t)mm->ny * N;
+    const size_t G = mm->shards.size();
+    std::vector<int> rcs(G, 0);
+    std::vector<std::string> errs(G);
+    auto work = [&](size_t g) {
+        // every shard: its own device, its own pinned staging and streams, its contiguous block of the host arrays
+        const double* u = U ? U + (u_stride ? mm->first[g] * u_stride : 0) : nullptr;
+        double* y = Y ? Y + mm->first[g] * y_stride : nullptr;
+        rcs[g] = acmeb200_run(mm->shards[g], u, u_stride, y, y_stride, N, 0, nullptr);
+        if (rcs[g]) errs[g] = acmeb200_last_error();  // the message is thread local
+    };
+    std::vector<std::thread> threads;
+    for (size_t g = 1; g < G; g++) threads.emplace_back(work, g);
+    work(0);
+    for (std::thread& t : threads) t.join();
+    for (size_t g = 0; g < G; g++)
+        if (rcs[g]) return fail(rcs[g], "shard %d: %s", (int)g, errs[g].c_str());
+    return ACMEB200_OK;
+}
+
+// ------------------------------------------------------------------ k-d tree, host side (kdcache.cuh: the device's own code)
+extern "C" int acmeb200_kdtree_build(int32_t np, int32_t n_columns, int32_t n_points, const double* ps, int32_t* cut_dim,
+                                     double* cut_val, int32_t* ps_idx) {
+    if (np < 0 || n_columns < 0 || n_points < 0 || n_points > n_columns) return fail(ACMEB200_EINVAL, "need 0 <= n_points <= n_columns");
+    if (n_points == 0) return ACMEB200_OK;
+    if ((np > 0 && !ps) || !ps_idx || (n_points > 1 && (!cut_dim || !cut_val))) return fail(ACMEB200_EINVAL, "null argument");
+    if (np > 255) return fail(ACMEB200_EUNSUPPORTED, "np > 255");
+    const int cap = n_columns;
+    std::vector<double> img((size_t)kd_store_doubles(np, 0, cap), 0.0), scratch((size_t)kd_scratch_doubles(cap), 0.0);
+    KdStore st = KdStore::at(img.data(), scratch.data(), np, 0, cap);
+    if (np > 0) memcpy(st.cols, ps, sizeof(double) * (size_t)np * cap);  // nn = 0: the columns are the points
+    kd_build(st, n_points, n_columns, n_columns);
+    for (int k = 0; k < n_points - 1; k++) { cut_dim[k] = st.cutdim(k + 1); cut_val[k] = st.cutval(k + 1); }
+    for (int k = 0; k < n_points; k++) ps_idx[k] = st.psidx(k + 1);
+    return ACMEB200_OK;
+}
+
+extern "C" int acmeb200_kdtree_indnearest(int32_t np, int32_t n_columns, int32_t n_points, const int32_t* cut_dim, const double* cut_val,
+                                          const int32_t* ps_idx, const double* ps, int32_t n_queries, const double* queries,
+                                          double best_dist, int32_t best_pidx, int32_t* nearest_out) {
+    if (np < 0 || n_columns < 0 || n_points < 0 || n_points > n_columns || n_queries < 0) return fail(ACMEB200_EINVAL, "bad sizes");
+    if (np > KD_MAXNP) return fail(ACMEB200_EUNSUPPORTED, "the search supports np <= %d", KD_MAXNP);
+    if (n_queries == 0) return ACMEB200_OK;
+    if (!nearest_out || (np > 0 && (!queries || !ps)) || (n_points > 0 && !ps_idx) || (n_points > 1 && (!cut_dim || !cut_val)))
+        return fail(ACMEB200_EINVAL, "null argument");
+    for (int k = 0; k < n_points; k++)
+        if (ps_idx[k] < 1 || ps_idx[k] > n_columns) return fail(ACMEB200_EINVAL, "ps_idx out of range");
+    for (int k = 0; k < n_points - 1; k++)
+        if (cut_dim[k] < 1 || cut_dim[k] > np) return fail(ACMEB200_EINVAL, "cut_dim out of range");
+    const int cap = std::max(n_columns, 1);
+    std::vector<double> img((size_t)kd_store_doubles(np, 0, cap), 0.0);
+    KdStore st = KdStore::at(img.data(), nullptr, np, 0, cap);
+    if (np > 0 && n_columns > 0) memcpy(st.cols, ps, sizeof(double) * (size_t)np * n_columns);
+    for (int k = 0; k < n_points - 1; k++) st.set_cut(k + 1, cut_dim[k], cut_val[k]);
+    for (int k = 0; k < n_points; k++) st.set_psidx(k + 1, ps_idx[k]);
+    for (int q = 0; q < n_queries; q++) {
+        const double* p = queries + (size_t)q * np;
+        int ovf = 0;
+        nearest_out[q] = kd_indnearest(st, n_points, [&](int i) { return p[i]; }, best_dist, best_pidx, &ovf);
+    }
     return ACMEB200_OK;
 }
 

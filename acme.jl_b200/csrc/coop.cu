@@ -15,7 +15,7 @@ using CoopSuperover = CoopStatic<11, 4, 1, 13, 29, 11, 8, 23>;
 bool coop_static_matches(const DevModel& dm) { return CoopSuperover::matches(dm); }
 
 int coop_lanes_for(const acmeb200_model* m) {
-    if (m->blob_stride != 0 || m->has_cache || m->dm.nsub == 0 || m->max_nn > MAX_ROWS || !m->rows_ok) return 0;
+    if (m->blob_stride != 0 || m->dm.nsub == 0 || m->max_nn > MAX_ROWS || !m->rows_ok) return 0;
     const int need = std::max(m->max_nn, m->max_nelem);
     int lanes = need <= 8 ? 8 : (need <= 16 ? 16 : 32);
     // small batches are latency-bound: one instance per warp avoids the two groups of a warp
@@ -32,7 +32,8 @@ int coop_lanes_for(const acmeb200_model* m) {
 template <int L, class P>
 static cudaError_t launch_coop(const acmeb200_model* m, const RunArgs& a, cudaStream_t stream) {
     const size_t smem = coop_smem_bytes<L>(m->dm);
-    static bool attr_set = false;
+    static bool attr_set_dev[ACME_MAX_DEVICES] = {};  // function attributes are per device: one process may drive several
+    bool& attr_set = attr_set_dev[m->device & (ACME_MAX_DEVICES - 1)];
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(k_coop<L, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return e;

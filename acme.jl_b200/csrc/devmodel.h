@@ -45,6 +45,14 @@ struct DevSub {
     int64_t kd_sstride;
     int kd_cap;     // 0: no store (solver without cache, or np beyond what the search holds)
     int kd_frozen;  // 1: the host-built store of the descriptor (read-only)
+    // Leaf mirror of the specialised kernels: the points of the current tree in leaf order, laid out for the kernel's
+    // lanes to scan (thread-per-instance: doubles, [(leaf*np + d)*kd_mld + instance]; warp-per-instance: see kernel_rows.cuh).
+    // What the reference's tree search returns is the nearest tree point if it is strictly nearer than the seed; scanning
+    // every leaf with all lanes finds it at streaming speed where the search is a chain of dependent loads -- the search
+    // itself only runs when two leaves tie for the minimum (then its visiting order decides).
+    double* kd_mir;
+    int64_t kd_mld;   // leading dimension of the mirror (instances), 1 for the shared mirror of a frozen store
+    int kd_mshared;   // 1: one mirror for all instances
 };
 
 struct DevModel {

@@ -12,6 +12,8 @@
 
 struct acmeb200_model;
 
+constexpr int ACME_MAX_DEVICES = 64;  // per-device launch state (function attributes) is kept in tables of this size
+
 // kernel launch: CUDA's <<<>>> in the product; the host emulation of tests/emu runs the CTAs as fibers
 #ifdef ACME_HOST_EMU
 #define ACME_LAUNCH(kernel, grid, block, smem, stream, ...) acme_emu::launch(kernel, (unsigned)(grid), (unsigned)(block), (size_t)(smem), __VA_ARGS__)
@@ -80,3 +82,4 @@ cudaError_t launch_coop_kernel(const acmeb200_model* m, const acme::RunArgs& a, 
 // rows.cu: warp-per-instance kernel, LU rows in registers
 int rows_shape(const acme::DevModel& dm);  // 0: no instantiation, else the shape index stored in acmeb200_model::rows
 cudaError_t launch_rows_kernel(const acmeb200_model* m, const acme::RunArgs& a, cudaStream_t stream);
+int64_t rows_mirror_doubles(int shape, int cap);  // per-instance size of the kernel's leaf mirror (kernel_rows.cuh)

@@ -6,7 +6,7 @@
 //                                                                      kd_after_solve (store, rebuild schedule)
 //
 // One store per (sub-problem, instance), instance-contiguous in global memory:
-//   hdr[8] ints | cut_val[cap] | ti[cap] (cut_dim + ps_idx packed) | ps[cap][np] | zs[cap][nn]
+//   hdr[8] ints | nodes[cap] (16 bytes: cut value, cut dimension, leaf column) | columns[cap][np + nn] (p then z)
 // plus a scratch block (keys + permutation, twice `cap` each) used only while a tree is rebuilt.
 //
 // What is reproduced on purpose, because it decides WHICH stored solution becomes the start point and
@@ -65,45 +65,48 @@ KD_HD double kd_sub(double a, double b) {
 #endif
 }
 
-// bytes of one instance's store / scratch (both multiples of 16)
-KD_HD int64_t kd_store_doubles(int np, int nn, int cap) {
-    return KD_HDR_INTS / 2 + (int64_t)cap + (cap + 1) / 2 + (int64_t)cap * np + (int64_t)cap * nn;
-}
+// doubles of one instance's store / scratch
+KD_HD int64_t kd_store_doubles(int np, int nn, int cap) { return KD_HDR_INTS / 2 + 2 * (int64_t)cap + (int64_t)cap * (np + nn); }
 KD_HD int64_t kd_scratch_doubles(int cap) { return 2 * (int64_t)cap + cap; }  // 2*cap keys + 2*cap ints
+
+// One tree node / leaf slot, 16 bytes: slot k-1 holds the cut of NODE k (nodes 1..Np-1) and the column of LEAF k
+// (leaves 1..Np) -- two unrelated things that share an index range, so a small tree is one or two cache lines.
+struct alignas(16) KdNode {
+    double cut_val;
+    int ti;  // bits 0..7 cut_dim (1-based), bits 8.. ps_idx (1-based column)
+    int pad;
+};
 
 struct KdStore {
     int* hdr;
-    double* cut_val;  // node k (1-based) at [k-1]
-    int* ti;          // [k-1]: bits 0..7 cut_dim (1-based) of node k, bits 8.. ps_idx (1-based column) of leaf k
-    double* ps;       // column c (1-based) at [(c-1)*np + d]
-    double* zs;
-    double* skey;     // scratch: [0,cap) keys of the range being sorted, [cap,2cap) merge buffer
-    int* sidx;        // scratch: [0,cap) permutation p_idx (1-based columns), [cap,2cap) merge buffer
+    KdNode* nodes;  // [cap]
+    double* cols;   // column c (1-based) at [(c-1)*(np+nn)]: p (np values) then z (nn values)
+    double* skey;   // scratch: [0,cap) keys of the range being sorted, [cap,2cap) merge buffer
+    int* sidx;      // scratch: [0,cap) permutation p_idx (1-based columns), [cap,2cap) merge buffer
     int np, nn, cap;
 
     KD_HD static KdStore at(double* base, double* scratch, int np, int nn, int cap) {
         KdStore c;
         c.np = np; c.nn = nn; c.cap = cap;
         c.hdr = reinterpret_cast<int*>(base);
-        c.cut_val = base + KD_HDR_INTS / 2;
-        c.ti = reinterpret_cast<int*>(c.cut_val + cap);
-        c.ps = c.cut_val + cap + (cap + 1) / 2;
-        c.zs = c.ps + (int64_t)cap * np;
+        c.nodes = reinterpret_cast<KdNode*>(base + KD_HDR_INTS / 2);
+        c.cols = base + KD_HDR_INTS / 2 + 2 * (int64_t)cap;
         c.skey = scratch;
         c.sidx = scratch ? reinterpret_cast<int*>(scratch + 2 * (int64_t)cap) : nullptr;
         return c;
     }
+    KD_HD double* col(int c1) const { return cols + (int64_t)(c1 - 1) * (np + nn); }
     // columns beyond the physical capacity are the virtual zero columns of the reference's doubled arrays
-    KD_HD double P(int d, int col) const { return col <= cap ? ps[(int64_t)(col - 1) * np + d] : 0.0; }
-    KD_HD double Z(int i, int col) const { return col <= cap ? zs[(int64_t)(col - 1) * nn + i] : 0.0; }
-    KD_HD int cutdim(int node) const { return ti[node - 1] & 0xff; }
-    KD_HD double cutval(int node) const { return cut_val[node - 1]; }
-    KD_HD int psidx(int leaf) const { return (int)((unsigned)ti[leaf - 1] >> 8); }
+    KD_HD double P(int d, int c1) const { return c1 <= cap ? col(c1)[d] : 0.0; }
+    KD_HD double Z(int i, int c1) const { return c1 <= cap ? col(c1)[np + i] : 0.0; }
+    KD_HD int cutdim(int node) const { return nodes[node - 1].ti & 0xff; }
+    KD_HD double cutval(int node) const { return nodes[node - 1].cut_val; }
+    KD_HD int psidx(int leaf) const { return (int)((unsigned)nodes[leaf - 1].ti >> 8); }
     KD_HD void set_cut(int node, int dim, double v) {
-        ti[node - 1] = (ti[node - 1] & ~0xff) | dim;
-        cut_val[node - 1] = v;
+        nodes[node - 1].ti = (nodes[node - 1].ti & ~0xff) | dim;
+        nodes[node - 1].cut_val = v;
     }
-    KD_HD void set_psidx(int leaf, int col) { ti[leaf - 1] = (ti[leaf - 1] & 0xff) | (col << 8); }
+    KD_HD void set_psidx(int leaf, int c1) { nodes[leaf - 1].ti = (nodes[leaf - 1].ti & 0xff) | (c1 << 8); }
 };
 
 // ---------------------------------------------------------------------------------------------- construction
@@ -340,32 +343,42 @@ KD_HD int kd_lookup(const KdStore& c, PF p, double best_diff, int* overflow) {
     return kd_indnearest(c, c.hdr[KD_H_TREEN], p, best_diff, idx, overflow);
 }
 
-// What follows the base solve (solvers.jl:374-394): store (p, z) if the solve needed more than 5 iterations and
-// converged, count down to the next rebuild, rebuild.  Returns true when the tree was rebuilt.
+// What follows the base solve (solvers.jl:374-389): store (p, z) if the solve needed more than 5 iterations and
+// converged, count down to the next rebuild.  Returns true when the tree is due for a rebuild (solvers.jl:390):
+// the caller rebuilds (kd_build, or kd_build_warp with its whole warp) and calls kd_rebuilt.
 template <class PF, class ZF>
-KD_HD bool kd_after_solve(KdStore& c, bool store, PF p, ZF z) {
+KD_HD bool kd_store_step(KdStore& c, bool store, PF p, ZF z, int* stored_col = nullptr) {
     int* const h = c.hdr;
+    if (stored_col) *stored_col = 0;
     if (h[KD_H_FLAGS] & KD_F_FROZEN) return false;
     if (store) {
         if (h[KD_H_NUM] < c.cap) {
             const int n = ++h[KD_H_NUM];
             if (n > h[KD_H_CAPREF]) h[KD_H_CAPREF] = 2 * n;  // the reference's arrays double here (solvers.jl:376-382)
-            for (int j = 0; j < c.np; j++) c.ps[(int64_t)(n - 1) * c.np + j] = p(j);
-            for (int j = 0; j < c.nn; j++) c.zs[(int64_t)(n - 1) * c.nn + j] = z(j);
+            double* const dst = c.col(n);
+            for (int j = 0; j < c.np; j++) dst[j] = p(j);
+            for (int j = 0; j < c.nn; j++) dst[c.np + j] = z(j);
             h[KD_H_NEW] += 1;
+            if (stored_col) *stored_col = n;
         } else {
             h[KD_H_FLAGS] |= KD_F_FULL;  // the reference would keep growing; this store stops learning
         }
     }
     if (h[KD_H_NEW] > 0) h[KD_H_LIMIT] -= 1;
-    if (h[KD_H_NEW] > h[KD_H_LIMIT]) {
-        const int cap_ref = h[KD_H_CAPREF];
-        kd_build(c, h[KD_H_NUM], cap_ref < c.cap ? cap_ref : c.cap, cap_ref);
-        h[KD_H_NEW] = 0;
-        h[KD_H_LIMIT] = 2 * cap_ref;
-        return true;
-    }
-    return false;
+    return h[KD_H_NEW] > h[KD_H_LIMIT];
+}
+KD_HD void kd_rebuilt(KdStore& c) {  // solvers.jl:391-393
+    c.hdr[KD_H_NEW] = 0;
+    c.hdr[KD_H_LIMIT] = 2 * c.hdr[KD_H_CAPREF];
+}
+// the whole of solvers.jl:374-394 by one thread.  Returns true when the tree was rebuilt.
+template <class PF, class ZF>
+KD_HD bool kd_after_solve(KdStore& c, bool store, PF p, ZF z, int* stored_col = nullptr) {
+    if (!kd_store_step(c, store, p, z, stored_col)) return false;
+    const int cap_ref = c.hdr[KD_H_CAPREF];
+    kd_build(c, c.hdr[KD_H_NUM], cap_ref < c.cap ? cap_ref : c.cap, cap_ref);
+    kd_rebuilt(c);
+    return true;
 }
 
 // CachingSolver(basesolver, initial_p = 0, initial_z, nn) (solvers.jl:327-333) on zero-filled memory
@@ -373,9 +386,9 @@ template <class ZF>
 KD_HD void kd_init(KdStore& c, ZF init_z) {
     c.hdr[KD_H_NUM] = 1; c.hdr[KD_H_NEW] = 0; c.hdr[KD_H_LIMIT] = 2; c.hdr[KD_H_CAPREF] = 1; c.hdr[KD_H_TREEN] = 1;
     c.hdr[KD_H_FLAGS] = 0; c.hdr[6] = 0; c.hdr[7] = 0;
-    for (int j = 0; j < c.np; j++) c.ps[j] = 0.0;
-    for (int j = 0; j < c.nn; j++) c.zs[j] = init_z(j);
-    c.ti[0] = 1 << 8;  // KDTree(hcat(initial_p)): one leaf, column 1
+    for (int j = 0; j < c.np; j++) c.cols[j] = 0.0;
+    for (int j = 0; j < c.nn; j++) c.cols[c.np + j] = init_z(j);
+    c.nodes[0].ti = 1 << 8;  // KDTree(hcat(initial_p)): one leaf, column 1
 }
 
 }  // namespace acme

@@ -306,62 +306,44 @@ __device__ inline GSolveResult c_simple_solve(const CCtx<L>& g, const DevSub& s,
     return r;
 }
 
-// solve(::CachingSolver, p)  (solvers.jl:347-396) with a DYNAMIC per-instance cache: the start
-// point is the nearest of {current origin, every stored solution}; solutions that needed more
-// than 5 iterations are appended (solvers.jl:374-386).  The reference finds the nearest stored
-// point with a k-d tree plus a linear scan of the newest entries; here all stored points are
-// scanned, the lanes of the group taking one point each -- the same exact nearest neighbour (up to
-// distance ties), no tree to rebuild.  Capacity is fixed (dyn_cap); once full nothing is added.
+// solve(::CachingSolver, p)  (solvers.jl:347-396) on the instance's solution store (kdcache.cuh: the reference's k-d
+// tree, newest-entries scan and rebuild schedule).  The search, the store and the rebuilds are serial code run by the
+// group's first lane (this kernel is the fallback for shapes without a specialised instantiation); the chosen column
+// is broadcast and the group re-origins / solves together.
 template <int L, class P>
 __device__ inline GSolveResult c_base_solve(const CCtx<L>& g, const DevSub& s, int si, int prow, int64_t inst) {
     const DevModel& m = g.m;
-    const bool caching = m.solver == ACMEB200_SOLVER_HOMOTOPY_CACHING && s.dyn_cap > 0;
-    double* cps = nullptr;
-    double* czs = nullptr;
-    int n = 0;
+    const bool caching = m.solver == ACMEB200_SOLVER_HOMOTOPY_CACHING && s.kd_cap > 0;
     if (caching) {
-        cps = s.dyn_ps + inst * (int64_t)SD(NP, s.np) * s.dyn_cap;
-        czs = s.dyn_zs + inst * (int64_t)SD(NN, s.nn) * s.dyn_cap;
-        n = s.dyn_n[inst];  // solutions stored so far; the ring buffer holds the newest dyn_cap of them
-        const int nvalid = n < s.dyn_cap ? n : s.dyn_cap;
-        double best = 0.0;
-        for (int i = 0; i < SD(NP, s.np); i++) {
-            const double d = g.W(prow + i) - g.W(SD(W_LASTP, s.w_lastp) + i);
-            best = fma(d, d, best);
-        }
-        double lbest = best;
-        int lidx = -1;
-        for (int idx = g.lane; idx < nvalid; idx += L) {
-            double d2 = 0.0;
-            for (int d = 0; d < SD(NP, s.np); d++) {
-                const double df = cps[(int64_t)d * s.dyn_cap + idx] - g.W(prow + d);
-                d2 = fma(df, df, d2);
+        int idx = 0;
+        if (g.lane == 0) {
+            double best = 0.0;
+            for (int i = 0; i < SD(NP, s.np); i++) {
+                const double d = g.W(prow + i) - g.W(SD(W_LASTP, s.w_lastp) + i);
+                best = kd_add(best, kd_mul(d, d));
             }
-            if (d2 < lbest) { lbest = d2; lidx = idx; }
+            const KdStore c = g_store(s, inst);
+            int ovf = 0;
+            idx = kd_lookup(c, [&](int i) { return g.W(prow + i); }, best, &ovf);
+            if (ovf) c.hdr[KD_H_FLAGS] |= KD_F_HEAP_OVERFLOW;
         }
-#pragma unroll
-        for (int o = L / 2; o > 0; o >>= 1) {
-            const double ob = __shfl_xor_sync(g.gmask, lbest, o, L);
-            const int oi = __shfl_xor_sync(g.gmask, lidx, o, L);
-            // ties: the current origin (-1) wins over stored points (the reference replaces it only on
-            // a strictly smaller distance), among stored points the older one wins
-            if (ob < lbest || (ob == lbest && (oi < 0 ? lidx >= 0 : (lidx >= 0 && oi < lidx)))) { lbest = ob; lidx = oi; }
-        }
-        if (lidx >= 0) {  // uniform within the group
+        idx = __shfl_sync(g.gmask, idx, 0, L);
+        if (idx != 0) {  // uniform within the group
+            const KdStore c = g_store(s, inst);
             g.sync();
-            for (int i = g.lane; i < SD(NP, s.np); i += L) g.W(SD(W_CP, m.w_cp) + i) = cps[(int64_t)i * s.dyn_cap + lidx];
-            for (int i = g.lane; i < SD(NN, s.nn); i += L) g.W(SD(W_Z, m.w_z) + i) = czs[(int64_t)i * s.dyn_cap + lidx];
+            for (int i = g.lane; i < SD(NP, s.np); i += L) g.W(SD(W_CP, m.w_cp) + i) = c.P(i, idx);
+            for (int i = g.lane; i < SD(NN, s.nn); i += L) g.W(SD(W_Z, m.w_z) + i) = c.Z(i, idx);
             g.sync();
             c_set_origin<L, P>(g, s, si, SD(W_CP, m.w_cp), SD(W_Z, m.w_z));
         }
     }
     const GSolveResult r = c_simple_solve<L, P>(g, s, si, prow);
-    if (caching && r.iters > 5 && r.converged) {
-        const int slot = n % s.dyn_cap;  // ring buffer: the oldest entry is overwritten
-        for (int i = g.lane; i < SD(NP, s.np); i += L) cps[(int64_t)i * s.dyn_cap + slot] = g.W(prow + i);
-        for (int i = g.lane; i < SD(NN, s.nn); i += L) czs[(int64_t)i * s.dyn_cap + slot] = g.W(SD(W_Z, m.w_z) + i);
+    if (caching && !s.kd_frozen) {  // solvers.jl:374-394
         g.sync();
-        if (g.lane == 0) s.dyn_n[inst] = n + 1;
+        if (g.lane == 0) {
+            KdStore c = g_store(s, inst);
+            kd_after_solve(c, r.iters > 5 && r.converged, [&](int i) { return g.W(prow + i); }, [&](int i) { return g.W(SD(W_Z, m.w_z) + i); });
+        }
         __threadfence_block();
         g.sync();
     }

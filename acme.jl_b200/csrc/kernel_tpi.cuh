@@ -23,7 +23,8 @@
 #include "devmodel.h"
 #include "tma.cuh"
 #include "elements.cuh"
-#include "kernel_generic.cuh"  // kd_nearest
+#include "kernel_generic.cuh"  // shares elements.cuh / kdcache.cuh
+#include "kdcache_warp.cuh"    // warp-cooperative tree rebuild
 
 namespace acme {
 
@@ -305,77 +306,159 @@ __device__ __forceinline__ bool tpi_simple_solve(const M& m, const double (&Cn)[
     return converged;
 }
 
-// ---- dynamic per-instance solution cache (CachingSolver, solvers.jl:319-396), SoA layout
-// ps[(idx*NP + d)*ld + inst], zs[(idx*NN + i)*ld + inst]; entry 0 is the initial (0, init_z).
-// The nearest stored point is found by scanning all entries (the reference uses a k-d tree plus a
-// linear scan of the newest entries: the same exact nearest neighbour up to distance ties).
+// ---- the CachingSolver's solution store (solvers.jl:319-396; kdcache.cuh: the reference's k-d tree on the device).
+// The searches, the stores and the tree rebuilds are out-of-line: a thread whose store holds nothing but the initial
+// solution (0, init_z) -- every instance of config 2 for most of its run -- decides in registers and touches no memory.
 template <class C>
-__device__ __forceinline__ int tpi_cache_nearest(const DevSub& c, int64_t inst, int64_t ld,
-                                                 const double (&p)[dim1(C::NP)], const double (&lp)[dim1(C::NP)],
-                                                 int& n_out) {
-    const int n = c.dyn_n[inst];  // solutions stored so far; the ring buffer holds the newest dyn_cap of them
-    n_out = n;
-    const int nvalid = n < c.dyn_cap ? n : c.dyn_cap;
-    double best = 0.0;
-    static_for<0, C::NP>([&](auto ii) {
-        constexpr int i = decltype(ii)::value;
-        const double d = p[i] - lp[i];
-        best = fma(d, d, best);
-    });
-    int cidx = -1;
-    // four entries per pass: their loads are independent and in flight together (a one-entry loop
-    // pays the L2 latency once per entry); the minimum is still taken in index order
-    constexpr int UNR = 4;
-#pragma unroll 1
-    for (int i0 = 0; i0 < nvalid; i0 += UNR) {
-        double d2[UNR];
-#pragma unroll
-        for (int k = 0; k < UNR; k++) {
-            const int idx = i0 + k < nvalid ? i0 + k : nvalid - 1;
-            double acc = 0.0;
-            static_for<0, C::NP>([&](auto ii) {
-                constexpr int i = decltype(ii)::value;
-                const double d = c.dyn_ps[((int64_t)idx * C::NP + i) * ld + inst] - p[i];
-                acc = fma(d, d, acc);
-            });
-            d2[k] = acc;
-        }
-#pragma unroll
-        for (int k = 0; k < UNR; k++)
-            if (i0 + k < nvalid && d2[k] < best) { best = d2[k]; cidx = i0 + k; }
+__device__ __forceinline__ KdStore tpi_store(const DevSub& c, int64_t inst) {
+    return KdStore::at(c.kd_base + inst * c.kd_stride, c.kd_scr ? c.kd_scr + inst * c.kd_sstride : nullptr, C::NP, C::NN, c.kd_cap);
+}
+// leaf mirror (devmodel.h): leaf `leaf` (0-based), dimension d of this instance
+template <class C>
+__device__ __forceinline__ double* tpi_mir(const DevSub& c, int64_t inst, int leaf, int d) {
+    return c.kd_mir + ((int64_t)leaf * C::NP + d) * c.kd_mld + (c.kd_mshared ? 0 : inst);
+}
+// after a (re)build by one thread: the tree's points in leaf order
+template <class C>
+__device__ inline void tpi_mirror_fill(const DevSub& cache, const KdStore& c, int64_t inst) {
+    if (!cache.kd_mir || cache.kd_mshared) return;
+    const int n = c.hdr[KD_H_TREEN];
+    for (int leaf = 0; leaf < n; leaf++) {
+        const int col = c.psidx(leaf + 1);
+        for (int d = 0; d < C::NP; d++) *tpi_mir<C>(cache, inst, leaf, d) = c.P(d, col);
     }
-    return cidx;
 }
-#ifndef ACME_TPI_CACHE_REG
-#define ACME_TPI_CACHE_REG 0  // experiment (off: unmeasured): the stored-solution count lives in a register for the whole
-                              // call and a cache that still holds only its initial entry (0, init_z) is searched without
-                              // touching memory -- config 2's common case pays two dependent loads per sample for it
-#endif
-#if ACME_TPI_CACHE_REG
-// same result as tpi_cache_nearest for a known count n: with n == 1 the only entry is slot 0 = (p = 0, init_z)
-// (written at initialisation, overwritten only when the ring wraps), whose squared distance is |p|^2
+// after a store into column `col`: a spare (zero) column that the tree holds as a leaf has become a real point
+// (kdtree.jl:37 lets spare columns into the tree; the reference's leaf then sees the new point through tree.ps)
 template <class C>
-__device__ __forceinline__ int tpi_cache_nearest_reg(const DevSub& c, int64_t inst, int64_t ld,
-                                                     const double (&p)[dim1(C::NP)], const double (&lp)[dim1(C::NP)], int n) {
-    double best = 0.0, d0 = 0.0;
+__device__ inline void tpi_mirror_fix(const DevSub& cache, const KdStore& c, int64_t inst, int col) {
+    if (!cache.kd_mir || cache.kd_mshared || col <= 0) return;
+    const int n = c.hdr[KD_H_TREEN];
+    for (int leaf = 0; leaf < n; leaf++)
+        if (c.psidx(leaf + 1) == col)
+            for (int d = 0; d < C::NP; d++) *tpi_mir<C>(cache, inst, leaf, d) = c.P(d, col);
+}
+
+// register copy of what the hot path needs to know about the store
+struct TpiKd {
+    int newc;   // new_count: > 0 means every solve counts down to the next rebuild (solvers.jl:387-389)
+    bool triv;  // learning store holding only column 1 = (0, init_z), tree of one leaf, nothing new
+    bool on;    // the model has a store at all
+    bool due;   // the tree is due for a rebuild (solvers.jl:390): done by the whole warp at the end of the sample
+    int treen;  // points in the current tree
+    int num;    // stored solutions
+    int limit;  // new_count_limit: counted down in this register while new_count > 0 (solvers.jl:387-389), written back to
+                // the store's header before anything else reads it (tpi_kd_flush)
+};
+// the register copy of new_count_limit back into the store's header
+template <class C>
+__device__ __forceinline__ void tpi_kd_flush(const DevSub& c, int64_t inst, const TpiKd& kd) {
+    if (kd.on && !c.kd_frozen) reinterpret_cast<int*>(c.kd_base + inst * c.kd_stride)[KD_H_LIMIT] = kd.limit;
+}
+template <class C>
+__device__ __forceinline__ TpiKd tpi_kd_state(const DevSub& c, int64_t inst) {
+    TpiKd k{0, false, false, false, 0, 0, 0};
+    if (c.kd_cap > 0) {
+        const int* h = reinterpret_cast<const int*>(c.kd_base + inst * c.kd_stride);
+        k.on = true;
+        k.newc = h[KD_H_NEW];
+        k.treen = h[KD_H_TREEN];
+        k.num = h[KD_H_NUM];
+        k.limit = h[KD_H_LIMIT];
+        k.triv = !c.kd_frozen && h[KD_H_NUM] == 1 && h[KD_H_NEW] == 0 && h[KD_H_TREEN] == 1;
+    }
+    return k;
+}
+template <class C>
+__device__ __noinline__ int tpi_kd_lookup(const DevSub* cache, int64_t inst, const double* p, double best) {
+    const KdStore c = tpi_store<C>(*cache, inst);
+    int ovf = 0;
+    const int idx = kd_lookup(c, [&](int i) { return p[i]; }, best, &ovf);
+    if (ovf) c.hdr[KD_H_FLAGS] |= KD_F_HEAP_OVERFLOW;
+    return idx;
+}
+// solvers.jl:374-389; returns whether the tree is due for a rebuild
+template <class C>
+__device__ __noinline__ bool tpi_kd_after(const DevSub* cache, int64_t inst, const double* p, const double* z, int store) {
+    KdStore c = tpi_store<C>(*cache, inst);
+    int stored = 0;
+    const bool due = kd_store_step(c, store != 0, [&](int i) { return p[i]; }, [&](int i) { return z[i]; }, &stored);
+    if (stored) tpi_mirror_fix<C>(*cache, c, inst, stored);
+    return due;
+}
+// squared distance, accumulated unfused like the reference's loops (solvers.jl:349-352)
+// indnearest (kdtree.jl:192-234) written out for a tree of one or two leaves and nothing new in the store -- what an
+// instance of an easy circuit holds once it has stored its first solution (config 2: a thread that calls the general
+// search every sample holds its whole warp back, and the kernel ends with its slowest warp).  Same decisions in the
+// same order as the general search: near leaf first, the far leaf only if its bound is below the best distance both
+// when it is enqueued and after the near leaf was seen.
+template <class C>
+__device__ __forceinline__ int tpi_kd_small(const DevSub& cache, int64_t inst, const double (&p)[dim1(C::NP)], double best, int treen) {
+    const double* const cst = cache.kd_base + inst * cache.kd_stride;
+    const KdNode* const nd = reinterpret_cast<const KdNode*>(cst + KD_HDR_INTS / 2);
+    const double* const cols = cst + KD_HDR_INTS / 2 + 2 * (int64_t)cache.kd_cap;
+    const int cap = cache.kd_cap;
+    auto dist = [&](int col) {
+        const double* const pc = cols + (int64_t)((col <= cap ? col : 1) - 1) * (C::NP + C::NN);
+        double acc = 0.0;
+        static_for<0, C::NP>([&](auto ii) {
+            constexpr int i = decltype(ii)::value;
+            const double d = p[i] - (col <= cap ? pc[i] : 0.0);
+            acc = __dadd_rn(acc, __dmul_rn(d, d));
+        });
+        return acc;
+    };
+    int bidx = 0;
+    if (treen <= 1) {
+        if (treen == 1) {
+            const int col = (int)((unsigned)nd[0].ti >> 8);
+            if (dist(col) < best) bidx = col;
+        }
+        return bidx;
+    }
+    const KdNode n0 = nd[0], n1 = nd[1];
+    const int dim = (n0.ti & 0xff) - 1;
+    double pd = p[0];
+    static_for<1, C::NP>([&](auto ii) { pd = dim == decltype(ii)::value ? p[decltype(ii)::value] : pd; });
+    const double dcut = pd - n0.cut_val;
+    const double far_norm = __dmul_rn(dcut, dcut);  // (0 - 0*0) + dcut^2
+    bool far = far_norm < best;                      // enqueue!  (kdtree.jl:207-210)
+    const bool left = pd <= n0.cut_val;
+    const int cnear = (int)((unsigned)(left ? n0.ti : n1.ti) >> 8), cfar = (int)((unsigned)(left ? n1.ti : n0.ti) >> 8);
+    const double dn = dist(cnear);
+    if (dn < best) { best = dn; bidx = cnear; far = far && far_norm < best; }  // update_best_dist! prunes (kdtree.jl:177-187)
+    if (far) {
+        const double df = dist(cfar);
+        if (df < best) bidx = cfar;
+    }
+    return bidx;
+}
+
+// KDTree(ps, num_ps) for the store of instance `inst`, by the whole warp (every lane calls this with the same inst)
+template <class C>
+__device__ __noinline__ void tpi_kd_rebuild(const DevSub* cache, int64_t inst, int lane) {
+    KdStore c = tpi_store<C>(*cache, inst);
+    __syncwarp();
+    const int num = c.hdr[KD_H_NUM], cap_ref = c.hdr[KD_H_CAPREF];
+    kd_build_warp(c, num, cap_ref < c.cap ? cap_ref : c.cap, cap_ref, lane);
+    if (lane == 0) kd_rebuilt(c);
+    if (cache->kd_mir && !cache->kd_mshared)  // the leaf mirror, lanes over leaves
+        for (int leaf = lane; leaf < num; leaf += 32) {
+            const int col = c.psidx(leaf + 1);
+            for (int d = 0; d < C::NP; d++) *tpi_mir<C>(*cache, inst, leaf, d) = c.P(d, col);
+        }
+    __threadfence_block();
+    __syncwarp();
+}
+template <class C>
+__device__ __forceinline__ double tpi_dist2(const double (&p)[dim1(C::NP)], const double (&q)[dim1(C::NP)]) {
+    double acc = 0.0;
     static_for<0, C::NP>([&](auto ii) {
         constexpr int i = decltype(ii)::value;
-        const double d = p[i] - lp[i];
-        best = fma(d, d, best);
-        d0 = fma(p[i], p[i], d0);
+        const double d = p[i] - q[i];
+        acc = __dadd_rn(acc, __dmul_rn(d, d));
     });
-    if (n == 1) return d0 < best ? 0 : -1;
-    int dummy;
-    return tpi_cache_nearest<C>(c, inst, ld, p, lp, dummy);
-}
-#endif
-template <class C>
-__device__ __forceinline__ void tpi_cache_append(const DevSub& c, int64_t inst, int64_t ld, int n,
-                                                 const double (&p)[dim1(C::NP)], const double (&z)[dim1(C::NN)]) {
-    const int slot = n % c.dyn_cap;  // ring buffer: the oldest entry is overwritten
-    static_for<0, C::NP>([&](auto i) { c.dyn_ps[((int64_t)slot * C::NP + decltype(i)::value) * ld + inst] = p[decltype(i)::value]; });
-    static_for<0, C::NN>([&](auto i) { c.dyn_zs[((int64_t)slot * C::NN + decltype(i)::value) * ld + inst] = z[decltype(i)::value]; });
-    c.dyn_n[inst] = n + 1;
+    return acc;
 }
 
 // everything the cold paths need, spilled to local memory on purpose
@@ -390,33 +473,28 @@ struct TpiCold {
     int used_homotopy;
 };
 
-// solve(::CachingSolver, p) against the frozen cache (solvers.jl:347-373)
+// solve(::CachingSolver, p) (solvers.jl:347-396) on the spilled state
 template <class C, class M>
 __device__ __forceinline__ bool tpi_base_solve_cold(const M& m, TpiCold<C>& k, const double (&p)[dim1(C::NP)],
                                                     const SolverCfg& sc, const DevSub& cache, int& iters) {
-    if (sc.solver == ACMEB200_SOLVER_HOMOTOPY_CACHING) {
-        double best = 0.0;
-        for (int i = 0; i < C::NP; i++) { const double d = p[i] - k.S.lp[i]; best = fma(d, d, best); }
-        double cp[dim1(C::NP)], cz[dim1(C::NN)];
-        bool take = false;
-        if (cache.cache_n > 0) {
-            const int idx = kd_nearest(cache, [&](int i) { return p[i]; }, best);
-            if (idx != 0) {
-                take = true;
-                for (int i = 0; i < C::NP; i++) cp[i] = cache.ps[(int64_t)(idx - 1) * C::NP + i];
-                for (int i = 0; i < C::NN; i++) cz[i] = cache.zs[(int64_t)(idx - 1) * C::NN + i];
-            }
+    if (sc.solver == ACMEB200_SOLVER_HOMOTOPY_CACHING && cache.kd_cap > 0) {
+        const double best = tpi_dist2<C>(p, k.S.lp);
+        KdStore c = tpi_store<C>(cache, k.inst);
+        int ovf = 0;
+        const int idx = kd_lookup(c, [&](int i) { return p[i]; }, best, &ovf);
+        if (ovf) c.hdr[KD_H_FLAGS] |= KD_F_HEAP_OVERFLOW;
+        if (idx != 0) {
+            double cp[dim1(C::NP)], cz[dim1(C::NN)];
+            for (int i = 0; i < C::NP; i++) cp[i] = c.P(i, idx);
+            for (int i = 0; i < C::NN; i++) cz[i] = c.Z(i, idx);
+            tpi_set_origin<C>(m, k.Cn, k.S, cp, cz, sc);
         }
-        if (take) tpi_set_origin<C>(m, k.Cn, k.S, cp, cz, sc);
-        if (cache.cache_n == 0 && cache.dyn_cap > 0) {
-            int n;
-            const int cidx = tpi_cache_nearest<C>(cache, k.inst, k.ld, p, k.S.lp, n);
-            const bool conv = tpi_simple_solve<C>(m, k.Cn, k.S, p, k.z, sc, iters, cidx >= 0,
-                                                  cache.dyn_ps + ((int64_t)(cidx < 0 ? 0 : cidx) * C::NP) * k.ld + k.inst,
-                                                  cache.dyn_zs + ((int64_t)(cidx < 0 ? 0 : cidx) * C::NN) * k.ld + k.inst, k.ld);
-            if (conv && iters > 5) tpi_cache_append<C>(cache, k.inst, k.ld, n, p, k.z);
-            return conv;
-        }
+        const bool conv = tpi_simple_solve<C>(m, k.Cn, k.S, p, k.z, sc, iters);
+        int stored = 0;
+        const bool rebuilt = kd_after_solve(c, conv && iters > 5, [&](int i) { return p[i]; }, [&](int i) { return k.z[i]; }, &stored);
+        if (rebuilt) tpi_mirror_fill<C>(cache, c, k.inst);
+        else if (stored) tpi_mirror_fix<C>(cache, c, k.inst, stored);
+        return conv;
     }
     return tpi_simple_solve<C>(m, k.Cn, k.S, p, k.z, sc, iters);
 }
@@ -585,38 +663,112 @@ __device__ __forceinline__ void tpi_output_update(const M& m, TpiState<C>& S, co
 template <class C, class M>
 __device__ __forceinline__ int tpi_step_hot(const M& m, const double (&Cn)[dim1(C::NC)], TpiState<C>& S,
                                             const double (&u)[dim1(C::NU)], double (&y)[dim1(C::NY)],
-                                            const SolverCfg& sc, const DevSub& cache, int64_t inst, int64_t ld
-#if ACME_TPI_CACHE_REG
-                                            , int& ncache  // stored solutions of this instance (register copy of dyn_n[inst])
-#endif
-) {
+                                            const SolverCfg& sc, const DevSub& cache, int64_t inst, TpiKd& kd) {
     constexpr int NN = C::NN, NP = C::NP;
     double zall[dim1(NN)];
     int iters = 0;
     if constexpr (NN > 0) {
         double p[dim1(NP)];
         tpi_calc_p<C>(m, S, u, p);
-        int cidx = -1, n_cache = 0;
-        const bool caching = sc.solver == ACMEB200_SOLVER_HOMOTOPY_CACHING;
+        const bool caching = sc.solver == ACMEB200_SOLVER_HOMOTOPY_CACHING && kd.on;
+        int col = 0;  // stored solution (1-based column) to re-origin at, 0: keep the origin
         if (caching) {
-            if (cache.cache_n > 0) return -1;  // frozen k-d tree: the cold path does the lookup
-#if ACME_TPI_CACHE_REG
-            if (cache.dyn_cap > 0) { n_cache = ncache; cidx = tpi_cache_nearest_reg<C>(cache, inst, ld, p, S.lp, ncache); }
-#else
-            if (cache.dyn_cap > 0) cidx = tpi_cache_nearest<C>(cache, inst, ld, p, S.lp, n_cache);
-#endif
+            const double best = tpi_dist2<C>(p, S.lp);
+            if (kd.triv) {  // the store holds only (0, init_z): its squared distance is |p|^2 -- no memory touched
+                double d0 = 0.0;
+                static_for<0, NP>([&](auto ii) { d0 = __dadd_rn(d0, __dmul_rn(p[decltype(ii)::value], p[decltype(ii)::value])); });
+                col = d0 < best ? 1 : 0;
+            } else {
+                // the new_count newest stored solutions, first minimum in index order (solvers.jl:354-363) ...
+                double bseed = best;
+                if (kd.newc > 0) {
+                    const double* const cols = cache.kd_base + inst * cache.kd_stride + KD_HDR_INTS / 2 + 2 * (int64_t)cache.kd_cap;
+#pragma unroll 1
+                    for (int i = kd.num - kd.newc + 1; i <= kd.num; i++) {
+                        const double* const pc = cols + (int64_t)(i - 1) * (NP + NN);
+                        double acc = 0.0;
+                        static_for<0, NP>([&](auto ii) {
+                            constexpr int k = decltype(ii)::value;
+                            const double d = pc[k] - p[k];
+                            acc = __dadd_rn(acc, __dmul_rn(d, d));
+                        });
+                        if (acc < bseed) { bseed = acc; col = i; }
+                    }
+                }
+                // ... then the tree, seeded with that (kdtree.jl:93-100, 192-234)
+                if (kd.treen <= 2) {
+                    const int tcol = tpi_kd_small<C>(cache, inst, p, bseed, kd.treen);
+                    col = tcol ? tcol : col;
+                } else if (cache.kd_mir) {
+                    // every leaf of the tree, several per pass (independent loads in flight together), lanes in step: the
+                    // nearest tree point, taken if it is strictly nearer than the seed (what indnearest returns)
+                    double bd = __longlong_as_double(0x7ff0000000000000ll);
+                    int bleaf = 0;
+                    bool tie = false;
+                    const int nt = kd.treen;
+                    constexpr int UNR = NP <= 2 ? 8 : 4;
+#pragma unroll 1
+                    for (int l0 = 0; l0 < nt; l0 += UNR) {
+                        double d2[UNR];
+#pragma unroll
+                        for (int k = 0; k < UNR; k++) {
+                            const int leaf = l0 + k < nt ? l0 + k : nt - 1;
+                            double acc = 0.0;
+                            static_for<0, NP>([&](auto ii) {
+                                constexpr int i = decltype(ii)::value;
+                                const double d = p[i] - *tpi_mir<C>(cache, inst, leaf, i);
+                                acc = __dadd_rn(acc, __dmul_rn(d, d));
+                            });
+                            d2[k] = acc;
+                        }
+#pragma unroll
+                        for (int k = 0; k < UNR; k++)
+                            if (l0 + k < nt) {
+                                tie = d2[k] < bd ? false : (d2[k] == bd ? true : tie);
+                                if (d2[k] < bd) { bd = d2[k]; bleaf = l0 + k; }
+                            }
+                    }
+                    if (bd < bseed) {
+                        if (!tie) {
+                            col = tpi_store<C>(cache, inst).psidx(bleaf + 1);
+                        } else {  // two leaves tie for the minimum: the order of the reference's search decides
+                            double pl[dim1(NP)];
+                            static_for<0, NP>([&](auto ii) { pl[decltype(ii)::value] = p[decltype(ii)::value]; });
+                            col = tpi_kd_lookup<C>(&cache, inst, pl, best);
+                        }
+                    }
+                } else {
+                    double pl[dim1(NP)];
+                    static_for<0, NP>([&](auto ii) { pl[decltype(ii)::value] = p[decltype(ii)::value]; });
+                    col = tpi_kd_lookup<C>(&cache, inst, pl, best);
+                }
+            }
         }
-        const int64_t e = cidx < 0 ? 0 : cidx;
-        if (!tpi_simple_solve<C>(m, Cn, S, p, zall, sc, iters, cidx >= 0, cache.dyn_ps + (e * NP) * ld + inst,
-                                 cache.dyn_zs + (e * NN) * ld + inst, ld)) {
+        const double* const cst = cache.kd_base + inst * cache.kd_stride;  // this instance's store (kdcache.cuh layout)
+        const int cap = cache.kd_cap;
+        const int64_t e = col > 0 && col <= cap ? col - 1 : 0;
+        const double* const pc = cst + KD_HDR_INTS / 2 + 2 * (int64_t)cap + e * (NP + NN);  // KdStore::col(col): p then z
+        const double* const zc = pc + NP;
+        if (caching && col > cap) return -1;  // a virtual zero column as start point (kdcache.cuh): the cold path handles it
+        const bool conv = tpi_simple_solve<C>(m, Cn, S, p, zall, sc, iters, col > 0, pc, zc, 1);
+        if (caching && !cache.kd_frozen) {  // solvers.jl:374-394
+            if (conv && iters > 5) {  // store (p, z), out of line
+                double pl[dim1(NP)], zl[dim1(NN)];
+                static_for<0, NP>([&](auto ii) { pl[decltype(ii)::value] = p[decltype(ii)::value]; });
+                static_for<0, NN>([&](auto ii) { zl[decltype(ii)::value] = zall[decltype(ii)::value]; });
+                tpi_kd_flush<C>(cache, inst, kd);
+                const bool due = tpi_kd_after<C>(&cache, inst, pl, zl, 1);
+                kd = tpi_kd_state<C>(cache, inst);
+                kd.due = due;
+            } else if (kd.newc > 0) {  // count down to the rebuild in registers
+                kd.limit -= 1;
+                if (kd.newc > kd.limit) { tpi_kd_flush<C>(cache, inst, kd); kd.due = true; }
+            }
+        }
+        if (!conv) {
             if (sc.solver != ACMEB200_SOLVER_SIMPLE) return -(iters + 1);
             return -(iters + 1) - (1 << 20);  // SimpleSolver only: no homotopy, the failure is final
         }
-#if ACME_TPI_CACHE_REG
-        if (caching && iters > 5 && cache.dyn_cap > 0) { tpi_cache_append<C>(cache, inst, ld, n_cache, p, zall); ncache = n_cache + 1; }
-#else
-        if (caching && iters > 5 && cache.dyn_cap > 0) tpi_cache_append<C>(cache, inst, ld, n_cache, p, zall);
-#endif
     }
     tpi_output_update<C>(m, S, u, zall, y);
     return iters;
@@ -732,10 +884,9 @@ __global__ void __launch_bounds__(TPI_TPB, ACME_TPI_MINB) k_tpi(const __grid_con
             static_for<0, NP>([&](auto i) { p0[decltype(i)::value] = 0.0; });
             static_for<0, NN>([&](auto i) { z0[decltype(i)::value] = a.initz[(int64_t)decltype(i)::value * a.ld + inst]; });
             tpi_set_origin<C>(m, Cn, S, p0, z0, sc);
-            if (cache.dyn_cap > 0) {  // CachingSolver ctor: the cache holds (0, init_z)  (solvers.jl:327-333)
-                static_for<0, NP>([&](auto i) { cache.dyn_ps[(int64_t)decltype(i)::value * a.ld + inst] = 0.0; });
-                static_for<0, NN>([&](auto i) { cache.dyn_zs[(int64_t)decltype(i)::value * a.ld + inst] = z0[decltype(i)::value]; });
-                cache.dyn_n[inst] = 1;
+            if (cache.kd_cap > 0 && !cache.kd_frozen) {  // CachingSolver ctor: the store holds (0, init_z)  (solvers.jl:327-333); memory zeroed by the host
+                KdStore c = tpi_store<C>(cache, inst);
+                kd_init(c, [&](int i) { return z0[i]; });
             }
         }
         store_state();
@@ -749,11 +900,9 @@ __global__ void __launch_bounds__(TPI_TPB, ACME_TPI_MINB) k_tpi(const __grid_con
     static_for<0, NN>([&](auto i) { S.lz[decltype(i)::value] = st[(int64_t)(C::S_LZ + decltype(i)::value) * a.ld]; });
     static_for<0, NN * NP>([&](auto i) { S.Mx[decltype(i)::value] = st[(int64_t)(C::S_MX + decltype(i)::value) * a.ld]; });
 
-#if ACME_TPI_CACHE_REG
-    int ncache = 0;
+    TpiKd kd{0, false, false, false, 0, 0, 0};
     if constexpr (NN > 0)
-        if (sc.solver == ACMEB200_SOLVER_HOMOTOPY_CACHING && cache.cache_n == 0 && cache.dyn_cap > 0) ncache = cache.dyn_n[inst];
-#endif
+        if (sc.solver == ACMEB200_SOLVER_HOMOTOPY_CACHING && active) kd = tpi_kd_state<C>(cache, inst);
     bool dead = !active || (a.status[inst] & ACMEB200_STATUS_NONFINITE);
     int dead_at = dead ? 0 : -1;  // sample index (this call) at which the instance halted, -1 = alive
     const bool shared_u = (a.u_stride == 0) || NU == 0;
@@ -872,44 +1021,66 @@ __global__ void __launch_bounds__(TPI_TPB, ACME_TPI_MINB) k_tpi(const __grid_con
                 tt = cnt;
             }
         } else {
+            // Every lane walks the tile in step (the trip counts are warp-uniform; halted and surplus lanes idle), so
+            // that the warp is converged wherever it has to act together: a tree rebuild of one lane's store is done by
+            // all 32 lanes (kdcache_warp.cuh).  The hot loop has no calls; it is left by the whole warp when some lane
+            // needs the cold path or a rebuild.
             int code = 0;
-            while (tt < cnt && !dead) {
-                // hot loop: no calls, no cold-path state
+            while (tt < cnt) {
     #pragma unroll 1
                 for (; tt < cnt; tt++) {
-                    double u[dim1(NU)], y[dim1(NY)];
-                    static_for<0, NU>([&](auto kk) {
-                        constexpr int q = decltype(kk)::value;
-                        u[q] = shared_u ? __ldg(a.U + (int64_t)(n0 + tt) * NU + q) : in_at(tt * NU + q);
-                    });
-#if ACME_TPI_CACHE_REG
-                    code = tpi_step_hot<C>(m, Cn, S, u, y, sc, cache, inst, a.ld, ncache);
-#else
-                    code = tpi_step_hot<C>(m, Cn, S, u, y, sc, cache, inst, a.ld);
-#endif
-                    if (code < 0) break;
-                    if (NN > 0) {
-                        if (code <= 8) hist_s[(code - 1) * 32] += 1u;
-                        else atomicAdd(&a.stats->iter_hist[(code > ACMEB200_HIST_BINS ? ACMEB200_HIST_BINS : code) - 1], 1ull),
-                             atomicAdd(&a.stats->newton_iters, (unsigned long long)code);
+                    code = 0;
+                    if (!dead) {
+                        double u[dim1(NU)], y[dim1(NY)];
+                        static_for<0, NU>([&](auto kk) {
+                            constexpr int q = decltype(kk)::value;
+                            u[q] = shared_u ? __ldg(a.U + (int64_t)(n0 + tt) * NU + q) : in_at(tt * NU + q);
+                        });
+                        code = tpi_step_hot<C>(m, Cn, S, u, y, sc, cache, inst, kd);
+                        if (code >= 0) {
+                            if (NN > 0) {
+                                if (code <= 8) hist_s[(code - 1) * 32] += 1u;
+                                else atomicAdd(&a.stats->iter_hist[(code > ACMEB200_HIST_BINS ? ACMEB200_HIST_BINS : code) - 1], 1ull),
+                                     atomicAdd(&a.stats->newton_iters, (unsigned long long)code);
+                            }
+                            static_for<0, NY>([&](auto kk) { out_at(tt * NY + decltype(kk)::value) = y[decltype(kk)::value]; });
+                        }
+                    } else {
+                        static_for<0, NY>([&](auto kk) { out_at(tt * NY + decltype(kk)::value) = NAN; });  // the reference throws (ACME.jl:692)
                     }
-                    static_for<0, NY>([&](auto kk) { out_at(tt * NY + decltype(kk)::value) = y[decltype(kk)::value]; });
+                    if (__any_sync(0xffffffffu, code < 0 || kd.due)) break;
                 }
-                if (tt < cnt) {
-                    // this lane's sample tt needs the cold path
-                    double u[dim1(NU)], y[dim1(NY)];
-                    static_for<0, NU>([&](auto kk) {
-                        constexpr int q = decltype(kk)::value;
-                        u[q] = shared_u ? __ldg(a.U + (int64_t)(n0 + tt) * NU + q) : in_at(tt * NU + q);
-                    });
-                    const int it = tpi_step_cold<C>(&m, Cn, &S, u, y, &sc, &cache, &a, inst, n0 + tt, code);
-#if ACME_TPI_CACHE_REG
-                    if constexpr (NN > 0)
-                        if (cache.dyn_cap > 0) ncache = cache.dyn_n[inst];  // the cold solve may have stored a solution
-#endif
-                    if (it < 0) { dead = true; dead_at = n0 + tt; break; }
-                    if (it >= 1 && it <= 8) hist_s[(it - 1) * 32] += 1u;
-                    static_for<0, NY>([&](auto kk) { out_at(tt * NY + decltype(kk)::value) = y[decltype(kk)::value]; });
+                if (tt < cnt) {  // warp-uniform
+                    if (code < 0) {
+                        // this lane's sample tt needs the cold path
+                        double u[dim1(NU)], y[dim1(NY)];
+                        static_for<0, NU>([&](auto kk) {
+                            constexpr int q = decltype(kk)::value;
+                            u[q] = shared_u ? __ldg(a.U + (int64_t)(n0 + tt) * NU + q) : in_at(tt * NU + q);
+                        });
+                        if constexpr (NN > 0) tpi_kd_flush<C>(cache, inst, kd);
+                        const int it = tpi_step_cold<C>(&m, Cn, &S, u, y, &sc, &cache, &a, inst, n0 + tt, code);
+                        if constexpr (NN > 0)
+                            if (kd.on) kd = tpi_kd_state<C>(cache, inst);  // the cold solves may have stored solutions / rebuilt the tree
+                        if (it < 0) {
+                            dead = true; dead_at = n0 + tt;
+                            static_for<0, NY>([&](auto kk) { out_at(tt * NY + decltype(kk)::value) = NAN; });
+                        } else {
+                            if (it >= 1 && it <= 8) hist_s[(it - 1) * 32] += 1u;
+                            static_for<0, NY>([&](auto kk) { out_at(tt * NY + decltype(kk)::value) = y[decltype(kk)::value]; });
+                        }
+                    }
+                    if constexpr (NN > 0) {
+                        // KDTree(ps, num_ps) (solvers.jl:390) for every lane whose store is due, one store at a time, all lanes
+                        unsigned due = __ballot_sync(0xffffffffu, kd.due);
+                        while (due) {
+                            const int src = __ffs(due) - 1;
+                            due &= due - 1;
+                            const int64_t isrc = __shfl_sync(0xffffffffu, (long long)inst, src);
+                            tpi_kd_rebuild<C>(&cache, isrc, lane);
+                            if (lane == src) { kd = tpi_kd_state<C>(cache, inst); kd.due = false; }
+                        }
+                    }
                     tt++;
                 }
             }
@@ -948,6 +1119,8 @@ __global__ void __launch_bounds__(TPI_TPB, ACME_TPI_MINB) k_tpi(const __grid_con
     __syncwarp();
 
     if (active) store_state();
+    if constexpr (NN > 0)
+        if (active) tpi_kd_flush<C>(cache, inst, kd);
     // warp-reduce the counters, one set of atomics per warp
     const unsigned full_mask = 0xffffffffu;
     unsigned hsum[8];

@@ -16,10 +16,13 @@ using RowsSuperoverBaked = CoopStatic<11, 1, 1, 7, 14, 5, 5, 11>;
 
 int rows_shape(const DevModel& dm) { return RowsSuperover::matches(dm) ? 1 : (RowsSuperoverBaked::matches(dm) ? 2 : 0); }
 
+int64_t rows_mirror_doubles(int shape, int cap) { return shape == 2 ? RowsMir<RowsSuperoverBaked>::doubles(cap) : RowsMir<RowsSuperover>::doubles(cap); }
+
 template <class S, int WARPS, bool PERINST>
 static cudaError_t launch_rows(const acmeb200_model* m, const RunArgs& a, cudaStream_t stream) {
     const size_t smem = rows_smem_bytes<S>(WARPS, m->dm.nconst, PERINST);
-    static bool attr_set = false;
+    static bool attr_set_dev[ACME_MAX_DEVICES] = {};  // function attributes are per device: one process may drive several
+    bool& attr_set = attr_set_dev[m->device & (ACME_MAX_DEVICES - 1)];
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(k_rows<S, WARPS, PERINST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return e;

@@ -91,8 +91,10 @@ static cudaError_t launch_tpi(const acmeb200_model* m, const RunArgs& a, cudaStr
     }
     const int64_t blocks = (a.ninst + TPI_TPB - 1) / TPI_TPB;
     const size_t smem = tpi_smem_bytes<C>();
+    const int dev = m->device & (ACME_MAX_DEVICES - 1);  // function attributes are per device: one process may drive several
     if (smem > 48 * 1024) {  // long tiles: opt in to the large dynamic shared memory carve-out
-        static bool attr_set = false;
+        static bool attr_set_dev[ACME_MAX_DEVICES] = {};
+        bool& attr_set = attr_set_dev[dev];
         if (!attr_set) {
             for (auto* k : {k_tpi<C, true, false>, k_tpi<C, false, false>, k_tpi<C, true, true>, k_tpi<C, false, true>}) {
                 const cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -106,12 +108,12 @@ static cudaError_t launch_tpi(const acmeb200_model* m, const RunArgs& a, cudaStr
         // unified array stays L1.  The learning cache's stored points are scanned from global memory
         // every sample (config 5: 124 KB per SM); with the default maximum carve-out (200 KB) only 39 % of
         // those loads hit L1 and the kernel waits on L2 latency (profiles/k_tpi_r1.md).
-        static int last_pct = -1, sms = 0, max_smem = 0;
+        static int last_pct_dev[ACME_MAX_DEVICES], sms_dev[ACME_MAX_DEVICES] = {}, max_smem_dev[ACME_MAX_DEVICES] = {};
+        int &last_pct = last_pct_dev[dev], &sms = sms_dev[dev], &max_smem = max_smem_dev[dev];
         if (!sms) {
-            int dev = 0;
-            cudaGetDevice(&dev);
-            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-            cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, m->device);
+            cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerMultiprocessor, m->device);
+            last_pct = -1;
         }
         const int64_t resident = std::min<int64_t>(ACME_TPI_MINB, (blocks + sms - 1) / std::max(sms, 1));
         const int64_t need = resident * (int64_t)(smem + 1024);

@@ -100,6 +100,40 @@ class BatchRunner:
         check(lib().acmeb200_get_cache_sizes(self._h, sub, n.ctypes.data_as(C.c_void_p), C.byref(cap)))
         return n, int(cap.value)
 
+    def cache_info(self, sub: int = 0) -> dict:
+        """the CachingSolver bookkeeping per instance (solvers.jl:321-325): num_ps, new_count, new_count_limit, the
+        capacity the reference's doubling arrays would have, points in the current tree, flags"""
+        a = np.zeros((self.batch, 8), dtype=np.int32)
+        check(lib().acmeb200_get_cache_info(self._h, sub, a.ctypes.data_as(C.c_void_p)))
+        return dict(num_ps=a[:, 0], new_count=a[:, 1], new_count_limit=a[:, 2], cap_ref=a[:, 3], tree_n=a[:, 4], flags=a[:, 5])
+
+    def solver_state(self) -> bytes:
+        """everything mutable -- x, extrapolation origins, learnt solution stores, status, statistics -- as one blob
+        (``deepcopy(model)`` minus the matrices; acmeb200_get_solver_state)"""
+        n = int(lib().acmeb200_solver_state_size(self._h))
+        if n < 0:
+            check(n)
+        buf = C.create_string_buffer(n)
+        check(lib().acmeb200_get_solver_state(self._h, buf, n))
+        return buf.raw
+
+    def set_solver_state(self, blob: bytes):
+        """restore a blob of :meth:`solver_state` taken from a runner of the same model, batch and kernel"""
+        check(lib().acmeb200_set_solver_state(self._h, blob, len(blob)))
+
+    def extrapolation_origin(self, sub: int = 0):
+        """``get_extrapolation_origin(solver)`` (solvers.jl:199) of every instance: (p (np, B), z (nn, B))"""
+        s = self.model.subs[sub]
+        p = np.zeros((s.np_, self.batch), order="F"); z = np.zeros((s.nn, self.batch), order="F")
+        check(lib().acmeb200_get_extrapolation_origin(self._h, sub, p.ctypes.data_as(C.c_void_p), z.ctypes.data_as(C.c_void_p)))
+        return p, z
+
+    @property
+    def device(self) -> int:
+        d = C.c_int32(-1)
+        check(lib().acmeb200_get_device(self._h, C.byref(d)))
+        return int(d.value)
+
     def status(self):
         st = np.zeros(self.batch, dtype=np.uint32)
         ff = np.zeros(self.batch, dtype=np.int64)
@@ -450,6 +484,79 @@ class BatchRunner:
             raise RuntimeError(ERR_NONFINITE)
         if (st & _abi.STATUS_NOT_CONVERGED).any():
             warnings.warn(WARN_NOT_CONVERGED)
+
+
+class _ShardView(BatchRunner):
+    """one shard of a :class:`MultiGpuRunner`: the handle is owned by the multi object"""
+
+    def __init__(self, model, handle, first, count, batch_total):
+        self.model, self._h, self.first, self.batch, self.batch_total = model, handle, first, count, batch_total
+        self._params = self._overrides = None
+        self._has_overrides = False
+
+    def close(self):
+        self._h = None
+
+
+class MultiGpuRunner:
+    """The batch over all the GPUs of the box from ONE host process through the C ABI alone (acmeb200_multi_*): contiguous
+    instance shards, one device model per GPU, no collective; ``run`` takes host arrays for the whole batch and drives
+    every shard's host-buffer pipeline from its own host thread.  (``distributed.ShardedBatchRunner`` is the
+    one-process-per-GPU variant for device-resident streams.)"""
+
+    def __init__(self, model, batch: int, n_gpus: int = 0, **desc_kw):
+        self.model, self.batch = model, batch
+        self._holder = make_desc(model, batch, **desc_kw)
+        h = C.c_void_p()
+        check(lib().acmeb200_multi_create(C.byref(self._holder.desc), batch, n_gpus, C.byref(h)))
+        self._h = h
+        self.shards = []
+        for g in range(lib().acmeb200_multi_shards(self._h)):
+            first, count = C.c_int64(0), C.c_int64(0)
+            mh = lib().acmeb200_multi_model(self._h, g, C.byref(first), C.byref(count))
+            self.shards.append(_ShardView(model, C.c_void_p(mh), int(first.value), int(count.value), batch))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            for s in self.shards:
+                s.close()
+            lib().acmeb200_multi_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def run(self, u, y=None, check_status: bool = True):
+        """u: (nu, N) shared or (nu, N, B) Fortran-ordered host array; returns y (ny, N, B)"""
+        m, B = self.model, self.batch
+        u = np.asarray(u, dtype=np.float64)
+        if u.ndim not in (2, 3) or u.shape[0] != m.nu:
+            raise DimensionMismatch(f"input matrix has {u.shape[0]} rows, but model has {m.nu} inputs")
+        N = u.shape[1]
+        if u.ndim == 3 and u.shape[2] != B:
+            raise DimensionMismatch(f"input has {u.shape[2]} instances, runner has {B}")
+        ubuf = np.ascontiguousarray(u.ravel(order="F")) if u.size else np.zeros(1)
+        if y is None:
+            y = np.empty((m.ny, N, B), order="F")
+        elif y.shape != (m.ny, N, B) or not y.flags.f_contiguous or y.dtype != np.float64:
+            raise DimensionMismatch(f"output must be a Fortran-contiguous float64 array of shape {(m.ny, N, B)}")
+        ybuf = y.reshape(-1, order="F") if y.size else np.empty(1)
+        check(lib().acmeb200_multi_run(self._h, ubuf.ctypes.data_as(C.c_void_p), m.nu * N if u.ndim == 3 else 0,
+                                       ybuf.ctypes.data_as(C.c_void_p), m.ny * N, N, 0))
+        if check_status:
+            for s in self.shards:
+                s.raise_for_status()
+        return y
+
+    def stats(self) -> dict:
+        tot = None
+        for s in self.shards:
+            d = s.stats()
+            tot = d if tot is None else {k: ([a + b for a, b in zip(tot[k], d[k])] if isinstance(d[k], list) else tot[k] + d[k]) for k in d}
+        return tot
 
 
 class ModelRunner(BatchRunner):

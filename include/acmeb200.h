@@ -67,11 +67,14 @@ extern "C" {
 #define ACMEB200_ELEM_TEST_QUAD 100
 
 /* solver selection; the reference default is HOMOTOPY_CACHING
- * (src/ACME.jl:150).  With HOMOTOPY_CACHING the device keeps a learning
- * per-instance solution cache (insertion when a solve needed > 5 iterations,
- * src/solvers.jl:374-386; nearest-start lookup, src/solvers.jl:347-371) with a
- * fixed capacity; alternatively a frozen, host-built k-d tree can be supplied
- * per sub-problem (acmeb200_cache), which is then used read-only instead. */
+ * (src/ACME.jl:150).  With HOMOTOPY_CACHING every instance keeps the reference's
+ * learning solution cache on the device: insertion when a solve needed > 5
+ * iterations (src/solvers.jl:374-386), the k-d tree of src/kdtree.jl rebuilt on the
+ * reference's schedule (src/solvers.jl:387-394), start point = nearest of {origin,
+ * newest entries, tree} (src/solvers.jl:347-371) -- the same start points, hence the
+ * same iteration counts, as the reference; the physical capacity is bounded
+ * (cache_capacity).  Alternatively a frozen, host-built k-d tree can be supplied per
+ * sub-problem (acmeb200_cache), which is then used read-only by all instances. */
 #define ACMEB200_SOLVER_SIMPLE            0 /* SimpleSolver                          */
 #define ACMEB200_SOLVER_HOMOTOPY          1 /* HomotopySolver{SimpleSolver}          */
 #define ACMEB200_SOLVER_HOMOTOPY_CACHING  2 /* HomotopySolver{CachingSolver{Simple}} */
@@ -166,6 +169,13 @@ typedef struct acmeb200_stats {
 
 typedef struct acmeb200_model acmeb200_model; /* opaque; owns all device memory */
 
+/* Devices: a model lives on the CUDA device that is current when it is created; hosts that do not link the CUDA
+ * runtime themselves choose it here.  Several models on several devices may be driven by one process (one host thread
+ * per model at a time). */
+int acmeb200_device_count(int32_t *count_out);
+int acmeb200_set_device(int32_t device);
+int acmeb200_get_device(acmeb200_model *m, int32_t *device_out);
+
 /* Create the device-resident model for instances [first_instance,
  * first_instance + n_instances) of the descriptor, on the current CUDA device.
  * Descriptor arrays are host pointers and are copied; nothing is retained.
@@ -186,20 +196,58 @@ void acmeb200_model_destroy(acmeb200_model *m);
 int acmeb200_run(acmeb200_model *m, const double *U, int64_t u_stride, double *Y,
                  int64_t y_stride, int64_t n_samples, uint32_t flags, void *stream);
 
+/* The batch over ALL the GPUs of the box from one call ("library drives all GPUs itself"):
+ * instances never interact, so the n_instances of the descriptor are split into contiguous shards
+ * [g*B/G, (g+1)*B/G) (the first B mod G shards one longer), one acmeb200_model per device.  acmeb200_multi_run is
+ * acmeb200_run with HOST streams for the whole batch: every shard runs its own host-buffer pipeline from its own host
+ * thread, concurrently; it returns when all of Y is complete.  n_gpus <= 0: every visible device.  Per-shard state
+ * and statistics are reached through acmeb200_multi_model (shard g, its first instance and instance count). */
+typedef struct acmeb200_multi acmeb200_multi;
+int acmeb200_multi_create(const acmeb200_model_desc *desc, int64_t n_instances, int32_t n_gpus, acmeb200_multi **out);
+void acmeb200_multi_destroy(acmeb200_multi *mm);
+int acmeb200_multi_shards(const acmeb200_multi *mm);
+acmeb200_model *acmeb200_multi_model(acmeb200_multi *mm, int32_t shard, int64_t *first_out, int64_t *count_out);
+int acmeb200_multi_run(acmeb200_multi *mm, const double *U, int64_t u_stride, double *Y, int64_t y_stride,
+                       int64_t n_samples, uint32_t flags);
+
 /* model.x (nx x B, column-major) */
 int acmeb200_get_state(acmeb200_model *m, double *x_host);
 int acmeb200_set_state(acmeb200_model *m, const double *x_host, int64_t stride);
 /* x = 0 and extrapolation origins back to (0, init_z); clears stats/status */
 int acmeb200_reset(acmeb200_model *m);
 
+/* The complete mutable state of the model -- what deepcopy(model) of the reference carries besides the matrices:
+ * x (src/ACME.jl:145), every solver's extrapolation origin last_p / last_z / last_LU / last_Jp
+ * (src/solvers.jl:155-158), the CachingSolver's stored solutions, tree and counters (src/solvers.jl:321-325),
+ * status words, statistics and the running sample count -- as one opaque blob.  A blob restores into a model created
+ * from the same descriptor and instance count with the same kernel selected (on any device, in any process):
+ * create -> run(chunk 1) -> get -> destroy -> create -> set -> run(chunk 2) equals one run, bit for bit.
+ * acmeb200_solver_state_size returns the bytes needed (negative: error). */
+int64_t acmeb200_solver_state_size(acmeb200_model *m);
+int acmeb200_get_solver_state(acmeb200_model *m, void *buf, int64_t bytes);
+int acmeb200_set_solver_state(acmeb200_model *m, const void *buf, int64_t bytes);
+/* get_extrapolation_origin(solver) (src/solvers.jl:199): origin (p, z) of sub-problem `sub` for every instance,
+ * p_host np x B and z_host nn x B column-major; either may be NULL */
+int acmeb200_get_extrapolation_origin(acmeb200_model *m, int32_t sub, double *p_host, double *z_host);
+
 /* status words (one uint32 per instance) and the first failing sample index
  * (int64 per instance, -1 if none); either pointer may be NULL */
 int acmeb200_get_status(acmeb200_model *m, uint32_t *status_host, int64_t *first_fail_host);
 int acmeb200_get_stats(acmeb200_model *m, acmeb200_stats *out);
-/* number of solutions the learning CachingSolver of sub-problem `sub` holds per instance
- * (num_ps of /root/reference/src/solvers.jl:321-323; 0 when the model has no dynamic cache);
- * *capacity_out (may be NULL) receives the fixed per-instance capacity */
+/* number of solutions the CachingSolver of sub-problem `sub` holds per instance
+ * (num_ps of /root/reference/src/solvers.jl:321-323; 0 when the model has no store);
+ * *capacity_out (may be NULL) receives the physical per-instance capacity: the reference's
+ * arrays double for ever (solvers.jl:376-382), the device store stops accepting solutions
+ * when it is full (flag ACMEB200_CACHE_FULL of acmeb200_get_cache_info) */
 int acmeb200_get_cache_sizes(acmeb200_model *m, int32_t sub, int32_t *sizes_host, int32_t *capacity_out);
+
+/* the CachingSolver bookkeeping of sub-problem `sub`, 8 int32 per instance: num_ps, new_count,
+ * new_count_limit (solvers.jl:321-325), the capacity the reference's doubling arrays would have,
+ * the number of points in the current tree, flags (ACMEB200_CACHE_*), 2 reserved */
+#define ACMEB200_CACHE_FROZEN        1 /* host-built store of the descriptor, read-only          */
+#define ACMEB200_CACHE_FULL          2 /* a solution could not be stored: capacity reached       */
+#define ACMEB200_CACHE_HEAP_OVERFLOW 4 /* a search dropped an alternative (never seen in tests)  */
+int acmeb200_get_cache_info(acmeb200_model *m, int32_t sub, int32_t *info_host);
 
 /* kernel selection: 0 = automatic, 1 = force the generic thread-per-instance
  * kernel, 2 = force the cooperative (lanes-per-instance) kernel, 3 = force the
@@ -208,6 +256,22 @@ int acmeb200_set_kernel(acmeb200_model *m, int32_t mode);
 const char *acmeb200_kernel_name(const acmeb200_model *m);
 /* number of kernels launched by this model since creation */
 int64_t acmeb200_launch_count(const acmeb200_model *m);
+
+/* KDTree(p, Np) (src/kdtree.jl:11-73), host side: builds the tree arrays of an acmeb200_cache over the first
+ * `n_points` of `ps` (np x n_columns, column-major) exactly as the reference's constructor does -- including its
+ * sort over ALL n_columns columns (kdtree.jl:37).  cut_dim / cut_val receive n_points-1 entries, ps_idx n_points
+ * (1-based, like the reference).  This is the same code the device runs when a learning CachingSolver rebuilds its
+ * tree (solvers.jl:390); a host that has collected solutions (ps, zs) uses it to freeze them into a cache. */
+int acmeb200_kdtree_build(int32_t np, int32_t n_columns, int32_t n_points, const double *ps,
+                          int32_t *cut_dim, double *cut_val, int32_t *ps_idx);
+/* indnearest(tree, p, alts) (src/kdtree.jl:192-234) with alts initialised by init!(alts, best_dist, best_pidx):
+ * the 1-based column of the tree point nearest to each of the n_queries columns of `queries` (np x n_queries) that
+ * is strictly nearer than best_dist (INFINITY: plain nearest neighbour), else best_pidx.  Host side, same code as
+ * the device search. */
+int acmeb200_kdtree_indnearest(int32_t np, int32_t n_columns, int32_t n_points, const int32_t *cut_dim,
+                               const double *cut_val, const int32_t *ps_idx, const double *ps,
+                               int32_t n_queries, const double *queries, double best_dist, int32_t best_pidx,
+                               int32_t *nearest_out);
 
 /* diagnostic: measured FP64 FMA throughput of the current device in TFLOP/s
  * (2 flops per DFMA), the denominator of the FP64-pipe roofline in bench.py */

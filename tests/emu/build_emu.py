@@ -21,19 +21,21 @@ def stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False) -> str:
-    if not force and not stale():
+def build(force: bool = False, defines=(), out: str = OUT) -> str:
+    """`defines` (e.g. ["ACME_ROWS_SCAN_MAX=4"]) builds a variant library under another name: tests use it to push
+    small cases through code paths that the product only takes at large sizes"""
+    if not force and not defines and not stale():
         return OUT
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
     fma = ["-mfma"] if "fma" in open("/proc/cpuinfo").read() else []
     cmd = ["g++", "-std=c++17", "-O1", "-g", "-ffp-contract=off", "-fPIC", "-shared", "-w"] + fma + \
-          ["-I", HERE, "-I", CSRC, "-o", OUT]
+          [f"-D{d}" for d in defines] + ["-I", HERE, "-I", CSRC, "-o", out]
     for s in SOURCES:
         cmd += ["-x", "c++", s]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("emulation build failed:\n" + (res.stdout + res.stderr)[-6000:])
-    return OUT
+    return out
 
 
 if __name__ == "__main__":

@@ -131,6 +131,8 @@ inline int __any_sync(unsigned m, int pred) { return emu_reduce(m, pred ? 1u : 0
 // ------------------------------------------------------------------ device intrinsics
 inline int __double2hiint(double v) { int64_t b; memcpy(&b, &v, 8); return (int)(b >> 32); }
 inline int __double2loint(double v) { int64_t b; memcpy(&b, &v, 8); return (int)(b & 0xffffffff); }
+inline unsigned __float_as_uint(float v) { unsigned b; memcpy(&b, &v, 4); return b; }
+inline float __uint_as_float(unsigned b) { float v; memcpy(&v, &b, 4); return v; }
 inline double __hiloint2double(int hi, int lo) { const uint64_t b = ((uint64_t)(uint32_t)hi << 32) | (uint32_t)lo; double v; memcpy(&v, &b, 8); return v; }
 inline double __longlong_as_double(long long b) { double v; memcpy(&v, &b, 8); return v; }
 inline long long __double_as_longlong(double v) { long long b; memcpy(&b, &v, 8); return b; }

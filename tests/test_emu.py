@@ -136,8 +136,8 @@ def test_gpu_parity_suite_subset_under_emulation(emu_lib):
     runtests.jl (K3-K9), frozen k-d tree caches, batched steady state, unaligned/odd streams (the synchronous
     tile path), per-instance matrices of a non-linear model, size checks.  (The long-running ones -- full
     waveforms on the lane-parallel kernels -- stay GPU-only.)"""
-    sel = ("K4 or K5 or K6 or K7 or K8 or K9 or empty_circuits or io_size or frozen_cache or steadystate_on_device or "
-           "run_bang or odd_lengths or per_instance_matrices_nonlinear or (K3 and not coop) or K12 or K13")
+    sel = ("K4 or K5 or K6 or K7 or K8 or K9 or empty_circuits or io_size or frozen_cache_lookup or steadystate_on_device or "
+           "run_bang or odd_lengths or per_instance_matrices_nonlinear or (K3 and not coop) or K12 or K13 or (solver_state and generic)")
     env = dict(os.environ, ACMEB200_LIB=emu_lib)
     res = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_parity.py"), "-m", "gpu", "-q", "-x",
                           "-p", "no:cacheprovider", "-k", sel], env=env, capture_output=True, text=True, timeout=900, cwd=ROOT)
