@@ -914,6 +914,29 @@ extern "C" int acmeb200_kdtree_indnearest(int32_t np, int32_t n_columns, int32_t
     return ACMEB200_OK;
 }
 
+// ------------------------------------------------------------------ device exp (diagnostic)
+__global__ void __launch_bounds__(256) k_diag_exp(const double* x, double* out, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+#ifdef ACME_HOST_EMU
+    if (i < n) out[i] = exp(x[i]);  // the host emulation has no device exp: libm's
+#else
+    if (i < n) out[i] = acme_exp(x[i], ACME_EXPC);
+#endif
+}
+extern "C" int acmeb200_diag_exp(const double* x_host, double* out_host, int64_t n) {
+    if (!x_host || !out_host || n < 0) return fail(ACMEB200_EINVAL, "bad argument");
+    if (n == 0) return ACMEB200_OK;
+    double *dx = nullptr, *dy = nullptr;
+    CUDA_TRY(cudaMalloc(&dx, sizeof(double) * (size_t)n));
+    CUDA_TRY(cudaMalloc(&dy, sizeof(double) * (size_t)n));
+    CUDA_TRY(cudaMemcpy(dx, x_host, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice));
+    ACME_LAUNCH(k_diag_exp, (unsigned)((n + 255) / 256), 256, 0, (cudaStream_t) nullptr, dx, dy, n);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpy(out_host, dy, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost));
+    cudaFree(dx); cudaFree(dy);
+    return ACMEB200_OK;
+}
+
 // ------------------------------------------------------------------ FP64 pipe peak (diagnostic)
 __global__ void __launch_bounds__(256) k_dfma_peak(double* out, int iters, double a, double b) {
     double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;

@@ -376,7 +376,7 @@ template <class PF, class ZF>
 KD_HD bool kd_after_solve(KdStore& c, bool store, PF p, ZF z, int* stored_col = nullptr) {
     if (!kd_store_step(c, store, p, z, stored_col)) return false;
     const int cap_ref = c.hdr[KD_H_CAPREF];
-    kd_build(c, c.hdr[KD_H_NUM], cap_ref < c.cap ? cap_ref : c.cap, cap_ref);
+    kd_build(c, c.hdr[KD_H_NUM], c.hdr[KD_H_NUM], cap_ref);  // spare columns, physical or not, are zeros: the virtual ones of kd_build
     kd_rebuilt(c);
     return true;
 }

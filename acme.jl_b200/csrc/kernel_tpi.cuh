@@ -440,7 +440,7 @@ __device__ __noinline__ void tpi_kd_rebuild(const DevSub* cache, int64_t inst, i
     KdStore c = tpi_store<C>(*cache, inst);
     __syncwarp();
     const int num = c.hdr[KD_H_NUM], cap_ref = c.hdr[KD_H_CAPREF];
-    kd_build_warp(c, num, cap_ref < c.cap ? cap_ref : c.cap, cap_ref, lane);
+    kd_build_warp(c, num, num, cap_ref, lane);  // spare columns, physical or not, are zeros: the virtual ones of kd_build
     if (lane == 0) kd_rebuilt(c);
     if (cache->kd_mir && !cache->kd_mshared)  // the leaf mirror, lanes over leaves
         for (int leaf = lane; leaf < num; leaf += 32) {

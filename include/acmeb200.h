@@ -277,6 +277,9 @@ int acmeb200_kdtree_indnearest(int32_t np, int32_t n_columns, int32_t n_points, 
  * (2 flops per DFMA), the denominator of the FP64-pipe roofline in bench.py */
 int acmeb200_measure_fp64_peak(double *tflops_out);
 
+/* diagnostic: the device's exp (csrc/elements.cuh, the one the diode and BJT laws use) of n host values */
+int acmeb200_diag_exp(const double *x_host, double *out_host, int64_t n);
+
 const char *acmeb200_last_error(void);
 int acmeb200_abi_version(void);
 

@@ -26,7 +26,7 @@ struct CSubDesc
 end
 struct CModelDesc
     abi_version::Int32; nx::Int32; nu::Int32; ny::Int32; nsub::Int32; solver::Int32; maxiter::Int32
-    reserved::Int32; tol::Float64
+    cache_capacity::Int32; tol::Float64
     a::CArray; b::CArray; c::CArray; x0::CArray; dy::CArray; ey::CArray; fy::CArray; y0::CArray
     subs::Ptr{CSubDesc}
 end
@@ -165,7 +165,8 @@ end
     cache_sizes(runner; sub=1) -> (stored::Vector{Int32}, capacity::Int)
 
 Solutions the learning `CachingSolver` of sub-problem `sub` has stored so far, per instance
-(`num_ps`, src/solvers.jl:321-323).  The device keeps the newest `capacity` of them (ring buffer).
+(`num_ps`, src/solvers.jl:321-323).  The device store is the reference's (same stored solutions, k-d tree rebuilt on
+the same schedule); `capacity` is its physical size (a full store stops accepting solutions, flag 2 of `cache_info`).
 """
 function cache_sizes(r::BatchRunner; sub::Integer=1)
     n = Vector{Int32}(undef, r.batch)
@@ -173,6 +174,97 @@ function cache_sizes(r::BatchRunner; sub::Integer=1)
     check(ccall((:acmeb200_get_cache_sizes, libacmeb200), Cint, (Ptr{Cvoid}, Int32, Ptr{Int32}, Ptr{Int32}),
                 r.handle, sub - 1, n, cap))
     return n, Int(cap[])
+end
+
+"""
+    cache_info(runner; sub=1) -> Matrix{Int32} (8 x batch)
+
+Rows: `num_ps`, `new_count`, `new_count_limit` (src/solvers.jl:321-325), the capacity the reference's doubling arrays
+would have, points in the current tree, flags (1 frozen, 2 capacity reached, 4 search heap overflow), 2 reserved.
+"""
+function cache_info(r::BatchRunner; sub::Integer=1)
+    a = Matrix{Int32}(undef, 8, r.batch)
+    check(ccall((:acmeb200_get_cache_info, libacmeb200), Cint, (Ptr{Cvoid}, Int32, Ptr{Int32}), r.handle, sub - 1, a))
+    return a
+end
+
+"""
+    frozen_cache(solver::ACME.CachingSolver) -> CCache (+ the arrays it points into)
+
+Freezes what a `CachingSolver` of the reference has learnt (`ps_tree.ps[:, 1:num_ps]`, `zs[:, 1:num_ps]`,
+src/solvers.jl:321-323) into the read-only cache of a sub-problem descriptor.  The tree is rebuilt by the library's
+host-side `KDTree` constructor (`acmeb200_kdtree_build`, src/kdtree.jl:11-73 -- the code the device runs when a learning
+store rebuilds its tree) over the stored solutions alone: the reference's own tree also sorts the zero-filled spare
+columns of its doubled arrays into place (kdtree.jl:37), which makes (p = 0, z = 0) a start point.
+"""
+function frozen_cache(s)
+    n = s.num_ps
+    ps = Matrix{Float64}(s.ps_tree.ps[:, 1:n]); zs = Matrix{Float64}(s.zs[:, 1:n])
+    cut_dim = Vector{Int32}(undef, max(n - 1, 1)); cut_val = Vector{Float64}(undef, max(n - 1, 1)); ps_idx = Vector{Int32}(undef, n)
+    check(ccall((:acmeb200_kdtree_build, libacmeb200), Cint, (Int32, Int32, Int32, Ptr{Float64}, Ptr{Int32}, Ptr{Float64}, Ptr{Int32}),
+                size(ps, 1), n, n, ps, cut_dim, cut_val, ps_idx))
+    keep = (ps, zs, cut_dim, cut_val, ps_idx)
+    return CCache(n, n, pointer(cut_dim), pointer(cut_val), pointer(ps_idx), pointer(ps), pointer(zs)), keep
+end
+
+"""
+    solver_state(runner) -> Vector{UInt8};  solver_state!(runner, blob)
+
+Everything mutable of the device model -- `x`, the extrapolation origins `last_p, last_z, last_LU, last_Jp`
+(src/solvers.jl:155-158), the learnt solution stores and their trees (src/solvers.jl:321-325), status, statistics -- as
+one blob: what `deepcopy(model)` carries besides the matrices.  Restores into a runner of the same model, batch and
+kernel, on any device: checkpointing, moving a batch between GPUs, warm starts.
+"""
+function solver_state(r::BatchRunner)
+    n = ccall((:acmeb200_solver_state_size, libacmeb200), Int64, (Ptr{Cvoid},), r.handle)
+    n > 0 || check(Cint(n))
+    blob = Vector{UInt8}(undef, n)
+    check(ccall((:acmeb200_get_solver_state, libacmeb200), Cint, (Ptr{Cvoid}, Ptr{UInt8}, Int64), r.handle, blob, n))
+    return blob
+end
+solver_state!(r::BatchRunner, blob::Vector{UInt8}) =
+    check(ccall((:acmeb200_set_solver_state, libacmeb200), Cint, (Ptr{Cvoid}, Ptr{UInt8}, Int64), r.handle, blob, length(blob)))
+
+"""
+    extrapolation_origin(runner; sub=1) -> (p::Matrix, z::Matrix)      # get_extrapolation_origin, src/solvers.jl:199
+"""
+function extrapolation_origin(r::BatchRunner; sub::Integer=1)
+    p = Matrix{Float64}(undef, np(r.model, sub), r.batch); z = Matrix{Float64}(undef, nn(r.model, sub), r.batch)
+    check(ccall((:acmeb200_get_extrapolation_origin, libacmeb200), Cint, (Ptr{Cvoid}, Int32, Ptr{Float64}, Ptr{Float64}), r.handle, sub - 1, p, z))
+    return p, z
+end
+
+# ---- devices: a model lives on the device that is current when it is created
+device_count() = (n = Ref{Int32}(0); check(ccall((:acmeb200_device_count, libacmeb200), Cint, (Ref{Int32},), n)); Int(n[]))
+set_device(d::Integer) = check(ccall((:acmeb200_set_device, libacmeb200), Cint, (Int32,), d))
+
+"""
+    MultiGpuRunner(desc_builder, batch; n_gpus=0);  run!(r::MultiGpuRunner, Y, U)
+
+The batch over all the GPUs of the box from one Julia process (`acmeb200_multi_create/run`): contiguous instance shards,
+one device model per GPU, host arrays for the whole batch, every shard's host-buffer pipeline on its own thread inside
+the library (which never calls back into Julia, so a plain `ccall` suffices).  `desc_builder()` returns the same
+`Ref{CModelDesc}` (and the arrays it points into) that `BatchRunner` assembles.
+"""
+mutable struct MultiGpuRunner
+    model::DiscreteModel
+    batch::Int
+    handle::Ptr{Cvoid}
+end
+function MultiGpuRunner(model::DiscreteModel, desc::Ref{CModelDesc}, keep, batch::Integer; n_gpus::Integer=0)
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    GC.@preserve keep check(ccall((:acmeb200_multi_create, libacmeb200), Cint, (Ref{CModelDesc}, Int64, Int32, Ref{Ptr{Cvoid}}), desc, batch, n_gpus, h))
+    r = MultiGpuRunner(model, batch, h[])
+    finalizer(r -> ccall((:acmeb200_multi_destroy, libacmeb200), Cvoid, (Ptr{Cvoid},), r.handle), r)
+    return r
+end
+function ACME.run!(r::MultiGpuRunner, Y::Array{Float64,3}, U::Array{Float64,3})
+    m = r.model; N = size(U, 2)
+    size(U, 1) == nu(m) || throw(DimensionMismatch("input matrix has $(size(U,1)) rows, but model has $(nu(m)) inputs"))
+    size(Y) == (ny(m), N, r.batch) || throw(DimensionMismatch("output must be $(ny(m)) x $N x $(r.batch)"))
+    GC.@preserve U Y check(ccall((:acmeb200_multi_run, libacmeb200), Cint,
+        (Ptr{Cvoid}, Ptr{Float64}, Int64, Ptr{Float64}, Int64, Int64, UInt32), r.handle, U, nu(m) * N, Y, ny(m) * N, N, 0))
+    return Y
 end
 
 end # module

@@ -516,10 +516,10 @@ static void alts_update_best(Alts *a, double dist, int p_idx) { /* src/kdtree.jl
 #else
 #define KDPROF(x)
 #endif
-static unsigned long long g_kd_queries, g_kd_leaves, g_kd_nodes, g_kd_maxheap, g_kd_rebuilds, g_kd_newscan, g_kd_maxleaves;
+static unsigned long long g_kd_reorigin, g_kd_queries, g_kd_leaves, g_kd_nodes, g_kd_maxheap, g_kd_rebuilds, g_kd_newscan, g_kd_maxleaves;
 void oracle_kd_counters(unsigned long long *out, int reset) {
-    out[0] = g_kd_queries; out[1] = g_kd_leaves; out[2] = g_kd_nodes; out[3] = g_kd_maxheap; out[4] = g_kd_rebuilds; out[5] = g_kd_newscan; out[6] = g_kd_maxleaves;
-    if (reset) g_kd_queries = g_kd_leaves = g_kd_nodes = g_kd_maxheap = g_kd_rebuilds = g_kd_newscan = g_kd_maxleaves = 0;
+    out[0] = g_kd_queries; out[1] = g_kd_leaves; out[2] = g_kd_nodes; out[3] = g_kd_maxheap; out[4] = g_kd_rebuilds; out[5] = g_kd_newscan; out[6] = g_kd_maxleaves; out[7] = g_kd_reorigin;
+    if (reset) g_kd_reorigin = g_kd_queries = g_kd_leaves = g_kd_nodes = g_kd_maxheap = g_kd_rebuilds = g_kd_newscan = g_kd_maxleaves = 0;
 }
 
 /* indnearest  src/kdtree.jl:192-234 (max_leaves = typemax) */
@@ -715,6 +715,7 @@ static double *caching_solve(SubSolver *s, const double *p) {
     KDPROF(g_kd_newscan += (unsigned long long)s->new_count;)
     alts_init(&s->alts, best_diff, idx);
     idx = kd_indnearest(&s->tree, p, &s->alts, s->delta_scratch);
+    KDPROF(if (idx != 0) g_kd_reorigin++;)
     if (idx != 0)
         simple_set_origin_eval(s, &CM(s->tree.ps, np, 0, idx - 1), &CM(s->zs, nn, 0, idx - 1));
 
