@@ -358,12 +358,15 @@ static int select_kernel(acmeb200_model* m) {
         if (m->dm.solver != ACMEB200_SOLVER_HOMOTOPY_CACHING || s.np > KD_MAXNP) continue;
         size_t free_b = 0, total_b = 0;
         CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
-        // Physical capacity in stored solutions per instance (the reference's arrays double for ever, solvers.jl:376-382;
-        // superover stores ~900 solutions in its first second and ~150 per second after that): as large as a memory budget
-        // allows, at most 4096; the descriptor (cache_capacity) or ACMEB200_CACHE_CAP override it
+        // Physical capacity in stored solutions per instance.  The reference's arrays double for ever (solvers.jl:376-382;
+        // superover stores ~900 solutions in its first second and ~150 per second after that), and a store that is full
+        // stops learning, which costs iterations from then on (measured at capacity 1024 on config 4: 3.2 -> 8.6 iterations
+        // per solve once the stores were full).  So: as large as a generous memory budget allows (a third of the free
+        // memory, at most 32 GB -- 9 GB for the 8192 superover instances at 4096 solutions each), at most 4096; the
+        // descriptor (cache_capacity) or ACMEB200_CACHE_CAP override it
         int cap = 4096;
         const size_t per_col = 8 * (size_t)(s.np + s.nn) + 16 + 24 + 8 * (size_t)s.np;
-        const size_t budget = std::min<size_t>(free_b / 8, (size_t)4 << 30);
+        const size_t budget = std::min<size_t>(free_b / 3, (size_t)32 << 30);
         while (cap > 64 && (size_t)m->B * cap * per_col > budget) cap /= 2;
         if (m->cache_capacity > 0) cap = m->cache_capacity;
         if (const char* e = getenv("ACMEB200_CACHE_CAP")) { const long v = atol(e); if (v >= 2 && v <= (1 << 20)) cap = (int)v; }  // tuning / test knob

@@ -19,8 +19,8 @@
 //     spare columns up to the physical capacity are zero-filled memory, the ones beyond it are virtual zeros;
 //   * the search is the reference's best-first search with its heap operations, so ties between equally
 //     distant points resolve the same way; distances and bounds are accumulated unfused, in the same order.
-// Bounded where the reference is unbounded: the physical capacity (a store that is full stops accepting
-// solutions: flag KD_F_FULL) and the heap of alternatives (KD_HEAP entries; an overflow is counted, never seen
+// Bounded where the reference is unbounded: the physical capacity (a store that is full forgets its older half,
+// kd_compact: flag KD_F_FULL) and the heap of alternatives (KD_HEAP entries; an overflow is counted, never seen
 // in the tests: the deepest heap observed on the BASELINE circuits holds 32 entries).
 #pragma once
 #include <cmath>
@@ -343,6 +343,31 @@ KD_HD int kd_lookup(const KdStore& c, PF p, double best_diff, int* overflow) {
     return kd_indnearest(c, c.hdr[KD_H_TREEN], p, best_diff, idx, overflow);
 }
 
+// A full store forgets its older half (the initial solution in column 1 stays): the newest cap/2 columns move down
+// to columns 2.., the rest is zeroed (spare columns are the zero-filled spare capacity of the reference's arrays), and
+// the tree is marked due for a rebuild at once.  This is where the device departs from the reference, whose arrays
+// double for ever (solvers.jl:376-382): it keeps learning with bounded memory.  (A store that simply stops accepting
+// solutions gets worse with time: measured on config 4 at capacity 1024, 3.2 -> 8.6 iterations per solve.)
+KD_HD void kd_compact(KdStore& c) {
+    int* const h = c.hdr;
+    const int cap = c.cap, keep = cap / 2, w = c.np + c.nn;
+    const int first = cap - keep + 1;  // oldest column that stays
+    for (int k = 0; k < keep; k++) {
+        const double* const src = c.col(first + k);
+        double* const dst = c.col(2 + k);
+        for (int j = 0; j < w; j++) dst[j] = src[j];
+    }
+    for (int col = keep + 2; col <= cap; col++) {
+        double* const dst = c.col(col);
+        for (int j = 0; j < w; j++) dst[j] = 0.0;
+    }
+    h[KD_H_NUM] = keep + 1;
+    h[KD_H_CAPREF] = keep + 1;  // from here the reference's doubling rule again (solvers.jl:376-382)
+    h[KD_H_NEW] = 1;     // with LIMIT = 0: the tree (whose leaves name the old columns) is rebuilt before the next search
+    h[KD_H_LIMIT] = 0;
+    h[KD_H_FLAGS] |= KD_F_FULL;
+}
+
 // What follows the base solve (solvers.jl:374-389): store (p, z) if the solve needed more than 5 iterations and
 // converged, count down to the next rebuild.  Returns true when the tree is due for a rebuild (solvers.jl:390):
 // the caller rebuilds (kd_build, or kd_build_warp with its whole warp) and calls kd_rebuilt.
@@ -351,19 +376,22 @@ KD_HD bool kd_store_step(KdStore& c, bool store, PF p, ZF z, int* stored_col = n
     int* const h = c.hdr;
     if (stored_col) *stored_col = 0;
     if (h[KD_H_FLAGS] & KD_F_FROZEN) return false;
+    bool compacted = false;
     if (store) {
+        if (h[KD_H_NUM] >= c.cap && c.cap >= 8) { kd_compact(c); compacted = true; }
         if (h[KD_H_NUM] < c.cap) {
             const int n = ++h[KD_H_NUM];
             if (n > h[KD_H_CAPREF]) h[KD_H_CAPREF] = 2 * n;  // the reference's arrays double here (solvers.jl:376-382)
             double* const dst = c.col(n);
             for (int j = 0; j < c.np; j++) dst[j] = p(j);
             for (int j = 0; j < c.nn; j++) dst[c.np + j] = z(j);
-            h[KD_H_NEW] += 1;
-            if (stored_col) *stored_col = n;
+            if (!compacted) h[KD_H_NEW] += 1;
+            if (stored_col) *stored_col = compacted ? 0 : n;
         } else {
-            h[KD_H_FLAGS] |= KD_F_FULL;  // the reference would keep growing; this store stops learning
+            h[KD_H_FLAGS] |= KD_F_FULL;  // capacity below 8: the store simply stops learning
         }
     }
+    if (compacted) return true;  // rebuild at once
     if (h[KD_H_NEW] > 0) h[KD_H_LIMIT] -= 1;
     return h[KD_H_NEW] > h[KD_H_LIMIT];
 }
@@ -375,8 +403,10 @@ KD_HD void kd_rebuilt(KdStore& c) {  // solvers.jl:391-393
 template <class PF, class ZF>
 KD_HD bool kd_after_solve(KdStore& c, bool store, PF p, ZF z, int* stored_col = nullptr) {
     if (!kd_store_step(c, store, p, z, stored_col)) return false;
-    const int cap_ref = c.hdr[KD_H_CAPREF];
-    kd_build(c, c.hdr[KD_H_NUM], c.hdr[KD_H_NUM], cap_ref);  // spare columns, physical or not, are zeros: the virtual ones of kd_build
+    // spare columns, physical or not, are zeros: the virtual ones of kd_build.  A store that has been compacted has left
+    // the reference's path anyway: its trees hold stored solutions only (no spare (p = 0, z = 0) columns as start points)
+    const int cap_ref = (c.hdr[KD_H_FLAGS] & KD_F_FULL) ? c.hdr[KD_H_NUM] : c.hdr[KD_H_CAPREF];
+    kd_build(c, c.hdr[KD_H_NUM], c.hdr[KD_H_NUM], cap_ref);
     kd_rebuilt(c);
     return true;
 }

@@ -439,7 +439,7 @@ template <class C>
 __device__ __noinline__ void tpi_kd_rebuild(const DevSub* cache, int64_t inst, int lane) {
     KdStore c = tpi_store<C>(*cache, inst);
     __syncwarp();
-    const int num = c.hdr[KD_H_NUM], cap_ref = c.hdr[KD_H_CAPREF];
+    const int num = c.hdr[KD_H_NUM], cap_ref = (c.hdr[KD_H_FLAGS] & KD_F_FULL) ? num : c.hdr[KD_H_CAPREF];  // kdcache.cuh kd_after_solve
     kd_build_warp(c, num, num, cap_ref, lane);  // spare columns, physical or not, are zeros: the virtual ones of kd_build
     if (lane == 0) kd_rebuilt(c);
     if (cache->kd_mir && !cache->kd_mshared)  // the leaf mirror, lanes over leaves

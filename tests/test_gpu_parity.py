@@ -448,8 +448,9 @@ def test_learning_cache_long_run_and_capacity(monkeypatch):
     """Two consecutive half seconds on the warp-per-instance kernel: hundreds of stored solutions and dozens of tree
     rebuilds per instance (the warp-cooperative KDTree constructor), state carried across calls -- histogram and store
     sizes equal the oracle's, outputs strictly within 1e-6.  Then the same run with a physical capacity too small
-    for it: the store fills up, says so (ACMEB200_CACHE_FULL), stops learning and the outputs stay within the
-    reference's own stopping-rule accuracy."""
+    for it: a full store forgets its older half (the one place where the device departs from the reference, whose arrays
+    double for ever), says so (ACMEB200_CACHE_FULL), keeps learning -- the iteration count stays near the reference's
+    instead of degrading -- and the outputs stay within the reference's own stopping-rule accuracy."""
     B, N = 6, 22050
     m = ex.superover()
     u = np.zeros((4, 2 * N, B), order="F")
@@ -476,7 +477,9 @@ def test_learning_cache_long_run_and_capacity(monkeypatch):
     r = BatchRunner(m, B, solver=HC)
     y2 = r.run(u)
     stored, cap = r.cache_sizes()
-    assert cap == 64 and (stored == 64).all() and (r.cache_info()["flags"] & 2).all()
+    assert cap == 64 and (stored > 32).all() and (stored <= 64).all() and (r.cache_info()["flags"] & 2).all()
+    it_small = r.stats()["newton_iters"] / r.stats()["solves"]
+    assert it_small < 1.25 * so["newton_iters"] / so["solves"]
     yexact = OracleModel(m, B, solver=H, tol=1e-13).run(u, threads=0)
     assert_parity_within_reference_accuracy(y2, yref, yexact)
     r.close()

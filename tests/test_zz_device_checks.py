@@ -40,5 +40,6 @@ def test_compute_sanitizer_clean(tool):
     env = dict(os.environ, SAN_SMALL="1")
     res = subprocess.run([exe, "--tool", tool, "--error-exitcode", "9", sys.executable, os.path.join(ROOT, "tools", "sanitize_run.py")],
                          env=env, capture_output=True, text=True, timeout=1500, cwd=ROOT)
-    tail = (res.stdout + res.stderr)[-3000:]
-    assert res.returncode == 0 and "ERROR SUMMARY: 0 errors" in res.stdout + res.stderr, tail
+    out = res.stdout + res.stderr
+    clean = "ERROR SUMMARY: 0 errors" in out if tool == "memcheck" else "RACECHECK SUMMARY: 0 hazards displayed (0 errors, 0 warnings)" in out
+    assert res.returncode == 0 and clean, out[-3000:]
