@@ -426,6 +426,10 @@ class DiscreteModel:
             return
         self._derive(circ, fr(t), decompose_nonlinearity)
 
+    def __getstate__(self):
+        # device runners cached by run_(model, u) hold library handles: they stay with this object
+        return {k: v for k, v in self.__dict__.items() if k != "_device_runners"}
+
     # ACME.jl:150-262
     def _derive(self, circ: Circuit, t: Fraction, decompose: bool):
         mats = model_matrices(circ, t)

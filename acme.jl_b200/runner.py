@@ -588,10 +588,16 @@ def run_(target, *args, showprogress=False, **kw):
         if isinstance(runner, ModelRunner):
             runner.model.x = runner.x[:, 0].copy()
         return y
+    # run!(model, u): in the reference the solvers live in the DiscreteModel (ACME.jl:118-148), so the extrapolation
+    # origin and what the CachingSolver has learnt persist from call to call.  Same here: the device runner is kept on
+    # the model (one per set of runner options) and reused; only model.x is handed over each call, as ACME.jl:561-562 does.
     model = target
     (u,) = args
-    runner = ModelRunner(model, showprogress, **kw)
-    try:
-        return run_(runner, u)
-    finally:
-        runner.close()
+    key = repr(sorted(kw.items()))
+    cache = model.__dict__.setdefault("_device_runners", {})
+    runner = cache.get(key)
+    if runner is None or getattr(runner, "_h", None) is None:
+        runner = cache[key] = ModelRunner(model, showprogress, **kw)
+    else:
+        runner.x = model.x
+    return run_(runner, u)

@@ -270,6 +270,35 @@ def timed_steps(D: Dist, stream, fn, warmup: int, steps: int) -> float:
     return D.maxr(e0.elapsed_time(e1)) / steps
 
 
+def host_copy_ceiling(D: Dist) -> dict:
+    """What the host side of this box can move: pinned host <-> device copies of 1 GiB, both directions at once on two
+    streams, every rank at the same time (the e2e leg does exactly that, plus a kernel): the e2e rate cannot exceed
+    aggregate_GBs_per_direction / 8 bytes per sample and direction."""
+    import torch
+    n = 1 << 27  # doubles: 1 GiB
+    hu = torch.empty(n, dtype=torch.float64, pin_memory=True); hy = torch.empty(n, dtype=torch.float64, pin_memory=True)
+    du = torch.empty(n, dtype=torch.float64, device=D.dev); dy = torch.zeros(n, dtype=torch.float64, device=D.dev)
+    hu.zero_()
+    s1, s2 = torch.cuda.Stream(D.dev), torch.cuda.Stream(D.dev)
+    reps = 4
+    for timed in (False, True):
+        torch.cuda.synchronize(); D.barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps if timed else 1):
+            with torch.cuda.stream(s1):
+                du.copy_(hu, non_blocking=True)
+            with torch.cuda.stream(s2):
+                hy.copy_(dy, non_blocking=True)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+    dt = D.maxr(dt)
+    per_dir = n * 8 * reps / dt / 1e9
+    del hu, hy, du, dy
+    return {"GBs_per_direction_per_gpu": per_dir, "aggregate_GBs_per_direction": per_dir * D.world,
+            "Msamples_per_s_ceiling": per_dir * D.world / 8 * 1e3,
+            "how": "1 GiB pinned H2D and D2H concurrently on two streams, all ranks at once, 4 repetitions"}
+
+
 def rel_err(y: np.ndarray, yref: np.ndarray) -> float:
     """the parity measure of tests/test_gpu_parity.py: |y - yref| / max(|yref|, 1e-3 max|yref|)"""
     peak = float(np.max(np.abs(yref))) if yref.size else 0.0
@@ -792,6 +821,10 @@ def main():
         if r2 is not runner:
             r2.close()
         del hu, hy
+        try:   # the bound, measured: how fast this box's host side moves the same bytes without any kernel
+            e2e["host_copy_ceiling"] = host_copy_ceiling(D)
+        except Exception as e:
+            e2e["host_copy_ceiling"] = {"error": f"{type(e).__name__}: {e}"}
     else:
         del U, Y
     kernel_name = runner.kernel_name
