@@ -16,11 +16,12 @@ from . import examples
 from .runner import BatchRunner, ModelRunner, MultiGpuRunner, run_, DimensionMismatch
 from .sweep import derive_sweep
 from .kdtree import KDTree, frozen_cache
+from ._specialise import specialise
 
 __all__ = [
     "Element", "NLElem", "Circuit", "circuit", "topomat", "DiscreteModel", "SubProblem",
     "gensolve", "rank_factorize", "examples",
-    "BatchRunner", "ModelRunner", "MultiGpuRunner", "run_", "DimensionMismatch", "derive_sweep", "KDTree", "frozen_cache",
+    "BatchRunner", "ModelRunner", "MultiGpuRunner", "run_", "DimensionMismatch", "derive_sweep", "KDTree", "frozen_cache", "specialise",
     "resistor", "potentiometer", "capacitor", "inductor", "transformer",
     "voltagesource", "currentsource", "voltageprobe", "currentprobe",
     "diode", "bjt", "mosfet", "opamp",

@@ -58,6 +58,7 @@ def lib():
         L.acmeb200_multi_model.restype = vp
         L.acmeb200_multi_run.argtypes = [vp, vp, i64, vp, i64, i64, u32]
         L.acmeb200_diag_exp.argtypes = [vp, vp, i64]
+        L.acmeb200_register_tpi.argtypes = [vp]
         L.acmeb200_set_kernel.argtypes = [vp, C.c_int32]
         L.acmeb200_kernel_name.argtypes = [vp]
         L.acmeb200_kernel_name.restype = C.c_char_p
@@ -67,6 +68,9 @@ def lib():
         L.acmeb200_last_error.restype = C.c_char_p
         L.acmeb200_abi_version.restype = C.c_int
         _LIB = L
+        if not path.endswith("_emu.so"):
+            from . import _specialise  # shape plugins built earlier (acme.jl_b200/shapes/)
+            _specialise.register_all()
     return _LIB
 
 
@@ -80,7 +84,7 @@ EXPORTS = ["acmeb200_model_create", "acmeb200_model_destroy", "acmeb200_run", "a
            "acmeb200_get_cache_info", "acmeb200_kdtree_build", "acmeb200_kdtree_indnearest",
            "acmeb200_solver_state_size", "acmeb200_get_solver_state", "acmeb200_set_solver_state", "acmeb200_get_extrapolation_origin",
            "acmeb200_device_count", "acmeb200_set_device", "acmeb200_get_device", "acmeb200_multi_create", "acmeb200_multi_destroy",
-           "acmeb200_multi_shards", "acmeb200_multi_model", "acmeb200_multi_run", "acmeb200_diag_exp",
+           "acmeb200_multi_shards", "acmeb200_multi_model", "acmeb200_multi_run", "acmeb200_diag_exp", "acmeb200_register_tpi",
            "acmeb200_set_kernel", "acmeb200_kernel_name", "acmeb200_launch_count", "acmeb200_measure_fp64_peak",
            "acmeb200_last_error", "acmeb200_abi_version"]
 

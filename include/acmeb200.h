@@ -249,6 +249,13 @@ int acmeb200_get_cache_sizes(acmeb200_model *m, int32_t sub, int32_t *sizes_host
 #define ACMEB200_CACHE_HEAP_OVERFLOW 4 /* a search dropped an alternative (never seen in tests)  */
 int acmeb200_get_cache_info(acmeb200_model *m, int32_t sub, int32_t *info_host);
 
+/* Shapes compiled outside the library.  The thread-per-instance kernel is a template over the model's dimensions and
+ * element sequence; the library instantiates it for the BASELINE circuits.  For any other small single-sub-problem
+ * model the host generates the one-line instantiation from csrc/shape_plugin.cu.in, builds it with nvcc into its own
+ * shared object (acme_jl_b200.specialise does both) and hands the plugin's entry (the pointer returned by
+ * the plugin's exported function `shape_entry` with the acmeb200_ prefix) to the library; later models of that shape run on the specialised kernel. */
+int acmeb200_register_tpi(const void *entry);
+
 /* kernel selection: 0 = automatic, 1 = force the generic thread-per-instance
  * kernel, 2 = force the cooperative (lanes-per-instance) kernel, 3 = force the
  * warp-per-instance kernel with the LU rows in registers; solver state is reset */
