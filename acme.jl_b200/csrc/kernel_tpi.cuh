@@ -28,6 +28,17 @@
 
 namespace acme {
 
+// ACME_TPI_PROF (tuning builds only, tools/build_variants.py): per-warp cycle counts and event counters of the
+// nonlinear sample loop in a device array, read back with acmeb200_diag_tpi_prof (tools/tail_prof.py).
+#ifdef ACME_TPI_PROF
+#define TPI_PROF(...) __VA_ARGS__
+constexpr int TPI_PROF_WARPS = 8192, TPI_PROF_REC = 8;
+__device__ unsigned long long g_tpi_prof[TPI_PROF_WARPS * TPI_PROF_REC];
+struct TpiProf { unsigned reo, tie, scan, stores, nontriv, small; };
+#else
+#define TPI_PROF(...)
+#endif
+
 template <class... Es> struct EList {};
 
 template <int ROW, int QOFF, int COFF, int JOFF, class F>
@@ -349,7 +360,25 @@ struct TpiKd {
     int num;    // stored solutions
     int limit;  // new_count_limit: counted down in this register while new_count > 0 (solvers.jl:387-389), written back to
                 // the store's header before anything else reads it (tpi_kd_flush)
+    bool sm;    // the lookup data of this (small) store is in the warp's shared memory (tpi_kd_sm_fill)
 };
+// A small learning store -- a tree of at most TPI_KT leaves and at most TPI_KN new solutions, what the stiff corner of a
+// parameter sweep holds (config 2: four solutions per instance) -- keeps what the start-point choice reads in the warp's
+// shared memory: the p-coordinates of the tree's points in leaf order with their columns, then those of the newest
+// entries, [slot][dimension][lane].  The choice then costs no global load (the chosen column's (p, z) still come from
+// the store).  Measured on config 2 (tools/tail_prof.py): the kernel ends with its slowest warps, and those are the
+// warps of the stiff corner, whose lanes choose among four solutions every sample and re-origin on a third of them;
+// their per-instance store blocks (one cache line per lane and access) do not stay in L1.  Filled whenever the
+// register copy of the header is (re)read (tpi_kd_reload).  Tried and measured slower: (z) in shared memory as well
+// (+25 % shared memory per warp: 18.2 against 21.0 Gsamples/s), and a memo of the extrapolation matrix per stored
+// solution (saves the origin evaluation, costs a round trip to L2: 18.9 against 19.7).
+// ACME_TPI_SMKD: 0 off, 1 every shape, 2 (default) shapes with one parameter -- with more the tiles' share of L1 is
+// worth more to the large stores of config 5 than this is (measured: birdie -16 % with it on).
+#ifndef ACME_TPI_SMKD
+#define ACME_TPI_SMKD 2
+#endif
+constexpr int TPI_KT = 4, TPI_KN = 4;
+template <class C> __host__ __device__ constexpr bool tpi_smkd() { return C::NN > 0 && (ACME_TPI_SMKD == 1 || (ACME_TPI_SMKD == 2 && C::NP == 1)); }
 // the register copy of new_count_limit back into the store's header
 template <class C>
 __device__ __forceinline__ void tpi_kd_flush(const DevSub& c, int64_t inst, const TpiKd& kd) {
@@ -357,7 +386,7 @@ __device__ __forceinline__ void tpi_kd_flush(const DevSub& c, int64_t inst, cons
 }
 template <class C>
 __device__ __forceinline__ TpiKd tpi_kd_state(const DevSub& c, int64_t inst) {
-    TpiKd k{0, false, false, false, 0, 0, 0};
+    TpiKd k{0, false, false, false, 0, 0, 0, false};
     if (c.kd_cap > 0) {
         const int* h = reinterpret_cast<const int*>(c.kd_base + inst * c.kd_stride);
         k.on = true;
@@ -368,6 +397,24 @@ __device__ __forceinline__ TpiKd tpi_kd_state(const DevSub& c, int64_t inst) {
         k.triv = !c.kd_frozen && h[KD_H_NUM] == 1 && h[KD_H_NEW] == 0 && h[KD_H_TREEN] == 1;
     }
     return k;
+}
+// header -> registers, small stores -> shared memory (smd: this lane's first double, smi: this lane's first int)
+template <class C>
+__device__ __noinline__ TpiKd tpi_kd_reload(const DevSub* cachep, int64_t inst, double* smd, int* smi) {
+    const DevSub& cache = *cachep;
+    TpiKd kd = tpi_kd_state<C>(cache, inst);
+    if (tpi_smkd<C>() && kd.on && !kd.triv && !cache.kd_frozen && kd.treen <= TPI_KT && kd.newc <= TPI_KN && kd.treen >= 1) {
+        const KdStore c = tpi_store<C>(cache, inst);
+        for (int leaf = 0; leaf < kd.treen; leaf++) {
+            const int col = c.psidx(leaf + 1);
+            smi[leaf * 32] = col;
+            for (int d = 0; d < C::NP; d++) smd[(leaf * C::NP + d) * 32] = c.P(d, col);
+        }
+        for (int i = 0; i < kd.newc; i++)
+            for (int d = 0; d < C::NP; d++) smd[((TPI_KT + i) * C::NP + d) * 32] = c.P(d, kd.num - kd.newc + 1 + i);
+        kd.sm = true;
+    }
+    return kd;
 }
 template <class C>
 __device__ __noinline__ int tpi_kd_lookup(const DevSub* cache, int64_t inst, const double* p, double best) {
@@ -603,7 +650,10 @@ struct TpiSmem {
     static constexpr int OUT_OFF = TPI_STAGES * IN_BYTES;
     static constexpr int HIST_OFF = OUT_OFF + TPI_OSTAGES * OUT_BYTES;
     static constexpr int BAR_OFF = HIST_OFF + 32 * 8 * 4;
-    static constexpr int PER_WARP = (BAR_OFF + 8 * TPI_STAGES + 1023) / 1024 * 1024;  // swizzled tiles want 1024-byte alignment
+    static constexpr int KD_OFF = (BAR_OFF + 8 * TPI_STAGES + 15) / 16 * 16;  // small solution stores (tpi_kd_reload)
+    static constexpr int KDI_OFF = KD_OFF + (tpi_smkd<C>() ? 32 * (TPI_KT + TPI_KN) * C::NP * 8 : 0);
+    static constexpr int KD_END = KDI_OFF + (tpi_smkd<C>() ? 32 * TPI_KT * 4 : 0);
+    static constexpr int PER_WARP = (KD_END + 1023) / 1024 * 1024;  // swizzled tiles want 1024-byte alignment
     // Byte offset of (row, byte o within the row) inside a tile = row*ROW + (o ^ xor_term(row)):
     // swizzled rows are at most 128 bytes long, so address bits >= 7 depend on the row alone and
     // the XOR term is a per-lane constant (computed once, outside the sample loop).
@@ -663,7 +713,8 @@ __device__ __forceinline__ void tpi_output_update(const M& m, TpiState<C>& S, co
 template <class C, class M>
 __device__ __forceinline__ int tpi_step_hot(const M& m, const double (&Cn)[dim1(C::NC)], TpiState<C>& S,
                                             const double (&u)[dim1(C::NU)], double (&y)[dim1(C::NY)],
-                                            const SolverCfg& sc, const DevSub& cache, int64_t inst, TpiKd& kd) {
+                                            const SolverCfg& sc, const DevSub& cache, int64_t inst, TpiKd& kd,
+                                            const double* smd, const int* smi TPI_PROF(, TpiProf& pr)) {
     constexpr int NN = C::NN, NP = C::NP;
     double zall[dim1(NN)];
     int iters = 0;
@@ -678,7 +729,50 @@ __device__ __forceinline__ int tpi_step_hot(const M& m, const double (&Cn)[dim1(
                 double d0 = 0.0;
                 static_for<0, NP>([&](auto ii) { d0 = __dadd_rn(d0, __dmul_rn(p[decltype(ii)::value], p[decltype(ii)::value])); });
                 col = d0 < best ? 1 : 0;
+            } else if (tpi_smkd<C>() && kd.sm) {
+                TPI_PROF(pr.nontriv++; pr.small++;)
+                // the same choice as below from shared memory: newest entries in index order (solvers.jl:354-363), then the
+                // nearest tree point if it is strictly nearer (kdtree.jl:192-234); two leaves tying -> the serial search
+                constexpr int F = NP;
+                double bseed = best;
+#pragma unroll
+                for (int i = 0; i < TPI_KN; i++)
+                    if (i < kd.newc) {
+                        double acc = 0.0;
+                        static_for<0, NP>([&](auto ii) {
+                            constexpr int k = decltype(ii)::value;
+                            const double d = smd[((TPI_KT + i) * F + k) * 32] - p[k];
+                            acc = __dadd_rn(acc, __dmul_rn(d, d));
+                        });
+                        if (acc < bseed) { bseed = acc; col = kd.num - kd.newc + 1 + i; }
+                    }
+                double bd = __longlong_as_double(0x7ff0000000000000ll);
+                int bleaf = 0;
+                bool tie = false;
+#pragma unroll
+                for (int l = 0; l < TPI_KT; l++)
+                    if (l < kd.treen) {
+                        double acc = 0.0;
+                        static_for<0, NP>([&](auto ii) {
+                            constexpr int k = decltype(ii)::value;
+                            const double d = p[k] - smd[(l * F + k) * 32];
+                            acc = __dadd_rn(acc, __dmul_rn(d, d));
+                        });
+                        tie = acc < bd ? false : (acc == bd ? true : tie);
+                        if (acc < bd) { bd = acc; bleaf = l; }
+                    }
+                if (bd < bseed) {
+                    if (!tie) {
+                        col = smi[bleaf * 32];
+                    } else {
+                        double pl[dim1(NP)];
+                        static_for<0, NP>([&](auto ii) { pl[decltype(ii)::value] = p[decltype(ii)::value]; });
+                        col = tpi_kd_lookup<C>(&cache, inst, pl, best);
+                        TPI_PROF(pr.tie++;)
+                    }
+                }
             } else {
+                TPI_PROF(pr.nontriv++;)
                 // the new_count newest stored solutions, first minimum in index order (solvers.jl:354-363) ...
                 double bseed = best;
                 if (kd.newc > 0) {
@@ -697,9 +791,11 @@ __device__ __forceinline__ int tpi_step_hot(const M& m, const double (&Cn)[dim1(
                 }
                 // ... then the tree, seeded with that (kdtree.jl:93-100, 192-234)
                 if (kd.treen <= 2) {
+                    TPI_PROF(pr.small++;)
                     const int tcol = tpi_kd_small<C>(cache, inst, p, bseed, kd.treen);
                     col = tcol ? tcol : col;
                 } else if (cache.kd_mir) {
+                    TPI_PROF(pr.scan++;)
                     // every leaf of the tree, several per pass (independent loads in flight together), lanes in step: the
                     // nearest tree point, taken if it is strictly nearer than the seed (what indnearest returns)
                     double bd = __longlong_as_double(0x7ff0000000000000ll);
@@ -735,6 +831,7 @@ __device__ __forceinline__ int tpi_step_hot(const M& m, const double (&Cn)[dim1(
                             double pl[dim1(NP)];
                             static_for<0, NP>([&](auto ii) { pl[decltype(ii)::value] = p[decltype(ii)::value]; });
                             col = tpi_kd_lookup<C>(&cache, inst, pl, best);
+                            TPI_PROF(pr.tie++;)
                         }
                     }
                 } else {
@@ -749,6 +846,7 @@ __device__ __forceinline__ int tpi_step_hot(const M& m, const double (&Cn)[dim1(
         const int64_t e = col > 0 && col <= cap ? col - 1 : 0;
         const double* const pc = cst + KD_HDR_INTS / 2 + 2 * (int64_t)cap + e * (NP + NN);  // KdStore::col(col): p then z
         const double* const zc = pc + NP;
+        TPI_PROF(if (col > 0) pr.reo++;)
         if (caching && col > cap) return -1;  // a virtual zero column as start point (kdcache.cuh): the cold path handles it
         const bool conv = tpi_simple_solve<C>(m, Cn, S, p, zall, sc, iters, col > 0, pc, zc, 1);
         if (caching && !cache.kd_frozen) {  // solvers.jl:374-394
@@ -757,8 +855,9 @@ __device__ __forceinline__ int tpi_step_hot(const M& m, const double (&Cn)[dim1(
                 static_for<0, NP>([&](auto ii) { pl[decltype(ii)::value] = p[decltype(ii)::value]; });
                 static_for<0, NN>([&](auto ii) { zl[decltype(ii)::value] = zall[decltype(ii)::value]; });
                 tpi_kd_flush<C>(cache, inst, kd);
+                TPI_PROF(pr.stores++;)
                 const bool due = tpi_kd_after<C>(&cache, inst, pl, zl, 1);
-                kd = tpi_kd_state<C>(cache, inst);
+                kd = tpi_kd_reload<C>(&cache, inst, const_cast<double*>(smd), const_cast<int*>(smi));
                 kd.due = due;
             } else if (kd.newc > 0) {  // count down to the rebuild in registers
                 kd.limit -= 1;
@@ -900,9 +999,12 @@ __global__ void __launch_bounds__(TPI_TPB, ACME_TPI_MINB) k_tpi(const __grid_con
     static_for<0, NN>([&](auto i) { S.lz[decltype(i)::value] = st[(int64_t)(C::S_LZ + decltype(i)::value) * a.ld]; });
     static_for<0, NN * NP>([&](auto i) { S.Mx[decltype(i)::value] = st[(int64_t)(C::S_MX + decltype(i)::value) * a.ld]; });
 
-    TpiKd kd{0, false, false, false, 0, 0, 0};
+    TpiKd kd{0, false, false, false, 0, 0, 0, false};
+    TPI_PROF(TpiProf pr{0, 0, 0, 0, 0, 0}; unsigned pr_cold = 0, pr_reb = 0; long long pr_t_cold = 0; const long long pr_t0 = clock64();)
+    double* const kd_smd = reinterpret_cast<double*>(wsm + SM::KD_OFF) + lane;
+    int* const kd_smi = reinterpret_cast<int*>(wsm + SM::KDI_OFF) + lane;
     if constexpr (NN > 0)
-        if (sc.solver == ACMEB200_SOLVER_HOMOTOPY_CACHING && active) kd = tpi_kd_state<C>(cache, inst);
+        if (sc.solver == ACMEB200_SOLVER_HOMOTOPY_CACHING && active) kd = tpi_kd_reload<C>(&cache, inst, kd_smd, kd_smi);
     bool dead = !active || (a.status[inst] & ACMEB200_STATUS_NONFINITE);
     int dead_at = dead ? 0 : -1;  // sample index (this call) at which the instance halted, -1 = alive
     const bool shared_u = (a.u_stride == 0) || NU == 0;
@@ -1036,7 +1138,7 @@ __global__ void __launch_bounds__(TPI_TPB, ACME_TPI_MINB) k_tpi(const __grid_con
                             constexpr int q = decltype(kk)::value;
                             u[q] = shared_u ? __ldg(a.U + (int64_t)(n0 + tt) * NU + q) : in_at(tt * NU + q);
                         });
-                        code = tpi_step_hot<C>(m, Cn, S, u, y, sc, cache, inst, kd);
+                        code = tpi_step_hot<C>(m, Cn, S, u, y, sc, cache, inst, kd, kd_smd, kd_smi TPI_PROF(, pr));
                         if (code >= 0) {
                             if (NN > 0) {
                                 if (code <= 8) hist_s[(code - 1) * 32] += 1u;
@@ -1051,7 +1153,9 @@ __global__ void __launch_bounds__(TPI_TPB, ACME_TPI_MINB) k_tpi(const __grid_con
                     if (__any_sync(0xffffffffu, code < 0 || kd.due)) break;
                 }
                 if (tt < cnt) {  // warp-uniform
+                    TPI_PROF(const long long pr_tc = clock64();)
                     if (code < 0) {
+                        TPI_PROF(pr_cold++;)
                         // this lane's sample tt needs the cold path
                         double u[dim1(NU)], y[dim1(NY)];
                         static_for<0, NU>([&](auto kk) {
@@ -1061,7 +1165,7 @@ __global__ void __launch_bounds__(TPI_TPB, ACME_TPI_MINB) k_tpi(const __grid_con
                         if constexpr (NN > 0) tpi_kd_flush<C>(cache, inst, kd);
                         const int it = tpi_step_cold<C>(&m, Cn, &S, u, y, &sc, &cache, &a, inst, n0 + tt, code);
                         if constexpr (NN > 0)
-                            if (kd.on) kd = tpi_kd_state<C>(cache, inst);  // the cold solves may have stored solutions / rebuilt the tree
+                            if (kd.on) kd = tpi_kd_reload<C>(&cache, inst, kd_smd, kd_smi);  // the cold solves may have stored solutions / rebuilt the tree
                         if (it < 0) {
                             dead = true; dead_at = n0 + tt;
                             static_for<0, NY>([&](auto kk) { out_at(tt * NY + decltype(kk)::value) = NAN; });
@@ -1078,10 +1182,12 @@ __global__ void __launch_bounds__(TPI_TPB, ACME_TPI_MINB) k_tpi(const __grid_con
                             due &= due - 1;
                             const int64_t isrc = __shfl_sync(0xffffffffu, (long long)inst, src);
                             tpi_kd_rebuild<C>(&cache, isrc, lane);
-                            if (lane == src) { kd = tpi_kd_state<C>(cache, inst); kd.due = false; }
+                            TPI_PROF(if (lane == src) pr_reb++;)
+                            if (lane == src) { kd = tpi_kd_reload<C>(&cache, inst, kd_smd, kd_smi); kd.due = false; }
                         }
                     }
                     tt++;
+                    TPI_PROF(pr_t_cold += clock64() - pr_tc;)
                 }
             }
         }
@@ -1121,6 +1227,30 @@ __global__ void __launch_bounds__(TPI_TPB, ACME_TPI_MINB) k_tpi(const __grid_con
     if (active) store_state();
     if constexpr (NN > 0)
         if (active) tpi_kd_flush<C>(cache, inst, kd);
+#ifdef ACME_TPI_PROF
+    if constexpr (NN > 0) {
+        const long long pr_t1 = clock64();
+        const int64_t gw = t / 32;
+        const unsigned r_reo = __reduce_add_sync(0xffffffffu, pr.reo), r_tie = __reduce_add_sync(0xffffffffu, pr.tie),
+                       r_scan = __reduce_add_sync(0xffffffffu, pr.scan), r_small = __reduce_add_sync(0xffffffffu, pr.small),
+                       r_nt = __reduce_add_sync(0xffffffffu, pr.nontriv), r_st = __reduce_add_sync(0xffffffffu, pr.stores),
+                       r_cold = __reduce_add_sync(0xffffffffu, pr_cold), r_reb = __reduce_add_sync(0xffffffffu, pr_reb);
+        const unsigned r_mx = __reduce_max_sync(0xffffffffu, pr.nontriv);
+        if (lane == 0 && gw < TPI_PROF_WARPS) {
+            unsigned long long* r = g_tpi_prof + gw * TPI_PROF_REC;
+            r[0] = (unsigned long long)(pr_t1 - pr_t0);
+            r[1] = (unsigned long long)pr_t_cold;
+            r[2] = ((unsigned long long)r_reo << 32) | r_tie;
+            r[3] = ((unsigned long long)r_scan << 32) | r_small;
+            r[4] = ((unsigned long long)r_nt << 32) | r_mx;
+            r[5] = ((unsigned long long)r_cold << 32) | r_reb;
+            r[6] = r_st;
+            unsigned smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            r[7] = smid;
+        }
+    }
+#endif
     // warp-reduce the counters, one set of atomics per warp
     const unsigned full_mask = 0xffffffffu;
     unsigned hsum[8];

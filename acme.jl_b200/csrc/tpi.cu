@@ -56,3 +56,12 @@ const TpiEntry* find_tpi(const DevModel& dm) {
     return nullptr;
 }
 
+
+#ifdef ACME_TPI_PROF
+// tuning builds only: the per-warp records of the last nonlinear thread-per-instance launch (kernel_tpi.cuh)
+extern "C" int acmeb200_diag_tpi_prof(unsigned long long* out, int n_warps) {
+    if (n_warps > TPI_PROF_WARPS) n_warps = TPI_PROF_WARPS;
+    cudaDeviceSynchronize();
+    return (int)cudaMemcpyFromSymbol(out, g_tpi_prof, sizeof(unsigned long long) * TPI_PROF_REC * n_warps);
+}
+#endif

@@ -9,6 +9,8 @@ which = os.environ.get("KB_MODEL", "clipper")
 dev = torch.device("cuda", 0)
 if which == "clipper":
     m = ex.diodeclipper(); P = [bench.sweep_params(B, 0, B)]
+    if os.environ.get("KB_STIFF"):  # every warp holds the stiff corner of the sweep (k 224..255, j 0..7)
+        idx = np.arange(B); P = [bench.sweep_params(65536, 0, 65536)[:, (224 + (idx % 256) % 32) + 256 * ((idx // 256) % 8)]]
     nu = 1
 elif which == "birdie":
     m = ex.birdie(vol=0.8); P = None; nu = 1
