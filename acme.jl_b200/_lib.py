@@ -58,6 +58,7 @@ def lib():
         L.acmeb200_multi_model.restype = vp
         L.acmeb200_multi_run.argtypes = [vp, vp, i64, vp, i64, i64, u32]
         L.acmeb200_diag_exp.argtypes = [vp, vp, i64]
+        L.acmeb200_eval_jq.argtypes = [vp, C.c_int32, vp, vp]
         L.acmeb200_register_tpi.argtypes = [vp]
         L.acmeb200_set_kernel.argtypes = [vp, C.c_int32]
         L.acmeb200_kernel_name.argtypes = [vp]
@@ -84,7 +85,7 @@ EXPORTS = ["acmeb200_model_create", "acmeb200_model_destroy", "acmeb200_run", "a
            "acmeb200_get_cache_info", "acmeb200_kdtree_build", "acmeb200_kdtree_indnearest",
            "acmeb200_solver_state_size", "acmeb200_get_solver_state", "acmeb200_set_solver_state", "acmeb200_get_extrapolation_origin",
            "acmeb200_device_count", "acmeb200_set_device", "acmeb200_get_device", "acmeb200_multi_create", "acmeb200_multi_destroy",
-           "acmeb200_multi_shards", "acmeb200_multi_model", "acmeb200_multi_run", "acmeb200_diag_exp", "acmeb200_register_tpi",
+           "acmeb200_multi_shards", "acmeb200_multi_model", "acmeb200_multi_run", "acmeb200_diag_exp", "acmeb200_eval_jq", "acmeb200_register_tpi",
            "acmeb200_set_kernel", "acmeb200_kernel_name", "acmeb200_launch_count", "acmeb200_measure_fp64_peak",
            "acmeb200_last_error", "acmeb200_abi_version"]
 

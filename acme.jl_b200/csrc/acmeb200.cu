@@ -784,6 +784,53 @@ extern "C" int acmeb200_get_extrapolation_origin(acmeb200_model* m, int32_t sub,
     return rows_to(zrow, s.nn, z_host);
 }
 
+// ------------------------------------------------------------------ element Jacobians of the whole batch
+// Jq = d(res)/dq of sub-problem `sub` at one q per instance (CircuitNLFunc's Jq, circuit.jl:10-17), with the
+// instance's own element constants: what the batched linearize (ACME.jl:505-550, solvers.jl:407-414) needs at the
+// steady state, for all instances in one launch instead of one host evaluation per instance.
+__global__ void __launch_bounds__(128) k_eval_jq(const DevModel* mp, int sub, const double* consts, int64_t ld, int64_t first,
+                                                 int64_t count, const double* q_in, double* jq_out) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= count) return;
+    const DevModel& m = *mp;
+    const DevSub& s = m.subs[sub];
+    for (int k = 0; k < s.nn * s.nq; k++) jq_out[(int64_t)k * count + t] = 0.0;
+    for (int e = 0; e < s.nelem; e++) {
+        const DevElem& el = m.elems[s.elem0 + e];
+        double C[20], q[5], res[2], jv[4];
+        const int nc = elem_nc(el.kind), nq = elem_nq(el.kind), nn = elem_nn(el.kind);
+        for (int k = 0; k < nc; k++) C[k] = consts[(int64_t)(el.c_off + k) * ld + first + t];
+        for (int k = 0; k < nq; k++) q[k] = q_in[(int64_t)(el.q_off + k) * count + t];
+        elem_eval(el.kind, C, q, res, jv);
+        for (int r = 0; r < nn; r++)
+            for (int c = 0; c < nq; c++)  // column c of the element's block: the row program applied to the unit vector e_c
+                jq_out[((int64_t)(el.q_off + c) * s.nn + el.row + r) * count + t] =
+                    elem_row(el.kind, r, jv, [&](int k) { return k == c ? 1.0 : 0.0; });
+    }
+}
+
+extern "C" int acmeb200_eval_jq(acmeb200_model* m, int32_t sub, const double* q_host, double* jq_host) {
+    if (!m) return fail(ACMEB200_EINVAL, "null model");
+    if (sub < 0 || sub >= m->dm.nsub) return fail(ACMEB200_EINVAL, "sub-problem %d out of range", sub);
+    if (!q_host || !jq_host) return fail(ACMEB200_EINVAL, "null argument");
+    CUDA_TRY(cudaSetDevice(m->device));
+    const DevSub& s = m->dm.subs[sub];
+    const size_t nq = (size_t)s.nq * m->B, nj = (size_t)s.nn * s.nq * m->B;
+    double *dq = nullptr, *dj = nullptr;
+    DevModel* ddm = nullptr;
+    CUDA_TRY(cudaMalloc(&dq, sizeof(double) * std::max<size_t>(nq, 1)));
+    CUDA_TRY(cudaMalloc(&dj, sizeof(double) * std::max<size_t>(nj, 1)));
+    CUDA_TRY(cudaMalloc(&ddm, sizeof(DevModel)));
+    CUDA_TRY(cudaMemcpy(ddm, &m->dm, sizeof(DevModel), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(dq, q_host, sizeof(double) * nq, cudaMemcpyHostToDevice));
+    ACME_LAUNCH(k_eval_jq, (unsigned)((m->B + 127) / 128), 128, 0, (cudaStream_t) nullptr, ddm, (int)sub, m->d_consts, m->B, (int64_t)0,
+                m->B, dq, dj);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpy(jq_host, dj, sizeof(double) * nj, cudaMemcpyDeviceToHost));
+    cudaFree(dq); cudaFree(dj); cudaFree(ddm);
+    return ACMEB200_OK;
+}
+
 // ------------------------------------------------------------------ devices, the batch over all GPUs
 extern "C" int acmeb200_device_count(int32_t* count_out) {
     if (!count_out) return fail(ACMEB200_EINVAL, "null argument");

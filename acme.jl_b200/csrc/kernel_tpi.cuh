@@ -803,20 +803,36 @@ __device__ __forceinline__ int tpi_step_hot(const M& m, const double (&Cn)[dim1(
                     bool tie = false;
                     const int nt = kd.treen;
                     constexpr int UNR = NP <= 2 ? 8 : 4;
+                    // addresses by pointer steps (the mirror is [(leaf*np + d)*ld + instance]): the scan is 40 % of the
+                    // instructions of config 5, and a third of those were 64-bit index arithmetic
+                    const int64_t ls = cache.kd_mld;
+                    const double* mp = cache.kd_mir + (cache.kd_mshared ? 0 : inst);  // leaf l0, dimension 0
+                    auto dist_at = [&](const double* q) {
+                        double acc = 0.0;
+                        static_for<0, NP>([&](auto ii) {
+                            constexpr int i = decltype(ii)::value;
+                            const double d = p[i] - *q;
+                            q += ls;
+                            acc = i == 0 ? __dmul_rn(d, d) : __dadd_rn(acc, __dmul_rn(d, d));  // 0 + d*d = d*d exactly
+                        });
+                        return acc;
+                    };
+                    int l0 = 0;
 #pragma unroll 1
-                    for (int l0 = 0; l0 < nt; l0 += UNR) {
+                    for (; l0 + UNR <= nt; l0 += UNR) {  // full blocks
                         double d2[UNR];
 #pragma unroll
+                        for (int k = 0; k < UNR; k++) { d2[k] = dist_at(mp); mp += NP * ls; }
+#pragma unroll
                         for (int k = 0; k < UNR; k++) {
-                            const int leaf = l0 + k < nt ? l0 + k : nt - 1;
-                            double acc = 0.0;
-                            static_for<0, NP>([&](auto ii) {
-                                constexpr int i = decltype(ii)::value;
-                                const double d = p[i] - *tpi_mir<C>(cache, inst, leaf, i);
-                                acc = __dadd_rn(acc, __dmul_rn(d, d));
-                            });
-                            d2[k] = acc;
+                            tie = d2[k] < bd ? false : (d2[k] == bd ? true : tie);
+                            if (d2[k] < bd) { bd = d2[k]; bleaf = l0 + k; }
                         }
+                    }
+                    if (l0 < nt) {  // the last, partial block: surplus slots re-read the last leaf and are ignored
+                        double d2[UNR];
+#pragma unroll
+                        for (int k = 0; k < UNR; k++) { d2[k] = dist_at(mp); if (l0 + k + 1 < nt) mp += NP * ls; }
 #pragma unroll
                         for (int k = 0; k < UNR; k++)
                             if (l0 + k < nt) {

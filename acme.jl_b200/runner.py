@@ -128,6 +128,16 @@ class BatchRunner:
         check(lib().acmeb200_get_extrapolation_origin(self._h, sub, p.ctypes.data_as(C.c_void_p), z.ctypes.data_as(C.c_void_p)))
         return p, z
 
+    def eval_jq(self, sub: int, q) -> np.ndarray:
+        """Element Jacobians ``Jq`` (circuit.jl:10-17) of sub-problem `sub` at one ``q`` per instance, evaluated on the
+        device with every instance's own element parameters: ``q`` (B, nq) -> (B, nn, nq)."""
+        s = self.model.subs[sub]
+        B = self.batch
+        qh = np.ascontiguousarray(np.asarray(q, dtype=np.float64).reshape(B, s.nq).T)       # [nq][B]
+        out = np.zeros((s.nq, s.nn, B))                                                       # [nq][nn][B]
+        check(lib().acmeb200_eval_jq(self._h, sub, qh.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p)))
+        return np.ascontiguousarray(out.transpose(2, 1, 0))
+
     @property
     def device(self) -> int:
         d = C.c_int32(-1)
@@ -420,8 +430,8 @@ class BatchRunner:
         """Batched ``linearize(model, usteady)`` (ACME.jl:505-550): the small-signal linear model of
         every instance around its own steady state, as a new runner of B linear instances (which the
         linear path of the sample loop then runs at memory speed).  The steady states come from the
-        device (``_steady``); the Jacobians at those points and the chain rule through the
-        sub-problems (ACME.jl:520-546) are host work, done once per instance.  Instances that share
+        device (``_steady``), and so do the element Jacobians at those points (``eval_jq``: one launch for the
+        batch); the chain rule through the sub-problems (ACME.jl:520-546) is batched numpy.  Instances that share
         everything give a runner without per-instance matrices."""
         from dataclasses import replace
         from . import hostsolve
@@ -441,18 +451,7 @@ class BatchRunner:
             zr = slice(zoff, zoff + s.nn)
             psteady = dq @ xB + eq @ uB + fqprev @ zB                     # (B, np, 1)
             q = (q0 + pexp @ psteady + fq @ zB[:, zr])[:, :, 0]            # (B, nq)
-            par = None
-            if getattr(self, "_params", None) is not None and self._params[i] is not None:
-                par = np.asarray(self._params[i])[:, self.first:self.first + B]
-            Jq = np.empty((B, s.nn, s.nq))
-            for k in range(B):
-                table = s.elems
-                if par is not None:
-                    table, o = [], 0
-                    for e, off in s.elems:
-                        table.append((replace(e, params=tuple(par[o:o + len(e.params), k])), off))
-                        o += len(e.params)
-                Jq[k] = hostsolve.eval_table(table, q[k], s.nn)[1]
+            Jq = self.eval_jq(i, q)                                        # (B, nn, nq), one launch for the batch
             try:
                 dzdp = -np.linalg.solve(Jq @ fq, Jq @ pexp)               # solvers.jl:407-414
             except np.linalg.LinAlgError:

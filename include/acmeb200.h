@@ -280,6 +280,12 @@ int acmeb200_kdtree_indnearest(int32_t np, int32_t n_columns, int32_t n_points, 
                                int32_t n_queries, const double *queries, double best_dist, int32_t best_pidx,
                                int32_t *nearest_out);
 
+/* Element Jacobians Jq = d(res)/dq of sub-problem `sub` for the whole batch (CircuitNLFunc, src/circuit.jl:10-17, as used
+ * by linearize, src/ACME.jl:520-546 / get_extrapolation_jacobian, src/solvers.jl:407-414): q_host holds one q per instance,
+ * [nq][count] with the instance index fastest; jq_host receives [nq][nn][count] (column-major nn x nq per instance,
+ * instance index fastest).  Uses each instance's own element constants; the solver state is not touched. */
+int acmeb200_eval_jq(acmeb200_model *m, int32_t sub, const double *q_host, double *jq_host);
+
 /* diagnostic: measured FP64 FMA throughput of the current device in TFLOP/s
  * (2 flops per DFMA), the denominator of the FP64-pipe roofline in bench.py */
 int acmeb200_measure_fp64_peak(double *tflops_out);

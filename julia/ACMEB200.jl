@@ -234,6 +234,19 @@ function extrapolation_origin(r::BatchRunner; sub::Integer=1)
     return p, z
 end
 
+"""
+    eval_jq(runner, q::Matrix; sub=1) -> Array{Float64,3}       # Jq of CircuitNLFunc (src/circuit.jl:10-17), nn x nq x batch
+
+Element Jacobians of the whole batch at one `q` (nq x batch) per instance, each with its own element
+parameters: what a batched `linearize` (src/ACME.jl:520-546) needs at the steady state.
+"""
+function eval_jq(r::BatchRunner, q::Matrix{Float64}; sub::Integer=1)
+    qh = permutedims(q)                                                # [nq][batch], instance index fastest
+    out = Array{Float64,3}(undef, r.batch, nn(r.model, sub), size(q, 1))
+    check(ccall((:acmeb200_eval_jq, libacmeb200), Cint, (Ptr{Cvoid}, Int32, Ptr{Float64}, Ptr{Float64}), r.handle, sub - 1, qh, out))
+    return permutedims(out, (2, 3, 1))
+end
+
 # ---- devices: a model lives on the device that is current when it is created
 device_count() = (n = Ref{Int32}(0); check(ccall((:acmeb200_device_count, libacmeb200), Cint, (Ref{Int32},), n)); Int(n[]))
 set_device(d::Integer) = check(ccall((:acmeb200_set_device, libacmeb200), Cint, (Int32,), d))

@@ -130,3 +130,35 @@ def test_linearize_of_a_baked_sweep():
     r.steadystate_()
     assert np.abs(lr.run(u) - r.run(u)).max() < 1e-4          # runtests.jl:749's bound for this circuit
     lr.close(); r.close()
+
+
+@pytest.mark.gpu
+def test_batched_element_jacobians_match_the_host_laws():
+    """acmeb200_eval_jq: Jq of the whole batch on the device == the host restatement of the element laws
+    (circuit.jl:10-17), per instance with its own swept parameters (diodes) and for a BJT stage"""
+    from acme_jl_b200 import BatchRunner, hostsolve
+    from dataclasses import replace
+    rng = np.random.default_rng(3)
+    B = 97
+    m = ex.diodeclipper()
+    P = np.vstack([10.0 ** rng.uniform(-16, -12, B), rng.uniform(1, 2, B), 10.0 ** rng.uniform(-16, -12, B), rng.uniform(1, 2, B)])
+    r = BatchRunner(m, B, params=[P])
+    s = m.subs[0]
+    q = rng.uniform(-0.6, 0.6, (B, s.nq))
+    J = r.eval_jq(0, q)
+    assert J.shape == (B, s.nn, s.nq)
+    for k in range(B):
+        table, o = [], 0
+        for e, off in s.elems:
+            table.append((replace(e, params=tuple(P[o:o + len(e.params), k])), off)); o += len(e.params)
+        want = hostsolve.eval_table(table, q[k], s.nn)[1]
+        assert np.allclose(J[k], want, rtol=1e-12, atol=1e-300), k
+    r.close()
+    m = ex.birdie(vol=0.8)
+    r = BatchRunner(m, 5)
+    s = m.subs[0]
+    q = rng.uniform(-0.5, 0.5, (5, s.nq))
+    J = r.eval_jq(0, q)
+    for k in range(5):
+        assert np.allclose(J[k], hostsolve.eval_table(s.elems, q[k], s.nn)[1], rtol=1e-12, atol=1e-300)
+    r.close()
