@@ -948,8 +948,10 @@ __device__ __noinline__ int tpi_step_cold(const M* mp, const double* Cn_, TpiSta
     return iters;
 }
 
+// (RunArgs is a __grid_constant__ too: its address goes to the cold path, and a plain parameter would be copied to the
+// stack and read from there -- measured +2.7 % on config 2.)
 template <class C, bool PERINST, bool SMAJ>
-__global__ void __launch_bounds__(TPI_TPB, ACME_TPI_MINB) k_tpi(const __grid_constant__ TpiMats<C> Msh, const RunArgs a,
+__global__ void __launch_bounds__(TPI_TPB, ACME_TPI_MINB) k_tpi(const __grid_constant__ TpiMats<C> Msh, const __grid_constant__ RunArgs a,
                                                  const __grid_constant__ SolverCfg sc, const __grid_constant__ DevSub cache,
                                                  const __grid_constant__ TpiMaps maps) {
     constexpr int NX = C::NX, NU = C::NU, NY = C::NY, NN = C::NN, NP = C::NP;
