@@ -12,13 +12,14 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.environ.get("ACMEB200_LIB") or os.path.join(HERE, "libacmeb200.so")
-SOURCES = ["acmeb200.cu", "tpi.cu", "coop.cu", "rows.cu"]  # one translation unit per kernel family
-HEADERS = ["devmodel.h", "hostmodel.h", "tma.cuh", "elements.cuh", "kernel_generic.cuh", "kdcache.cuh", "kdcache_warp.cuh", "tpi_launch.cuh", "kernel_tpi.cuh",
+SOURCES = ["acmeb200.cu", "tpi.cu", "tpi_wide.cu", "coop.cu", "rows.cu"]  # one translation unit per kernel family
+HEADERS = ["devmodel.h", "hostmodel.h", "tma.cuh", "elements.cuh", "kernel_generic.cuh", "kdcache.cuh", "kdcache_warp.cuh", "tpi_launch.cuh", "tpi_shapes.h", "kernel_tpi.cuh",
            "kernel_coop.cuh", "kernel_rows.cuh", os.path.join("..", "..", "include", "acmeb200.h")]
 # what each translation unit includes (besides devmodel.h / hostmodel.h / acmeb200.h, which all do)
 TU_DEPS = {
     "acmeb200.cu": ["elements.cuh", "kernel_generic.cuh"],
-    "tpi.cu": ["elements.cuh", "kernel_generic.cuh", "kernel_tpi.cuh", "tma.cuh", "tpi_launch.cuh", "kdcache_warp.cuh"],
+    "tpi.cu": ["elements.cuh", "kernel_generic.cuh", "kernel_tpi.cuh", "tma.cuh", "tpi_launch.cuh", "tpi_shapes.h", "kdcache_warp.cuh"],
+    "tpi_wide.cu": ["elements.cuh", "kernel_generic.cuh", "kernel_tpi.cuh", "tma.cuh", "tpi_launch.cuh", "tpi_shapes.h", "kdcache_warp.cuh"],
     "coop.cu": ["elements.cuh", "kernel_generic.cuh", "kernel_coop.cuh", "tma.cuh"],
     "rows.cu": ["elements.cuh", "kernel_generic.cuh", "kernel_coop.cuh", "kernel_rows.cuh", "tma.cuh", "kdcache_warp.cuh"],
 }

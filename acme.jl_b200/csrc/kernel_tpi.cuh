@@ -33,7 +33,7 @@ namespace acme {
 #ifdef ACME_TPI_PROF
 #define TPI_PROF(...) __VA_ARGS__
 constexpr int TPI_PROF_WARPS = 8192, TPI_PROF_REC = 8;
-__device__ unsigned long long g_tpi_prof[TPI_PROF_WARPS * TPI_PROF_REC];
+static __device__ unsigned long long g_tpi_prof[TPI_PROF_WARPS * TPI_PROF_REC];  // one per translation unit: profile with ACMEB200_TPI_WIDE=0
 struct TpiProf { unsigned reo, tie, scan, stores, nontriv, small; };
 #else
 #define TPI_PROF(...)
@@ -598,6 +598,13 @@ __device__ __noinline__ bool tpi_cold_solve(const M* mp, TpiCold<C>* kp, const S
 #ifndef ACME_TPI_MINB
 #define ACME_TPI_MINB 8
 #endif
+// CTAs per SM of the "wide" instantiation of the non-linear kernels: a batch that needs at most this many CTAs per SM
+// runs a build compiled for 255 registers (no spills in the sample loop; the 128-register build that lets all 1024 CTAs
+// of config 2 be resident at once makes ~170 local-memory loads per sample in the BJT shapes).  Measured: birdie
+// B = 32768 +21 %, the diode clipper at B = 32768 +20 %.
+#ifndef ACME_TPI_WIDE_MINB
+#define ACME_TPI_WIDE_MINB 4
+#endif
 #ifndef ACME_TPI_T
 #define ACME_TPI_T 8
 #endif
@@ -950,8 +957,8 @@ __device__ __noinline__ int tpi_step_cold(const M* mp, const double* Cn_, TpiSta
 
 // (RunArgs is a __grid_constant__ too: its address goes to the cold path, and a plain parameter would be copied to the
 // stack and read from there -- measured +2.7 % on config 2.)
-template <class C, bool PERINST, bool SMAJ>
-__global__ void __launch_bounds__(TPI_TPB, ACME_TPI_MINB) k_tpi(const __grid_constant__ TpiMats<C> Msh, const __grid_constant__ RunArgs a,
+template <class C, bool PERINST, bool SMAJ, bool WIDE = false>
+__global__ void __launch_bounds__(TPI_TPB, WIDE ? ACME_TPI_WIDE_MINB : ACME_TPI_MINB) k_tpi(const __grid_constant__ TpiMats<C> Msh, const __grid_constant__ RunArgs a,
                                                  const __grid_constant__ SolverCfg sc, const __grid_constant__ DevSub cache,
                                                  const __grid_constant__ TpiMaps maps) {
     constexpr int NX = C::NX, NU = C::NU, NY = C::NY, NN = C::NN, NP = C::NP;

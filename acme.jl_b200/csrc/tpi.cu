@@ -7,15 +7,16 @@
 #include <deque>
 #include <vector>
 
-#include "tpi_launch.cuh"
+#include "tpi_shapes.h"
 
 using namespace acme;
 
-// shapes of the BASELINE circuits (SURVEY.md section 8 size table) + small test circuits
-using CfgDiodeClipper = TpiCfg<1, 1, 1, 1, Diode, Diode>;  // examples/diodeclipper.jl
-using CfgSallenKey = TpiCfg<2, 1, 1, 0>;                   // examples/sallenkey.jl (linear)
-using CfgBirdieFixed = TpiCfg<3, 1, 1, 2, Bjt>;            // examples/birdie.jl, vol baked in
-using CfgBirdieVol = TpiCfg<3, 2, 1, 3, Bjt, Pot>;         // examples/birdie.jl, vol as input
+#ifndef ACME_HOST_EMU
+// the 255-register build of the non-linear shapes lives in tpi_wide.cu
+#define X(CFG) extern template cudaError_t acme::launch_tpi_k<CFG, true>(const acmeb200_model*, const RunArgs&, const TpiMats<CFG>&, const SolverCfg&, const DevSub&, const TpiMaps&, int64_t, int, cudaStream_t);
+ACME_TPI_WIDE_SHAPES(X)
+#undef X
+#endif
 
 static std::deque<TpiEntry>& tpi_registry() {  // a deque: models keep pointers to entries, registration must not move them
     static std::deque<TpiEntry> reg = {

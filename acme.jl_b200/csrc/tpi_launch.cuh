@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -72,6 +73,58 @@ static bool make_tile_map(CUtensorMap* tm, const double* base, int64_t stride, i
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// attributes, carve-out and the launch of one register-budget variant (WIDE: see kernel_tpi.cuh)
+template <class C, bool WIDE>
+cudaError_t launch_tpi_k(const acmeb200_model* m, const RunArgs& a, const TpiMats<C>& M, const SolverCfg& sc, const DevSub& cache,
+                                const TpiMaps& maps, int64_t blocks, int sms, cudaStream_t stream) {
+    constexpr int MINB = WIDE ? ACME_TPI_WIDE_MINB : ACME_TPI_MINB;
+    const size_t smem = tpi_smem_bytes<C>();
+    const int dev = m->device & (ACME_MAX_DEVICES - 1);  // function attributes are per device: one process may drive several
+    if (smem > 48 * 1024) {  // long tiles: opt in to the large dynamic shared memory carve-out
+        static bool attr_set_dev[ACME_MAX_DEVICES] = {};
+        bool& attr_set = attr_set_dev[dev];
+        if (!attr_set) {
+            for (auto* k : {k_tpi<C, true, false, WIDE>, k_tpi<C, false, false, WIDE>, k_tpi<C, true, true, WIDE>, k_tpi<C, false, true, WIDE>}) {
+                const cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                if (e != cudaSuccess) return e;
+            }
+            attr_set = true;
+        }
+    }
+    {
+        // Shared-memory carve-out: only what the CTAs resident for THIS batch need, the rest of the
+        // unified array stays L1.  The learning cache's stored points are scanned from global memory
+        // every sample (config 5: 124 KB per SM); with the default maximum carve-out (200 KB) only 39 % of
+        // those loads hit L1 and the kernel waits on L2 latency (profiles/k_tpi_r1.md).
+        static int last_pct_dev[ACME_MAX_DEVICES], max_smem_dev[ACME_MAX_DEVICES] = {};
+        static bool seen_dev[ACME_MAX_DEVICES] = {};
+        int &last_pct = last_pct_dev[dev], &max_smem = max_smem_dev[dev];
+        if (!seen_dev[dev]) {
+            cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerMultiprocessor, m->device);
+            last_pct = -1;
+            seen_dev[dev] = true;
+        }
+        const int64_t resident = std::min<int64_t>(MINB, (blocks + sms - 1) / std::max(sms, 1));
+        const int64_t need = resident * (int64_t)(smem + 1024);
+        const int pct = (int)std::min<int64_t>(100, (need * 100 + max_smem - 1) / std::max(max_smem, 1));
+        if (pct != last_pct) {
+            for (auto* k : {k_tpi<C, true, false, WIDE>, k_tpi<C, false, false, WIDE>, k_tpi<C, true, true, WIDE>, k_tpi<C, false, true, WIDE>})
+                cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+            last_pct = pct;
+        }
+    }
+    if (a.smaj) {  // sample-major streams: transposed tiles (kernel_tpi.cuh)
+        if (m->blob_stride)
+            ACME_LAUNCH((k_tpi<C, true, true, WIDE>), (unsigned)blocks, TPI_TPB, smem, stream, M, a, sc, cache, maps);
+        else
+            ACME_LAUNCH((k_tpi<C, false, true, WIDE>), (unsigned)blocks, TPI_TPB, smem, stream, M, a, sc, cache, maps);
+    } else if (m->blob_stride)
+        ACME_LAUNCH((k_tpi<C, true, false, WIDE>), (unsigned)blocks, TPI_TPB, smem, stream, M, a, sc, cache, maps);
+    else
+        ACME_LAUNCH((k_tpi<C, false, false, WIDE>), (unsigned)blocks, TPI_TPB, smem, stream, M, a, sc, cache, maps);
+    return cudaGetLastError();
+}
+
 template <class C>
 static cudaError_t launch_tpi(const acmeb200_model* m, const RunArgs& a, cudaStream_t stream) {
     TpiMats<C> M;
@@ -92,50 +145,17 @@ static cudaError_t launch_tpi(const acmeb200_model* m, const RunArgs& a, cudaStr
         maps.out_ok = C::NY > 0 && make_tile_map(&maps.y, a.Y, a.y_stride, a.ninst, a.N * C::NY, TPI_T * C::NY);
     }
     const int64_t blocks = (a.ninst + TPI_TPB - 1) / TPI_TPB;
-    const size_t smem = tpi_smem_bytes<C>();
-    const int dev = m->device & (ACME_MAX_DEVICES - 1);  // function attributes are per device: one process may drive several
-    if (smem > 48 * 1024) {  // long tiles: opt in to the large dynamic shared memory carve-out
-        static bool attr_set_dev[ACME_MAX_DEVICES] = {};
-        bool& attr_set = attr_set_dev[dev];
-        if (!attr_set) {
-            for (auto* k : {k_tpi<C, true, false>, k_tpi<C, false, false>, k_tpi<C, true, true>, k_tpi<C, false, true>}) {
-                const cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-                if (e != cudaSuccess) return e;
-            }
-            attr_set = true;
-        }
+    int sms = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, m->device);
+#ifndef ACME_HOST_EMU
+    if constexpr (C::NN > 0) {  // small batches of non-linear shapes: the 255-register build (kernel_tpi.cuh, ACME_TPI_WIDE_MINB)
+        // (both stream layouts take the same build: they are bit-identical to each other, the two builds only to rounding)
+        bool wide = blocks <= (int64_t)ACME_TPI_WIDE_MINB * std::max(sms, 1);
+        if (const char* e = getenv("ACMEB200_TPI_WIDE")) wide = atoi(e) != 0;  // tests, tuning
+        if (wide) return launch_tpi_k<C, true>(m, a, M, sc, cache, maps, blocks, sms, stream);
     }
-    {
-        // Shared-memory carve-out: only what the CTAs resident for THIS batch need, the rest of the
-        // unified array stays L1.  The learning cache's stored points are scanned from global memory
-        // every sample (config 5: 124 KB per SM); with the default maximum carve-out (200 KB) only 39 % of
-        // those loads hit L1 and the kernel waits on L2 latency (profiles/k_tpi_r1.md).
-        static int last_pct_dev[ACME_MAX_DEVICES], sms_dev[ACME_MAX_DEVICES] = {}, max_smem_dev[ACME_MAX_DEVICES] = {};
-        int &last_pct = last_pct_dev[dev], &sms = sms_dev[dev], &max_smem = max_smem_dev[dev];
-        if (!sms) {
-            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, m->device);
-            cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerMultiprocessor, m->device);
-            last_pct = -1;
-        }
-        const int64_t resident = std::min<int64_t>(ACME_TPI_MINB, (blocks + sms - 1) / std::max(sms, 1));
-        const int64_t need = resident * (int64_t)(smem + 1024);
-        const int pct = (int)std::min<int64_t>(100, (need * 100 + max_smem - 1) / std::max(max_smem, 1));
-        if (pct != last_pct) {
-            for (auto* k : {k_tpi<C, true, false>, k_tpi<C, false, false>, k_tpi<C, true, true>, k_tpi<C, false, true>})
-                cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-            last_pct = pct;
-        }
-    }
-    if (a.smaj) {  // sample-major streams: transposed tiles (kernel_tpi.cuh)
-        if (m->blob_stride)
-            ACME_LAUNCH((k_tpi<C, true, true>), (unsigned)blocks, TPI_TPB, smem, stream, M, a, sc, cache, maps);
-        else
-            ACME_LAUNCH((k_tpi<C, false, true>), (unsigned)blocks, TPI_TPB, smem, stream, M, a, sc, cache, maps);
-    } else if (m->blob_stride)
-        ACME_LAUNCH((k_tpi<C, true, false>), (unsigned)blocks, TPI_TPB, smem, stream, M, a, sc, cache, maps);
-    else
-        ACME_LAUNCH((k_tpi<C, false, false>), (unsigned)blocks, TPI_TPB, smem, stream, M, a, sc, cache, maps);
-    return cudaGetLastError();
+#endif
+    return launch_tpi_k<C, false>(m, a, M, sc, cache, maps, blocks, sms, stream);
 }
 
 template <class C>

@@ -18,12 +18,17 @@ for spec in sys.argv[1:]:
     name, tpb, mb, T, st, ost, *extra = spec.split(":")
     defines = [f"-D{d}" for d in extra[0].split(",")] if extra else []
     obj = f"{libs}/tpi_{name}.o"
-    cmd = [b.nvcc()] + b.NVCC_FLAGS + [f"-DACME_TPI_TPB={tpb}", f"-DACME_TPI_MINB={mb}", f"-DACME_TPI_T={T}",
-                                      f"-DACME_TPI_STAGES={st}", f"-DACME_TPI_OSTAGES={ost}"] + defines + ["-Xptxas", "-v", "-c", "-o", obj,
-                                      os.path.join(b.CSRC, "tpi.cu")]
-    procs.append((name, obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
-for name, obj, p in procs:
+    flags = [f"-DACME_TPI_TPB={tpb}", f"-DACME_TPI_MINB={mb}", f"-DACME_TPI_T={T}", f"-DACME_TPI_STAGES={st}", f"-DACME_TPI_OSTAGES={ost}"] + defines
+    cmd = [b.nvcc()] + b.NVCC_FLAGS + flags + ["-Xptxas", "-v", "-c", "-o", obj, os.path.join(b.CSRC, "tpi.cu")]
+    wobj = f"{libs}/tpi_wide_{name}.o"  # the 255-register build of the same variant (tpi_wide.cu), compiled alongside
+    wp = subprocess.Popen([b.nvcc()] + b.NVCC_FLAGS + flags + ["-c", "-o", wobj, os.path.join(b.CSRC, "tpi_wide.cu")], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    procs.append((name, obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True), wobj, wp))
+for name, obj, p, wobj, wp in procs:
     out = p.communicate()[0]
+    wout = wp.communicate()[0]
+    if wp.returncode:
+        print(name, 'FAILED (wide)\n', wout[-1500:])
+        continue
     if p.returncode:
         print(name, "FAILED\n", out[-1500:])
         continue
@@ -32,8 +37,8 @@ for name, obj, p in procs:
         if "Compiling entry function" in l and ("Li1ELi1ELi1ELi1EJNS_5DiodeES2_EEELb0" in l or "Li2ELi1ELi1ELi0EJEEELb1" in l):
             print(name, l.split("'")[1][20:60], "|", lines[i + 2].strip()[:70], "|", lines[i + 3].strip()[:40])
     lib = f"{libs}/lib_{name}.so"
-    objs = [obj if s == "tpi.cu" else b._obj(s) for s in b.SOURCES]
+    objs = [obj if s == "tpi.cu" else (wobj if s == "tpi_wide.cu" else b._obj(s)) for s in b.SOURCES]
     r = subprocess.run([b.nvcc(), "-shared", "-cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a",
                         "-Xcompiler", "-fPIC", "-o", lib] + objs, capture_output=True, text=True)
     print(name, "->", lib if r.returncode == 0 else r.stderr[-300:])
-    os.remove(obj)
+    os.remove(obj); os.remove(wobj)
