@@ -573,10 +573,16 @@ def test_rows_kernel_state_persists_and_matches_coop(solver):
     assert st1["iter_hist"] == stc["iter_hist"] and st1["homotopy_solves"] == stc["homotopy_solves"]
 
 
-def test_rows_kernel_small_and_ragged_batches():
-    """1 instance, and a batch that does not fill the last CTA of the 4-warp variant"""
+def test_rows_kernel_small_and_ragged_batches(monkeypatch):
+    """1 instance, and a batch that does not fill the last CTA of the 4-warp variant (forced: since the 255-register
+    one-warp build became the choice at every batch size of this shape, the 4-warp build is what ACMEB200_ROWS_SMALL_MAX
+    selects), and the same batch on the automatic choice"""
     m = ex.superover()
-    for B in (1, 2371):
+    for B, small_max in ((1, None), (2371, "0"), (2371, None)):
+        if small_max is None:
+            monkeypatch.delenv("ACMEB200_ROWS_SMALL_MAX", raising=False)
+        else:
+            monkeypatch.setenv("ACMEB200_ROWS_SMALL_MAX", small_max)
         N = 400 if B > 1 else 1500
         u = superover_inputs(B, N)
         r = BatchRunner(m, B, kernel="rows", solver=H)
