@@ -69,6 +69,9 @@ class BatchRunner:
             raise ValueError("kernel must be 'auto', 'generic', 'coop' or 'rows'")
 
     def close(self):
+        for r in getattr(self, "_steady_runners", {}).values():
+            r.close()
+        self._steady_runners = {}
         if getattr(self, "_h", None):
             lib().acmeb200_model_destroy(self._h)
             self._h = None
@@ -404,14 +407,18 @@ class BatchRunner:
             sov = None
             if bk > 1:  # per-instance matrices: the derived model has per-instance eq / fq
                 sov = {"eq0": np.asfortranarray(np.moveaxis(eq_d, 0, -1)), "fq0": np.asfortranarray(np.moveaxis(fq_d, 0, -1))}
-            r = BatchRunner(sm, B, params=params, overrides=sov, tol=1e-15)
-            try:
-                uin = np.asfortranarray(np.vstack([u, steady_z, np.ones((1, B))]).reshape(nin, 1, B))
-                z = r.run(uin, check_status=False)[:, 0, :]
-                if (r.status()[0] != 0).any():
-                    raise RuntimeError("Failed to find steady state solution")  # ACME.jl:492
-            finally:
-                r.close()
+            # the derived model does not depend on u: one device model per sub-problem for the life of this runner, reset
+            # before every use (the reference builds a fresh solver per call, ACME.jl:481-485)
+            cache = self.__dict__.setdefault("_steady_runners", {})
+            r = cache.get(i)
+            if r is None:
+                r = cache[i] = BatchRunner(sm, B, params=params, overrides=sov, tol=1e-15)
+            else:
+                r.reset()
+            uin = np.asfortranarray(np.vstack([u, steady_z, np.ones((1, B))]).reshape(nin, 1, B))
+            z = r.run(uin, check_status=False)[:, 0, :]
+            if (r.status()[0] != 0).any():
+                raise RuntimeError("Failed to find steady state solution")  # ACME.jl:492
             steady_z[zoff:zoff + s.nn] = z
             zoff += s.nn
         if not m.nx:

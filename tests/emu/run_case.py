@@ -63,8 +63,10 @@ elif case == "steady":
     # batched steadystate (ACME.jl:474-497) through the ABI: shared matrices, per-instance matrices of a non-linear
     # model (derived zero-state model with per-instance eq/fq), per-instance matrices of a linear model
     m = ex.birdie(vol=0.8)
-    r = BatchRunner(m, 3); xs = r.steadystate(np.array([[0.0, 0.1, 0.3]])); r.close()
+    r = BatchRunner(m, 3); xs = r.steadystate(np.array([[0.0, 0.1, 0.3]]))
+    xs2 = r.steadystate(np.array([[0.3, 0.0, -0.2]])); r.close()   # second call: the derived device model is reused (reset)
     out["shared"] = max(float(np.abs(xs[:, b] - m.steadystate([uv])).max()) for b, uv in enumerate([0.0, 0.1, 0.3]))
+    out["reuse"] = max(float(np.abs(xs2[:, b] - m.steadystate([uv])).max()) for b, uv in enumerate([0.3, 0.0, -0.2]))
     pts = [(0.2, 0.5), (0.7, 0.4), (0.45, 0.9)]
     base, kw, B = A.derive_sweep(lambda d, t: ex.superover(d, t, 1.0), pts, workers=1)
     r = BatchRunner(base, B, **kw); xs = r.steadystate_(np.array([[0.0, 0.05, -0.02]]))

@@ -64,6 +64,7 @@ def test_batched_steadystate_with_per_instance_matrices(emu_lib):
     emulated library): equals each instance's own host-side steadystate, and the instances stay there"""
     out = run_case(emu_lib, "steady")
     assert out["shared"] < 1e-10 and out["perinst"] < 1e-10 and out["linear"] < 1e-10
+    assert out["reuse"] < 1e-10          # a second call on the same runner reuses (and resets) the derived device model
     assert out["drift"] < 1e-9          # checksteady! (runtests.jl:664-682) compares the state
     assert out["y_span"] < 1e-4          # the output only up to the Newton stopping rule (res < 1e-10 A at high-impedance nodes)
 
