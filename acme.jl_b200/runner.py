@@ -440,8 +440,6 @@ class BatchRunner:
         device (``_steady``), and so do the element Jacobians at those points (``eval_jq``: one launch for the
         batch); the chain rule through the sub-problems (ACME.jl:520-546) is batched numpy.  Instances that share
         everything give a runner without per-instance matrices."""
-        from dataclasses import replace
-        from . import hostsolve
         from .model import DiscreteModel
         m, B = self.model, self.batch
         xs, zs, u = self._steady(usteady)
